@@ -55,7 +55,10 @@ class FixSnapshot : public Fix {
       if (strcmp(arg[i], "pairs") == 0) with_pairs = 1;
   }
   int setmask() { return FixConst::END_OF_STEP; }
-  void setup(int) { write(); }
+  void setup(int) {
+    write_meta();
+    write();
+  }
   void end_of_step() { write(); }
 
  private:
@@ -94,6 +97,21 @@ class FixSnapshot : public Fix {
       int32_t v = a[order[k]];
       fwrite(&v, 4, 1, fp);
     }
+  }
+
+  // text sidecar: neighbour settings, pair style and (id, style, groupbit) of every fix, so the
+  // fixture generator need not guess group bit assignments
+  void write_meta() {
+    std::string fn = prefix + ".meta.txt";
+    FILE *fp = fopen(fn.c_str(), "w");
+    if (!fp) error->one(FLERR, "cannot open snapshot meta file");
+    fprintf(fp, "neighbor %.17g %d %d %d\n", neighbor->skin, neighbor->every, neighbor->delay,
+            neighbor->dist_check);
+    fprintf(fp, "cutneighmax %.17g\n", neighbor->cutneighmax);
+    fprintf(fp, "pair_style %s\n", force->pair_style ? force->pair_style : "none");
+    for (int i = 0; i < modify->nfix; i++)
+      fprintf(fp, "fix %s %s %d\n", modify->fix[i]->id, modify->fix[i]->style, modify->fix[i]->groupbit);
+    fclose(fp);
   }
 
   void write() {
