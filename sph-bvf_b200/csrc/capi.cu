@@ -1,0 +1,794 @@
+// capi.cu -- the extern "C" layer of include/sphbvf.h: context, device memory, and the
+// timestep driver that sequences the kernels in the order Verlet::setup / Verlet::run call the
+// reference's styles (verlet.cpp:88-170, 223-354).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "sphbvf_internal.cuh"
+#include "context.cuh"
+
+using namespace sphbvf;
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+int sphbvf_ctx::fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return ctx->fail(SPHBVF_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define CKLAUNCH() CK(cudaGetLastError())
+
+template <typename T>
+static cudaError_t dev_realloc(T *&p, size_t old_n, size_t new_n, cudaStream_t st, bool keep, bool zero) {
+  T *q = nullptr;
+  if (new_n == 0) new_n = 1;
+  cudaError_t e = cudaMalloc((void **)&q, new_n * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (zero) cudaMemsetAsync(q, 0, new_n * sizeof(T), st);
+  if (p && keep && old_n) cudaMemcpyAsync(q, p, std::min(old_n, new_n) * sizeof(T), cudaMemcpyDeviceToDevice, st);
+  if (p) {
+    cudaStreamSynchronize(st);
+    cudaFree(p);
+  }
+  p = q;
+  return cudaSuccess;
+}
+
+void sphbvf_ctx::tic(int fam, int nlaunch) {
+  launches_fam[fam] += nlaunch;
+  if (!profiling) return;
+  cudaEvent_t a, b;
+  if (ev_pool.size() >= 2) {
+    a = ev_pool.back(); ev_pool.pop_back();
+    b = ev_pool.back(); ev_pool.pop_back();
+  } else {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+  }
+  cudaEventRecord(a, st);
+  ev_open = {fam, a, b};
+}
+
+void sphbvf_ctx::toc() {
+  if (!profiling) return;
+  cudaEventRecord(ev_open.b, st);
+  ev_list.push_back(ev_open);
+}
+
+void sphbvf_ctx::drain_events() {
+  for (auto &e : ev_list) {
+    float ms = 0.f;
+    cudaEventSynchronize(e.b);
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    ms_fam[e.fam] += ms;
+    ev_pool.push_back(e.a);
+    ev_pool.push_back(e.b);
+  }
+  ev_list.clear();
+}
+
+static int ensure_scan(sphbvf_ctx *ctx, long n) {
+  const long need = n / 1024 + 8192;
+  if (need <= ctx->scan_cap) return 0;
+  if (ctx->w.scan_tmp) cudaFree(ctx->w.scan_tmp);
+  ctx->w.scan_tmp = nullptr;
+  CK(cudaMalloc((void **)&ctx->w.scan_tmp, sizeof(int) * need));
+  ctx->scan_cap = need;
+  return 0;
+}
+
+// ensure capacity for `nmax` owned atoms and `nallmax` owned+ghost atoms
+static int ensure_capacity(sphbvf_ctx *ctx, int nmax, int nallmax) {
+  DevState &d = ctx->d;
+  const int S = ctx->co.nspecies > 0 ? ctx->co.nspecies : 1;
+  cudaStream_t st = ctx->st;
+  if (nmax > d.nmax) {
+    const size_t o = d.nmax, n = nmax;
+#define RE(p, w, keep) CK(dev_realloc(p, o *(w), n *(w), st, keep, true))
+    RE(d.tag, 1, true); RE(d.type, 1, true); RE(d.mask, 1, true); RE(d.solid, 1, true); RE(d.fixed, 1, true); RE(d.slot, 1, true);
+    RE(d.x, 3, true); RE(d.v, 3, true); RE(d.vest, 3, true); RE(d.rho, 1, true); RE(d.rhoI, 1, true); RE(d.e, 1, true);
+    RE(d.C, S, true); RE(d.dev, 9, true);
+    RE(d.f, 3, true); RE(d.nw, 3, true); RE(d.ddv, 3, true); RE(d.ddx, 3, true); RE(d.drho, 1, true); RE(d.phi, 1, true);
+    RE(d.nd, 1, true); RE(d.rhoAux1, 1, true); RE(d.rhoAux2, 1, true); RE(d.Pnew, 1, true); RE(d.ddev, 9, true); RE(d.Q, S, true);
+    RE(d.xhold, 3, true); RE(d.numneigh, 1, true);
+    RE(ctx->w.perm, 1, false);
+#undef RE
+    CK(dev_realloc(ctx->w.nimg, 0, n + 1, st, false, true));   // nmax+1 entries (scan sentinel)
+    { int rc_ = ensure_scan(ctx, (long)n + 2); if (rc_) return rc_; }
+    if ((size_t)9 * n * sizeof(double) > ctx->w.tmp_perm_bytes) {
+      if (ctx->w.tmp_perm) cudaFree(ctx->w.tmp_perm);
+      ctx->w.tmp_perm_bytes = (size_t)9 * n * sizeof(double);
+      CK(cudaMalloc(&ctx->w.tmp_perm, ctx->w.tmp_perm_bytes));
+    }
+    // neighbour list storage is tied to the stride = nmax
+    if (d.maxneigh > 0) {
+      if (d.neigh) cudaFree(d.neigh);
+      d.neigh = nullptr;
+      CK(cudaMalloc((void **)&d.neigh, sizeof(int) * (size_t)d.maxneigh * n));
+    }
+    d.stride = nmax;
+    d.nmax = nmax;
+  }
+  if (nallmax > d.nallmax) {
+    const size_t o = d.nallmax, n = nallmax;
+#define RE(p, w) CK(dev_realloc(p, o *(w), n *(w), st, true, true))
+    RE(d.pA, 1); RE(d.pB, 1); RE(d.pC, 1); RE(d.pD, 1); RE(d.pCs, S); RE(d.pdev, 9); RE(d.pflags, 1); RE(d.ptag, 1);
+    RE(d.gowner, 1); RE(d.gshift, 3); RE(ctx->w.cellid, 1); RE(ctx->w.gorder, 1);
+#undef RE
+    d.nallmax = nallmax;
+  }
+  return 0;
+}
+
+static int ensure_cells(sphbvf_ctx *ctx, long ncells) {
+  NeighWork &w = ctx->w;
+  if (ncells + 1 <= w.ncells_cap) return 0;
+  const long cap = ncells + 1 + ncells / 8;
+  for (int **p : {&w.cell_count, &w.cell_start, &w.gcell_count, &w.gcell_start}) {
+    if (*p) cudaFree(*p);
+    CK(cudaMalloc((void **)p, sizeof(int) * cap));
+  }
+  w.ncells_cap = cap;
+  return ensure_scan(ctx, cap);
+}
+
+static int ensure_neigh(sphbvf_ctx *ctx, int maxneigh) {
+  DevState &d = ctx->d;
+  if (maxneigh <= d.maxneigh && d.neigh) return 0;
+  if (d.neigh) cudaFree(d.neigh);
+  d.neigh = nullptr;
+  d.maxneigh = maxneigh;
+  CK(cudaMalloc((void **)&d.neigh, sizeof(int) * (size_t)d.maxneigh * d.stride));
+  return 0;
+}
+
+// Neighbor::init cutoffs (neighbor.cpp:278-310) + the cell grid (nbin_standard.cpp:53-186)
+static int init_neighbor(sphbvf_ctx *ctx) {
+  Coeffs &co = ctx->co;
+  const double skin = ctx->cfg.skin;
+  ctx->triggersq = 0.25 * skin * skin;
+  ctx->cutneighmax = 0.0;
+  for (int i = 1; i <= co.ntypes; i++)
+    for (int j = 1; j <= co.ntypes; j++) {
+      if (!ctx->pairset[i][j]) return ctx->fail(SPHBVF_EINVAL, "Not all pair ssa_tsdpd/bvf coeffs are set");
+      const double cutoff = sqrt(co.cutsq[i][j]);
+      const double delta = cutoff > 0.0 ? skin : 0.0;
+      const double cut = cutoff + delta;
+      co.cutneighsq[i][j] = cut * cut;
+      ctx->cutneighmax = std::max(ctx->cutneighmax, cut);
+    }
+  if (ctx->cutneighmax <= 0.0) return ctx->fail(SPHBVF_EINVAL, "all pair cutoffs are zero");
+  Grid &g = ctx->grid;
+  const Box &b = ctx->box;
+  const double binsize = 0.5 * ctx->cutneighmax;
+  g.ncells = 1;
+  g.dim = b.dim;
+  for (int k = 0; k < 3; k++) {
+    if (b.dim == 2 && k == 2) {
+      g.lo[k] = b.sublo[k];
+      g.n[k] = 1;
+      g.inv[k] = 1.0 / std::max(b.subhi[k] - b.sublo[k], 1e-300);
+      g.s[k] = 0;
+      continue;
+    }
+    const double lo = b.sublo[k] - ctx->cutneighmax, hi = b.subhi[k] + ctx->cutneighmax;
+    int n = (int)((hi - lo) / binsize);
+    if (n < 1) n = 1;
+    const double size = (hi - lo) / n;
+    g.lo[k] = lo;
+    g.n[k] = n;
+    g.inv[k] = 1.0 / size;
+    int s = (int)(ctx->cutneighmax * g.inv[k]);
+    if (s * size < ctx->cutneighmax) s++;
+    g.s[k] = s;
+    g.ncells *= n;
+  }
+  if (g.ncells > 2000000000L) return ctx->fail(SPHBVF_EINVAL, "Too many neighbor bins");
+  return ensure_cells(ctx, g.ncells);
+}
+
+static int fetch_flags(sphbvf_ctx *ctx) {
+  CK(cudaMemcpyAsync(ctx->h_flags, ctx->w.flags, sizeof(int) * 8, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
+// pbc + (migration) + sort + ghosts + Verlet list: the rebuild branch of verlet.cpp:268-296
+static int rebuild(sphbvf_ctx *ctx) {
+  DevState &d = ctx->d;
+  NeighWork &w = ctx->w;
+  cudaStream_t st = ctx->st;
+  const Coeffs &co = ctx->co;
+  int rc;
+  ctx->tic(K_NEIGH, 40);
+  CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * 8, st));
+  launch_cell_ids(d, ctx->grid, ctx->box, w, st);
+  launch_sort_owned(d, ctx->grid, w, st);
+  const int n = d.nlocal, S = co.nspecies;
+  launch_permute(d.x, w.tmp_perm, w.perm, n, 3, 8, st);
+  launch_permute(d.v, w.tmp_perm, w.perm, n, 3, 8, st);
+  launch_permute(d.vest, w.tmp_perm, w.perm, n, 3, 8, st);
+  launch_permute(d.rho, w.tmp_perm, w.perm, n, 1, 8, st);
+  launch_permute(d.rhoI, w.tmp_perm, w.perm, n, 1, 8, st);
+  launch_permute(d.e, w.tmp_perm, w.perm, n, 1, 8, st);
+  if (S) launch_permute(d.C, w.tmp_perm, w.perm, n, S, 8, st);
+  if (ctx->with_dev) launch_permute(d.dev, w.tmp_perm, w.perm, n, 9, 8, st);
+  for (int *p : {d.tag, d.type, d.mask, d.solid, d.fixed, d.slot}) launch_permute(p, w.tmp_perm, w.perm, n, 1, 4, st);
+  CKLAUNCH();
+
+  // ghosts: periodic self images (single rank per periodic dimension)
+  launch_count_images(d, ctx->box, ctx->cutneighmax, w, st);
+  int nghost = 0;
+  CK(cudaMemcpyAsync(&ctx->h_flags[8], w.nimg + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if ((rc = fetch_flags(ctx))) return rc;
+  nghost = ctx->h_flags[8];
+  if (ctx->h_flags[0]) return ctx->fail(SPHBVF_ENONFINITE, "Non-numeric positions - simulation unstable");
+  if (ctx->h_flags[1]) return ctx->fail(SPHBVF_ELOST, "Lost atoms: an owned atom left the non-periodic box");
+  if (d.nlocal + nghost > d.nallmax)
+    if ((rc = ensure_capacity(ctx, d.nmax, d.nlocal + nghost + nghost / 4 + 1024))) return rc;
+  d.nghost = nghost;
+  launch_fill_images(d, ctx->box, ctx->cutneighmax, w, st);
+  CK(cudaMemcpyAsync(d.ptag, d.tag, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
+  launch_pack(d, co, ctx->with_dev, st);
+  launch_ghost_refresh(d, co, ctx->with_dev, st);
+  launch_bin_ghosts(d, ctx->grid, w, st);
+  CKLAUNCH();
+
+  for (int attempt = 0; attempt < 3; attempt++) {
+    if (d.maxneigh == 0) {
+      // first guess from the number density: neighbours within cutneighmax of a uniform fluid
+      const Box &b = ctx->box;
+      double vol = 1.0;
+      for (int k = 0; k < b.dim; k++) vol *= (b.subhi[k] - b.sublo[k]);
+      const double dens = d.nlocal / std::max(vol, 1e-300);
+      const double sph = b.dim == 3 ? 4.18879 * pow(ctx->cutneighmax, 3) : 3.14159 * pow(ctx->cutneighmax, 2);
+      if ((rc = ensure_neigh(ctx, std::max(16, (int)(1.3 * dens * sph) + 8)))) return rc;
+    }
+    CK(cudaMemsetAsync(w.flags + 2, 0, sizeof(int), st));
+    launch_build_list(d, ctx->grid, co, w, st);
+    CKLAUNCH();
+    if ((rc = fetch_flags(ctx))) return rc;
+    if (ctx->h_flags[2] <= d.maxneigh) break;
+    if (attempt == 2) return ctx->fail(SPHBVF_EOVERFLOW, "Neighbor list overflow");
+    if ((rc = ensure_neigh(ctx, ctx->h_flags[2] + ctx->h_flags[2] / 8 + 4))) return rc;
+  }
+  ctx->maxneigh_seen = ctx->h_flags[2];
+  launch_copy_xhold(d, st);
+  ctx->toc();
+  ctx->ago = 0;
+  ctx->nbuilds++;
+  return 0;
+}
+
+static PairFlags pair_flags(const sphbvf_ctx *ctx) {
+  PairFlags pf;
+  const int var = ctx->co.variant;
+  pf.filter_step = var == SPHBVF_FSI ? 0 : (ctx->ntimestep % 20) == 0;
+  pf.with_dev = ctx->with_dev;
+  pf.any_solid = ctx->any_solid;
+  // density diffusion of the fsi pair style: amplDamp = 0.1 while ntimestep*dt <= dt*nsteps
+  // (pair_ssa_tsdpd_bvf_fsi.cpp:531-539)
+  const double tnow = ctx->ntimestep * ctx->cfg.dt, tmax = ctx->cfg.dt * ctx->run_nsteps;
+  pf.damp = (var == SPHBVF_FSI && tnow <= tmax) ? 0.1 : 0.0;
+  return pf;
+}
+
+template <typename T>
+__global__ void scatter_rows_kernel(const T *in, T *out, const int *slot, int n, int ncols, int to_slot) {
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long)n * ncols) return;
+  const int row = (int)(q / ncols), col = (int)(q - (long)row * ncols);
+  const long s = (long)slot[row] * ncols + col;
+  if (to_slot) out[s] = in[q];   // device order -> host slot order
+  else out[q] = in[s];           // host slot order -> device order
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int sphbvf_version(void) { return SPHBVF_VERSION; }
+
+int sphbvf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int sphbvf_create(const sphbvf_config *cfg, sphbvf_ctx **out) {
+  if (!cfg || !out) return SPHBVF_EINVAL;
+  *out = nullptr;
+  if (cfg->ntypes < 1 || cfg->ntypes + 1 > MAXT || cfg->nspecies < 0 || cfg->nspecies > MAXS ||
+      (cfg->dim != 2 && cfg->dim != 3) || cfg->variant < 0 || cfg->variant > 2)
+    return SPHBVF_EINVAL;
+  if (sphbvf_device_count() <= cfg->device) return SPHBVF_ECUDA;   // no GPU: fail loudly, no fallback
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return SPHBVF_ECUDA;
+  sphbvf_ctx *ctx = new sphbvf_ctx();
+  ctx->cfg = *cfg;
+  if (ctx->cfg.nranks < 1) { ctx->cfg.nranks = 1; ctx->cfg.rank = 0; }
+  for (int k = 0; k < 3; k++) if (ctx->cfg.procgrid[k] < 1) ctx->cfg.procgrid[k] = 1;
+  if (ctx->cfg.neigh_every < 1) ctx->cfg.neigh_every = 1;
+  memset(&ctx->co, 0, sizeof ctx->co);
+  ctx->co.dim = cfg->dim;
+  ctx->co.variant = cfg->variant;
+  ctx->co.nspecies = cfg->nspecies;
+  ctx->co.ntypes = cfg->ntypes;
+  Box &b = ctx->box;
+  b.dim = cfg->dim;
+  for (int k = 0; k < 3; k++) {
+    b.lo[k] = cfg->boxlo[k];
+    b.hi[k] = cfg->boxhi[k];
+    b.prd[k] = cfg->boxhi[k] - cfg->boxlo[k];
+    b.periodic[k] = cfg->periodic[k];
+  }
+  sphbvf_brick_bounds(&ctx->cfg, ctx->cfg.rank, b.sublo, b.subhi);
+  if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost((void **)&ctx->h_flags, sizeof(int) * 16) != cudaSuccess ||
+      cudaMalloc((void **)&ctx->w.flags, sizeof(int) * 8) != cudaSuccess) {
+    delete ctx;
+    return SPHBVF_ECUDA;
+  }
+  cudaMemset(ctx->w.flags, 0, sizeof(int) * 8);
+  ctx->run_nsteps_user = -1;
+  *out = ctx;
+  return 0;
+}
+
+void sphbvf_destroy(sphbvf_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  cudaStreamSynchronize(ctx->st);
+  ctx->drain_events();
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  comm_destroy(ctx);
+  DevState &d = ctx->d;
+  void *ptrs[] = {d.tag, d.type, d.mask, d.solid, d.fixed, d.slot, d.x, d.v, d.vest, d.rho, d.rhoI, d.e, d.C, d.dev,
+                  d.f, d.nw, d.ddv, d.ddx, d.drho, d.phi, d.nd, d.rhoAux1, d.rhoAux2, d.Pnew, d.ddev, d.Q,
+                  d.pA, d.pB, d.pC, d.pD, d.pCs, d.pdev, d.pflags, d.ptag, d.xhold, d.gowner, d.gshift, d.neigh,
+                  d.numneigh, ctx->w.cellid, ctx->w.perm, ctx->w.cell_count, ctx->w.cell_start, ctx->w.gcell_count,
+                  ctx->w.gcell_start, ctx->w.gorder, ctx->w.scan_tmp, ctx->w.nimg, ctx->w.flags, ctx->w.tmp_perm};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  cudaStreamDestroy(ctx->st);
+  delete ctx;
+}
+
+const char *sphbvf_last_error(const sphbvf_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int sphbvf_set_type(sphbvf_ctx *ctx, int t, double mass, double rho0, double c0, double G0) {
+  if (t < 1 || t > ctx->co.ntypes) return ctx->fail(SPHBVF_EINVAL, "type %d out of range", t);
+  Coeffs &co = ctx->co;
+  co.mass[t] = mass;
+  co.rho0[t] = rho0;
+  co.c0[t] = c0;
+  co.B[t] = c0 * c0 * rho0 / 7.0;   // pair_...transport_velocity.cpp:981
+  co.G0[t] = G0;
+  return 0;
+}
+
+int sphbvf_set_pair(sphbvf_ctx *ctx, int i, int j, double eta, double h, double cutc, const double *kappa) {
+  Coeffs &co = ctx->co;
+  if (i < 1 || j < 1 || i > co.ntypes || j > co.ntypes) return ctx->fail(SPHBVF_EINVAL, "type pair %d %d out of range", i, j);
+  const int a[2] = {i, j}, b[2] = {j, i};
+  for (int s = 0; s < 2; s++) {   // init_one mirrors (pair_...:1040-1050); cutsq = cut*cut (pair.cpp:245)
+    co.eta[a[s]][b[s]] = eta;
+    co.cut[a[s]][b[s]] = h;
+    co.cutsq[a[s]][b[s]] = h * h;
+    co.cutc[a[s]][b[s]] = cutc;
+    for (int k = 0; k < co.nspecies; k++) co.kappa[a[s]][b[s]][k] = kappa ? kappa[k] : 0.0;
+    ctx->pairset[a[s]][b[s]] = 1;
+  }
+  return 0;
+}
+
+int sphbvf_set_dt(sphbvf_ctx *ctx, double dt) { ctx->cfg.dt = dt; return 0; }
+int sphbvf_set_timestep(sphbvf_ctx *ctx, long n) { ctx->ntimestep = n; return 0; }
+int sphbvf_set_run_length(sphbvf_ctx *ctx, long n) { ctx->run_nsteps_user = n; ctx->run_nsteps = n; return 0; }
+
+int sphbvf_set_atoms(sphbvf_ctx *ctx, int n, const int *tag, const int *type, const int *mask, const int *solid,
+                     const int *fixed, const double *x, const double *v, const double *rho, const double *e,
+                     const double *C, const double *dev) {
+  if (n < 0 || !tag || !type || !solid || !fixed || !x || !rho) return ctx->fail(SPHBVF_EINVAL, "set_atoms: null array");
+  if (n >= NEIGH_JMASK / 2) return ctx->fail(SPHBVF_EINVAL, "too many atoms for one GPU");
+  cudaSetDevice(ctx->cfg.device);
+  int rc;
+  if ((rc = ensure_capacity(ctx, n + n / 8 + 1024, n + n / 4 + 4096))) return rc;
+  DevState &d = ctx->d;
+  cudaStream_t st = ctx->st;
+  const int S = ctx->co.nspecies;
+  d.nlocal = n;
+  d.nghost = 0;
+  for (int i = 0; i < n; i++)
+    if (type[i] < 1 || type[i] > ctx->co.ntypes) return ctx->fail(SPHBVF_EINVAL, "atom %d has type %d out of range", i, type[i]);
+  ctx->any_solid = 0;
+  int has_dev = 0;
+  for (int i = 0; i < n; i++) {
+    if (solid[i]) {
+      ctx->any_solid = 1;
+      if (ctx->co.G0[type[i]] != 0.0) has_dev = 1;
+    }
+  }
+  if (dev)
+    for (size_t q = 0; q < (size_t)9 * n && !has_dev; q++) if (dev[q] != 0.0) has_dev = 1;
+  ctx->with_dev = has_dev;
+#define UP(dst, src, cnt, T)                                                                         \
+  do {                                                                                               \
+    if (src) CK(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)(cnt), cudaMemcpyHostToDevice, st));   \
+    else CK(cudaMemsetAsync(dst, 0, sizeof(T) * (size_t)(cnt), st));                                 \
+  } while (0)
+  UP(d.tag, tag, n, int); UP(d.type, type, n, int); UP(d.solid, solid, n, int); UP(d.fixed, fixed, n, int);
+  UP(d.x, x, 3 * (size_t)n, double); UP(d.v, v, 3 * (size_t)n, double); UP(d.rho, rho, n, double); UP(d.e, e, n, double);
+  if (S) UP(d.C, C, (size_t)S * n, double);
+  UP(d.dev, dev, 9 * (size_t)n, double);
+#undef UP
+  std::vector<int> iota(n), ones;
+  for (int i = 0; i < n; i++) iota[i] = i;
+  CK(cudaMemcpyAsync(d.slot, iota.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  if (mask) CK(cudaMemcpyAsync(d.mask, mask, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  else {
+    ones.assign(n, 1);
+    CK(cudaMemcpyAsync(d.mask, ones.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  }
+  // create_atom defaults (atom_vec_ssa_tsdpd_atomic.cpp:1873-1936): vest = 0, rhoI = 0, outputs 0
+  CK(cudaMemsetAsync(d.vest, 0, sizeof(double) * 3 * n, st));
+  CK(cudaMemsetAsync(d.rhoI, 0, sizeof(double) * n, st));
+  for (double *p : {d.f, d.nw, d.ddv, d.ddx}) CK(cudaMemsetAsync(p, 0, sizeof(double) * 3 * n, st));
+  for (double *p : {d.drho, d.phi, d.nd, d.rhoAux1, d.rhoAux2, d.Pnew}) CK(cudaMemsetAsync(p, 0, sizeof(double) * n, st));
+  CK(cudaMemsetAsync(d.ddev, 0, sizeof(double) * 9 * n, st));
+  CK(cudaMemsetAsync(d.Q, 0, sizeof(double) * (S ? S : 1) * n, st));
+  CK(cudaStreamSynchronize(st));
+  ctx->e_nonzero = 0;
+  if (e) for (int i = 0; i < n; i++) if (e[i] != 0.0) { ctx->e_nonzero = 1; break; }
+  ctx->atoms_set = 1;
+  ctx->setup_done = 0;
+  ctx->migrated = 0;
+  return 0;
+}
+
+static int add_fix(sphbvf_ctx *ctx, const FixDesc &f) {
+  if (ctx->nfix == MAXFIX) return ctx->fail(SPHBVF_EINVAL, "too many fixes");
+  ctx->fixes[ctx->nfix++] = f;
+  return 0;
+}
+int sphbvf_add_buoyancy(sphbvf_ctx *ctx, int groupbit, int gravity, double accel, int coord, int k, double Cref) {
+  if (coord < 0 || coord > 2 || (!gravity && (k < 0 || k >= ctx->co.nspecies)))
+    return ctx->fail(SPHBVF_EINVAL, "Illegal fix ssa_tsdpd/buoyancy command");
+  FixDesc f = {FIX_BUOYANCY, groupbit, {gravity, coord, k, 0}, 0, {accel, Cref, 0, 0, 0, 0}};
+  return add_fix(ctx, f);
+}
+int sphbvf_add_forcing(sphbvf_ctx *ctx, int groupbit, int kind, long step, int idx, int shape, double cx, double cy,
+                       double a, double b, double value) {
+  if ((kind == 0 && (idx < 0 || idx >= ctx->co.nspecies)) || (kind == 1 && (idx < 0 || idx > 2)) || kind < 0 || kind > 1)
+    return ctx->fail(SPHBVF_EINVAL, "Illegal fix ssa_tsdpd_forcing command");
+  FixDesc f = {FIX_FORCING, groupbit, {kind, idx, shape, 0}, step, {cx, cy, a, b, value, 0}};
+  return add_fix(ctx, f);
+}
+int sphbvf_add_buffer(sphbvf_ctx *ctx, int groupbit, int kind, int axis, long step, int idx, double cx, double cy,
+                      double length, double width, double value) {
+  if ((kind == 0 && (idx < 0 || idx >= ctx->co.nspecies)) || (kind == 1 && (idx < 0 || idx > 2)) || kind < 0 || kind > 2)
+    return ctx->fail(SPHBVF_EINVAL, "Illegal fix ssa_tsdpd_buffer command");
+  FixDesc f = {FIX_BUFFER, groupbit, {kind, idx, axis, 0}, step, {cx, cy, length, width, value, 0}};
+  return add_fix(ctx, f);
+}
+int sphbvf_add_setforce(sphbvf_ctx *ctx, int groupbit, double fx, double fy, double fz) {
+  FixDesc f = {FIX_SETFORCE, groupbit, {0, 0, 0, 0}, 0, {fx, fy, fz, 0, 0, 0}};
+  return add_fix(ctx, f);
+}
+
+static int run_fixes(sphbvf_ctx *ctx, int hook) {
+  bool any = false;
+  for (int q = 0; q < ctx->nfix; q++) {
+    if (!any) { ctx->tic(K_FIX, 0); any = true; }
+    ctx->launches_fam[K_FIX]++;
+    launch_fix(ctx->d, ctx->co, ctx->fixes[q], hook, ctx->ntimestep, ctx->st);
+  }
+  if (any) { ctx->toc(); CKLAUNCH(); }
+  return 0;
+}
+
+int sphbvf_build_neighbors(sphbvf_ctx *ctx) {
+  if (!ctx->atoms_set) return ctx->fail(SPHBVF_ESTATE, "build_neighbors before set_atoms");
+  cudaSetDevice(ctx->cfg.device);
+  int rc;
+  if ((rc = init_neighbor(ctx))) return rc;
+  if (ctx->cfg.nranks > 1) return comm_rebuild(ctx);
+  return rebuild(ctx);
+}
+
+int sphbvf_setup(sphbvf_ctx *ctx) {
+  if (!ctx->atoms_set) return ctx->fail(SPHBVF_ESTATE, "setup before set_atoms");
+  cudaSetDevice(ctx->cfg.device);
+  int rc;
+  // ghosts are created BEFORE setup_pre_force in Verlet::setup (verlet.cpp:118-132), so at step 0
+  // they carry the vest / rhoI their owners had then; same order here.
+  if ((rc = sphbvf_build_neighbors(ctx))) return rc;
+  ctx->nbuilds = 0;   // neighbor->ncalls = 0 (verlet.cpp:128)
+  ctx->ndanger = 0;
+  launch_setup_pre_force(ctx->d, ctx->cfg.integrate_groupbit, ctx->st);
+  ctx->tic(K_PACK);
+  launch_pack(ctx->d, ctx->co, ctx->with_dev, ctx->st);
+  ctx->toc();
+  CKLAUNCH();
+  ctx->setup_done = 1;
+  if ((rc = sphbvf_pair_compute(ctx))) return rc;
+  if ((rc = run_fixes(ctx, 1))) return rc;   // modify->setup(): FixSetForce::setup, FixSsaTsdpdBuoyancy::setup
+  CK(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
+int sphbvf_initial_integrate(sphbvf_ctx *ctx) {
+  ctx->tic(K_INITIAL);
+  launch_initial_integrate(ctx->d, ctx->co, ctx->cfg.dt, ctx->ntimestep, ctx->cfg.integrate_groupbit, ctx->st);
+  ctx->toc();
+  CKLAUNCH();
+  return 0;
+}
+
+int sphbvf_post_integrate(sphbvf_ctx *ctx) { return run_fixes(ctx, 0); }
+int sphbvf_post_force(sphbvf_ctx *ctx) { return run_fixes(ctx, 1); }
+int sphbvf_end_of_step(sphbvf_ctx *ctx) { return run_fixes(ctx, 2); }
+
+int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt) {
+  if (!ctx->setup_done) return ctx->fail(SPHBVF_ESTATE, "neighbor before setup");
+  int rc, flag = 0;
+  // Neighbor::decide (neighbor.cpp:1922-1937)
+  ctx->ago++;
+  if (ctx->ago >= ctx->cfg.neigh_delay && ctx->ago % ctx->cfg.neigh_every == 0) {
+    if (ctx->cfg.neigh_check == 0) flag = 1;
+    else {
+      CK(cudaMemsetAsync(ctx->w.flags + 3, 0, sizeof(int), ctx->st));
+      launch_check_distance(ctx->d, ctx->triggersq, ctx->w.flags + 3, ctx->st);
+      if ((rc = fetch_flags(ctx))) return rc;
+      flag = ctx->h_flags[3];
+      if (ctx->cfg.nranks > 1 && (rc = comm_vote(ctx, &flag))) return rc;   // MPI_Allreduce(MAX) neighbor.cpp:1997
+      if (flag && ctx->ago == std::max(ctx->cfg.neigh_every, ctx->cfg.neigh_delay)) ctx->ndanger++;
+    }
+  }
+  if (rebuilt) *rebuilt = flag;
+  if (flag) return ctx->cfg.nranks > 1 ? comm_rebuild(ctx) : rebuild(ctx);
+  // Comm::forward_comm (comm_brick.cpp:460-520): refresh the packed records of owned atoms and ghosts
+  ctx->tic(K_PACK);
+  launch_pack(ctx->d, ctx->co, ctx->with_dev, ctx->st);
+  if (ctx->cfg.nranks > 1) { if ((rc = comm_forward(ctx))) return rc; }
+  else launch_ghost_refresh(ctx->d, ctx->co, ctx->with_dev, ctx->st);
+  ctx->toc();
+  CKLAUNCH();
+  return 0;
+}
+
+int sphbvf_pair_compute(sphbvf_ctx *ctx) {
+  if (!ctx->setup_done) return ctx->fail(SPHBVF_ESTATE, "pair_compute before setup");
+  ctx->tic(K_PAIR);
+  launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->st);
+  ctx->toc();
+  CKLAUNCH();
+  return 0;
+}
+
+int sphbvf_final_integrate(sphbvf_ctx *ctx) {
+  ctx->tic(K_FINAL);
+  launch_final_integrate(ctx->d, ctx->co, ctx->cfg.dt, ctx->ntimestep, ctx->cfg.integrate_groupbit, ctx->st);
+  ctx->toc();
+  CKLAUNCH();
+  return 0;
+}
+
+int sphbvf_run(sphbvf_ctx *ctx, int nsteps) {
+  if (!ctx->setup_done) return ctx->fail(SPHBVF_ESTATE, "run before setup");
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->run_nsteps_user < 0) ctx->run_nsteps = nsteps;   // update->nsteps
+  int rc;
+  for (int s = 0; s < nsteps; s++) {
+    ctx->ntimestep++;
+    if ((rc = sphbvf_initial_integrate(ctx))) return rc;
+    if ((rc = sphbvf_post_integrate(ctx))) return rc;
+    if ((rc = sphbvf_neighbor(ctx, nullptr))) return rc;
+    if ((rc = sphbvf_pair_compute(ctx))) return rc;
+    if ((rc = sphbvf_post_force(ctx))) return rc;
+    if ((rc = sphbvf_final_integrate(ctx))) return rc;
+    if ((rc = sphbvf_end_of_step(ctx))) return rc;
+  }
+  CK(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
+int sphbvf_nlocal(const sphbvf_ctx *ctx) { return ctx->d.nlocal; }
+int sphbvf_nghost(const sphbvf_ctx *ctx) { return ctx->d.nghost; }
+long sphbvf_ntimestep(const sphbvf_ctx *ctx) { return ctx->ntimestep; }
+int sphbvf_nbuilds(const sphbvf_ctx *ctx) { return ctx->nbuilds; }
+int sphbvf_ndanger(const sphbvf_ctx *ctx) { return ctx->ndanger; }
+void *sphbvf_stream(sphbvf_ctx *ctx) { return (void *)ctx->st; }
+
+int sphbvf_sync(sphbvf_ctx *ctx) {
+  CK(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
+long sphbvf_launch_count(const sphbvf_ctx *ctx) {
+  long n = 0;
+  for (int k = 0; k < K_NFAM; k++) n += ctx->launches_fam[k];
+  return n;
+}
+
+int sphbvf_set_profiling(sphbvf_ctx *ctx, int on) {
+  cudaStreamSynchronize(ctx->st);
+  ctx->drain_events();
+  ctx->profiling = on;
+  for (int k = 0; k < K_NFAM; k++) { ctx->ms_fam[k] = 0.0; ctx->launches_fam[k] = 0; }
+  return 0;
+}
+
+double sphbvf_kernel_ms(const sphbvf_ctx *cctx, int which, long *launches) {
+  sphbvf_ctx *ctx = const_cast<sphbvf_ctx *>(cctx);
+  if (which < 0 || which >= K_NFAM) return -1.0;
+  cudaStreamSynchronize(ctx->st);
+  ctx->drain_events();
+  if (launches) *launches = ctx->launches_fam[which];
+  return ctx->ms_fam[which];
+}
+
+// ---- field access --------------------------------------------------------------------------
+static bool field_info(sphbvf_ctx *ctx, int field, void **ptr, int *ncols, int *is_int) {
+  DevState &d = ctx->d;
+  const int S = ctx->co.nspecies;
+  *is_int = 0;
+  *ncols = 1;
+  switch (field) {
+    case SPHBVF_F_TAG: *ptr = d.tag; *is_int = 1; break;
+    case SPHBVF_F_TYPE: *ptr = d.type; *is_int = 1; break;
+    case SPHBVF_F_MASK: *ptr = d.mask; *is_int = 1; break;
+    case SPHBVF_F_SOLID_TAG: *ptr = d.solid; *is_int = 1; break;
+    case SPHBVF_F_FIXED_TAG: *ptr = d.fixed; *is_int = 1; break;
+    case SPHBVF_F_X: *ptr = d.x; *ncols = 3; break;
+    case SPHBVF_F_V: *ptr = d.v; *ncols = 3; break;
+    case SPHBVF_F_VEST: *ptr = d.vest; *ncols = 3; break;
+    case SPHBVF_F_F: *ptr = d.f; *ncols = 3; break;
+    case SPHBVF_F_RHO: *ptr = d.rho; break;
+    case SPHBVF_F_RHOI: *ptr = d.rhoI; break;
+    case SPHBVF_F_DRHO: *ptr = d.drho; break;
+    case SPHBVF_F_E: *ptr = d.e; break;
+    case SPHBVF_F_PHI: *ptr = d.phi; break;
+    case SPHBVF_F_NUMBER_DENSITY: *ptr = d.nd; break;
+    case SPHBVF_F_NW: *ptr = d.nw; *ncols = 3; break;
+    case SPHBVF_F_DDV: *ptr = d.ddv; *ncols = 3; break;
+    case SPHBVF_F_DDX: *ptr = d.ddx; *ncols = 3; break;
+    case SPHBVF_F_RHOAUX1: *ptr = d.rhoAux1; break;
+    case SPHBVF_F_RHOAUX2: *ptr = d.rhoAux2; break;
+    case SPHBVF_F_PNEW: *ptr = d.Pnew; break;
+    case SPHBVF_F_DEV: *ptr = d.dev; *ncols = 9; break;
+    case SPHBVF_F_DDEV: *ptr = d.ddev; *ncols = 9; break;
+    case SPHBVF_F_C: *ptr = d.C; *ncols = S; break;
+    case SPHBVF_F_Q: *ptr = d.Q; *ncols = S; break;
+    default: return false;
+  }
+  return true;
+}
+
+static int stage(sphbvf_ctx *ctx, size_t bytes) {
+  if (bytes > ctx->w.tmp_perm_bytes) {
+    if (ctx->w.tmp_perm) cudaFree(ctx->w.tmp_perm);
+    ctx->w.tmp_perm_bytes = bytes;
+    CK(cudaMalloc(&ctx->w.tmp_perm, bytes));
+  }
+  return 0;
+}
+
+int sphbvf_download(sphbvf_ctx *ctx, int field, void *host) {
+  void *p;
+  int nc, is_int, rc;
+  if (!field_info(ctx, field, &p, &nc, &is_int)) return ctx->fail(SPHBVF_EINVAL, "unknown field %d", field);
+  if (ctx->migrated) return ctx->fail(SPHBVF_ESTATE, "atoms migrated between ranks: use sphbvf_download_local");
+  const int n = ctx->d.nlocal;
+  if (!n || !nc) return 0;
+  cudaSetDevice(ctx->cfg.device);
+  const size_t eb = is_int ? 4 : 8, bytes = eb * (size_t)n * nc;
+  if ((rc = stage(ctx, bytes))) return rc;
+  const long tot = (long)n * nc;
+  const int blocks = (int)((tot + 255) / 256);
+  if (is_int) scatter_rows_kernel<int><<<blocks, 256, 0, ctx->st>>>((const int *)p, (int *)ctx->w.tmp_perm, ctx->d.slot, n, nc, 1);
+  else scatter_rows_kernel<double><<<blocks, 256, 0, ctx->st>>>((const double *)p, (double *)ctx->w.tmp_perm, ctx->d.slot, n, nc, 1);
+  CK(cudaMemcpyAsync(host, ctx->w.tmp_perm, bytes, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
+int sphbvf_download_local(sphbvf_ctx *ctx, int field, void *host, int cap_rows) {
+  void *p;
+  int nc, is_int;
+  if (!field_info(ctx, field, &p, &nc, &is_int)) return ctx->fail(SPHBVF_EINVAL, "unknown field %d", field);
+  const int n = ctx->d.nlocal;
+  if (cap_rows < n) return ctx->fail(SPHBVF_EINVAL, "download_local: buffer too small (%d < %d)", cap_rows, n);
+  if (!n || !nc) return 0;
+  cudaSetDevice(ctx->cfg.device);
+  CK(cudaMemcpyAsync(host, p, (is_int ? 4 : 8) * (size_t)n * nc, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
+int sphbvf_upload(sphbvf_ctx *ctx, int field, const void *host) {
+  void *p;
+  int nc, is_int, rc;
+  if (!field_info(ctx, field, &p, &nc, &is_int)) return ctx->fail(SPHBVF_EINVAL, "unknown field %d", field);
+  if (ctx->migrated) return ctx->fail(SPHBVF_ESTATE, "atoms migrated between ranks: upload by slot is undefined");
+  const int n = ctx->d.nlocal;
+  if (!n || !nc) return 0;
+  cudaSetDevice(ctx->cfg.device);
+  const size_t eb = is_int ? 4 : 8, bytes = eb * (size_t)n * nc;
+  if ((rc = stage(ctx, bytes))) return rc;
+  CK(cudaMemcpyAsync(ctx->w.tmp_perm, host, bytes, cudaMemcpyHostToDevice, ctx->st));
+  const long tot = (long)n * nc;
+  const int blocks = (int)((tot + 255) / 256);
+  if (is_int) scatter_rows_kernel<int><<<blocks, 256, 0, ctx->st>>>((const int *)ctx->w.tmp_perm, (int *)p, ctx->d.slot, n, nc, 0);
+  else scatter_rows_kernel<double><<<blocks, 256, 0, ctx->st>>>((const double *)ctx->w.tmp_perm, (double *)p, ctx->d.slot, n, nc, 0);
+  CKLAUNCH();
+  CK(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
+// each unordered pair once, as (tag_i, tag_j): what the reference's half list holds
+long sphbvf_get_pairs(sphbvf_ctx *ctx, int *out, long cap) {
+  DevState &d = ctx->d;
+  const int n = d.nlocal, nall = d.nlocal + d.nghost;
+  if (!d.neigh || !n) return 0;
+  cudaSetDevice(ctx->cfg.device);
+  cudaStreamSynchronize(ctx->st);
+  std::vector<int> nn(n), ptag(nall), gowner(std::max(d.nghost, 1));
+  std::vector<double> gshift(3 * (size_t)std::max(d.nghost, 1));
+  cudaMemcpy(nn.data(), d.numneigh, sizeof(int) * n, cudaMemcpyDeviceToHost);
+  cudaMemcpy(ptag.data(), d.ptag, sizeof(int) * nall, cudaMemcpyDeviceToHost);
+  if (d.nghost) {
+    cudaMemcpy(gowner.data(), d.gowner, sizeof(int) * d.nghost, cudaMemcpyDeviceToHost);
+    cudaMemcpy(gshift.data(), d.gshift, sizeof(double) * 3 * d.nghost, cudaMemcpyDeviceToHost);
+  }
+  int mx = 0;
+  for (int i = 0; i < n; i++) mx = std::max(mx, nn[i]);
+  std::vector<int> row(n);
+  long cnt = 0;
+  for (int k = 0; k < mx; k++) {
+    cudaMemcpy(row.data(), d.neigh + (size_t)k * d.stride, sizeof(int) * n, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n; i++) {
+      if (k >= nn[i]) continue;
+      const int j = row[i] & NEIGH_JMASK;
+      bool emit;
+      if (j < n) emit = i < j;
+      else {
+        const int g = j - n;
+        if (ptag[i] != ptag[j]) emit = ptag[i] < ptag[j];
+        else {   // an atom and its own periodic image: keep the lexicographically positive shift
+          const double *s = &gshift[3 * (size_t)g];
+          emit = s[2] > 0 || (s[2] == 0 && (s[1] > 0 || (s[1] == 0 && s[0] > 0)));
+        }
+      }
+      if (!emit) continue;
+      if (out && cnt < cap) { out[2 * cnt] = ptag[i]; out[2 * cnt + 1] = ptag[j]; }
+      cnt++;
+    }
+  }
+  return cnt;
+}
+
+}  // extern "C"

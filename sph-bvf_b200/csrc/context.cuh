@@ -1,0 +1,54 @@
+// context.cuh -- the opaque sphbvf_ctx behind include/sphbvf.h
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "sphbvf_internal.cuh"
+
+struct CommState;   // comm.cu
+
+struct EvPair {
+  int fam;
+  cudaEvent_t a, b;
+};
+
+struct sphbvf_ctx {
+  sphbvf_config cfg{};
+  sphbvf::Coeffs co{};
+  sphbvf::Box box{};
+  sphbvf::Grid grid{};
+  sphbvf::DevState d{};
+  sphbvf::NeighWork w{};
+  cudaStream_t st = nullptr;
+  int pairset[sphbvf::MAXT][sphbvf::MAXT] = {};
+  sphbvf::FixDesc fixes[sphbvf::MAXFIX];
+  int nfix = 0;
+  long ntimestep = 0, run_nsteps = 0, run_nsteps_user = -1;
+  int ago = 0, nbuilds = 0, ndanger = 0, maxneigh_seen = 0;
+  int atoms_set = 0, setup_done = 0, with_dev = 0, any_solid = 0, e_nonzero = 0, migrated = 0;
+  double cutneighmax = 0.0, triggersq = 0.0;
+  long scan_cap = 0;
+  int *h_flags = nullptr;      // pinned, 16 ints
+  void *h_stage = nullptr;     // pinned staging (halo counts)
+  CommState *comm = nullptr;
+  std::string err;
+  // accounting
+  int profiling = 0;
+  long launches_fam[sphbvf::K_NFAM] = {};
+  double ms_fam[sphbvf::K_NFAM] = {};
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<EvPair> ev_list;
+  EvPair ev_open{};
+
+  int fail(int code, const char *fmt, ...);
+  void tic(int fam, int nlaunch = 1);
+  void toc();
+  void drain_events();
+};
+
+// comm.cu: brick decomposition over NCCL (one rank per GPU)
+int comm_rebuild(sphbvf_ctx *ctx);        // pbc + migration + sort + borders + list
+int comm_forward(sphbvf_ctx *ctx);        // per-step halo of the packed records
+int comm_vote(sphbvf_ctx *ctx, int *flag); // rebuild vote: max over ranks
+void comm_destroy(sphbvf_ctx *ctx);

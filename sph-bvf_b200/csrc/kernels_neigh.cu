@@ -1,0 +1,338 @@
+// kernels_neigh.cu -- kernel (1) of the hot path: periodic wrap, rebuild trigger, cell binning,
+// deterministic counting sort of the owned atoms, periodic-image ghosts, and the Verlet list.
+//
+// Replaces Domain::pbc (domain.cpp:498-600), Neighbor::check_distance (neighbor.cpp:1950-2006),
+// NBinStandard::{setup_bins,bin_atoms} + NBin::coord2bin (nbin_standard.cpp:53-232, nbin.cpp:116-148),
+// the NStencil*Bin* offsets (nstencil.cpp:145-228), NPair{HalfBinAtomonlyNewton,FullBinAtomonly}::build
+// (npair_half_bin_atomonly_newton.cpp:37-118, npair_full_bin_atomonly.cpp:34-95) and, for one rank,
+// CommBrick::borders (comm_brick.cpp:709-880).
+//
+// The reference's linked-list bins become a counting sort that physically reorders the owned
+// atoms (coalesced streaming everywhere else); its half list with Newton mirror becomes a FULL
+// list per owned atom (gather form, no atomics, no reverse communication).  The SET of
+// interacting pairs is the reference's: rsq <= cutneighsq[itype][jtype] at rebuild time, with rsq
+// evaluated without FMA contraction in the reference's operation order, so the lists compare
+// bit-exactly as sorted tag pairs.
+#include "sphbvf_internal.cuh"
+
+namespace sphbvf {
+
+static inline int nblocks(long n, int t) { return (int)((n + t - 1) / t); }
+
+// flags: [0] non-finite coordinate, [1] lost atom (outside the cell grid), [2] max neighbour
+// count, [3] some atom moved more than skin/2
+__device__ __forceinline__ double rsq_nofma(double dx, double dy, double dz) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+__global__ void check_distance_kernel(const DevState d, const double triggersq, int *flag_moved) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.nlocal) return;
+  const size_t i3 = 3 * (size_t)i;
+  const double rsq = rsq_nofma(d.x[i3] - d.xhold[i3], d.x[i3 + 1] - d.xhold[i3 + 1], d.x[i3 + 2] - d.xhold[i3 + 2]);
+  if (rsq > triggersq) *flag_moved = 1;
+}
+
+void launch_check_distance(const DevState &d, double triggersq, int *flag_moved, cudaStream_t st) {
+  if (d.nlocal) check_distance_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, triggersq, flag_moved);
+}
+
+__device__ __forceinline__ int cell_of(const Grid &g, double x, double y, double z, bool &ok) {
+  const double fx = (x - g.lo[0]) * g.inv[0], fy = (y - g.lo[1]) * g.inv[1], fz = (z - g.lo[2]) * g.inv[2];
+  int cx = (int)floor(fx), cy = (int)floor(fy), cz = (int)floor(fz);
+  ok = cx >= 0 && cy >= 0 && cz >= 0 && cx < g.n[0] && cy < g.n[1] && cz < g.n[2];
+  return (cz * g.n[1] + cy) * g.n[0] + cx;
+}
+
+__global__ void pbc_cellid_kernel(const DevState d, const Box b, const Grid g, int *cellid, int *cell_count, int *flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.nlocal) return;
+  double x[3];
+  for (int k = 0; k < 3; k++) {
+    double xk = d.x[3 * (size_t)i + k];
+    if (!isfinite(xk)) { flags[0] = 1; xk = b.lo[k]; }
+    if (b.periodic[k]) {
+      if (xk < b.lo[k]) xk += b.prd[k];
+      if (xk >= b.hi[k]) {
+        xk -= b.prd[k];
+        xk = xk > b.lo[k] ? xk : b.lo[k];
+      }
+      d.x[3 * (size_t)i + k] = xk;
+    }
+    x[k] = xk;
+  }
+  if (b.dim == 2) x[2] = g.lo[2];
+  bool ok;
+  int c = cell_of(g, x[0], x[1], x[2], ok);
+  if (!ok) { flags[1] = 1; c = 0; }
+  cellid[i] = c;
+  atomicAdd(&cell_count[c], 1);
+}
+
+void launch_cell_ids(const DevState &d, const Grid &g, const Box &b, const NeighWork &w, cudaStream_t st) {
+  cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (g.ncells + 1), st);
+  if (d.nlocal) pbc_cellid_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, b, g, w.cellid, w.cell_count, w.flags);
+}
+
+// ---------------------------------------------------------------- exclusive scan (int32)
+constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_B = SCAN_T * SCAN_E;
+
+__global__ void scan_block_kernel(const int *in, int *out, long n, int *block_sums) {
+  __shared__ int warp_tot[SCAN_T / 32];
+  const long base = (long)blockIdx.x * SCAN_B + (long)threadIdx.x * SCAN_E;
+  int v[SCAN_E], tsum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    tsum += v[k];
+  }
+  // inclusive scan of per-thread sums across the block
+  int x = tsum;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_tot[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int t = lane < SCAN_T / 32 ? warp_tot[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < SCAN_T / 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += y;
+    }
+    if (lane < SCAN_T / 32) warp_tot[lane] = t;
+  }
+  __syncthreads();
+  int excl = x - tsum + (wid ? warp_tot[wid - 1] : 0);
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++) {
+    if (base + k < n) out[base + k] = excl;
+    excl += v[k];
+  }
+  if (threadIdx.x == SCAN_T - 1 && block_sums) block_sums[blockIdx.x] = excl;
+}
+
+__global__ void scan_add_kernel(int *out, long n, const int *block_offsets) {
+  const long i = (long)blockIdx.x * SCAN_B + threadIdx.x;
+  const int off = block_offsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++) {
+    const long q = i + (long)k * SCAN_T;
+    if (q < n) out[q] += off;
+  }
+}
+
+// out[0..n) = exclusive scan of in[0..n); tmp needs >= n/SCAN_B + 2*SCAN_B ints.  `in` must have
+// n+1 readable entries with in[n] arbitrary: callers pass n+1 so out[n] is the grand total.
+void exclusive_scan(const int *in, int *out, long n, int *tmp, cudaStream_t st) {
+  if (n <= 0) return;
+  const long nb = (n + SCAN_B - 1) / SCAN_B;
+  if (nb == 1) {
+    scan_block_kernel<<<1, SCAN_T, 0, st>>>(in, out, n, nullptr);
+    return;
+  }
+  scan_block_kernel<<<(int)nb, SCAN_T, 0, st>>>(in, out, n, tmp);
+  exclusive_scan(tmp, tmp, nb, tmp + nb, st);
+  scan_add_kernel<<<(int)nb, SCAN_T, 0, st>>>(out, n, tmp);
+}
+
+// ---------------------------------------------------------------- counting sort of owned atoms
+__global__ void scatter_kernel(const int n, const int *cellid, const int *cell_start, int *cursor, int *perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cellid[i];
+  const int r = atomicAdd(&cursor[c], 1);
+  perm[cell_start[c] + r] = i;
+}
+
+// restore determinism: within each cell order by previous index (cells hold a handful of atoms)
+__global__ void cell_order_kernel(const long ncells, const int *cell_start, int *perm) {
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const int a = cell_start[c], b = cell_start[c + 1];
+  for (int p = a + 1; p < b; p++) {
+    const int v = perm[p];
+    int q = p - 1;
+    while (q >= a && perm[q] > v) { perm[q + 1] = perm[q]; q--; }
+    perm[q + 1] = v;
+  }
+}
+
+void launch_sort_owned(const DevState &d, const Grid &g, const NeighWork &w, cudaStream_t st) {
+  // cell_count[ncells] = 0 sentinel so that cell_start[ncells] = nlocal
+  exclusive_scan(w.cell_count, w.cell_start, g.ncells + 1, w.scan_tmp, st);
+  cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (g.ncells + 1), st);
+  if (!d.nlocal) return;
+  scatter_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d.nlocal, w.cellid, w.cell_start, w.cell_count, w.perm);
+  cell_order_kernel<<<nblocks(g.ncells, 256), 256, 0, st>>>(g.ncells, w.cell_start, w.perm);
+}
+
+template <typename T>
+__global__ void permute_kernel(const T *in, T *out, const int *perm, const int n, const int ncols) {
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long)n * ncols) return;
+  const int row = (int)(q / ncols), col = (int)(q - (long)row * ncols);
+  out[q] = in[(long)perm[row] * ncols + col];
+}
+
+// arr[new] = arr[perm[new]] through the staging buffer
+void launch_permute(void *arr, void *tmp, const int *perm, int n, int ncols, int elem_bytes, cudaStream_t st) {
+  if (!n || !ncols) return;
+  const long tot = (long)n * ncols;
+  if (elem_bytes == 8) permute_kernel<double><<<nblocks(tot, 256), 256, 0, st>>>((const double *)arr, (double *)tmp, perm, n, ncols);
+  else permute_kernel<int><<<nblocks(tot, 256), 256, 0, st>>>((const int *)arr, (int *)tmp, perm, n, ncols);
+  cudaMemcpyAsync(arr, tmp, (size_t)tot * elem_bytes, cudaMemcpyDeviceToDevice, st);
+}
+
+// ---------------------------------------------------------------- periodic self-image ghosts
+// An owned atom needs an image shifted by s (s_k in {-1,0,+1}, periodic dims only, s != 0) iff for
+// every shifted dim it lies in the slab the reference's staged swaps send across that face:
+// s_k = +1: x_k <= lo + cutghost ; s_k = -1: x_k >= hi - cutghost (comm_brick.cpp:355-395, 765-770).
+__device__ __forceinline__ void image_slabs(const Box &b, const double cutghost, const double *x, int lo[3], int hi[3]) {
+  for (int k = 0; k < 3; k++) {
+    const bool use = b.periodic[k] && !(b.dim == 2 && k == 2) && b.sublo[k] == b.lo[k] && b.subhi[k] == b.hi[k];
+    lo[k] = use && x[k] <= b.lo[k] + cutghost;
+    hi[k] = use && x[k] >= b.hi[k] - cutghost;
+  }
+}
+
+__global__ void count_images_kernel(const DevState d, const Box b, const double cutghost, int *nimg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > d.nlocal) return;
+  if (i == d.nlocal) { nimg[i] = 0; return; }
+  int lo[3], hi[3];
+  image_slabs(b, cutghost, &d.x[3 * (size_t)i], lo, hi);
+  nimg[i] = (1 + lo[0] + hi[0]) * (1 + lo[1] + hi[1]) * (1 + lo[2] + hi[2]) - 1;
+}
+
+__global__ void fill_images_kernel(const DevState d, const Box b, const double cutghost, const int *img_start) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.nlocal) return;
+  int lo[3], hi[3];
+  image_slabs(b, cutghost, &d.x[3 * (size_t)i], lo, hi);
+  int g = img_start[i];
+  for (int sz = -1; sz <= 1; sz++)
+    for (int sy = -1; sy <= 1; sy++)
+      for (int sx = -1; sx <= 1; sx++) {
+        if (!sx && !sy && !sz) continue;
+        const int s[3] = {sx, sy, sz};
+        bool need = true;
+        for (int k = 0; k < 3; k++)
+          if ((s[k] == 1 && !lo[k]) || (s[k] == -1 && !hi[k])) need = false;
+        if (!need) continue;
+        d.gowner[g] = i;
+        for (int k = 0; k < 3; k++) d.gshift[3 * (size_t)g + k] = s[k] * b.prd[k];
+        d.ptag[d.nlocal + g] = d.tag[i];
+        g++;
+      }
+}
+
+void launch_count_images(const DevState &d, const Box &b, double cutghost, const NeighWork &w, cudaStream_t st) {
+  count_images_kernel<<<nblocks(d.nlocal + 1, 256), 256, 0, st>>>(d, b, cutghost, w.nimg);
+  exclusive_scan(w.nimg, w.nimg, d.nlocal + 1, w.scan_tmp, st);
+}
+
+void launch_fill_images(const DevState &d, const Box &b, double cutghost, const NeighWork &w, cudaStream_t st) {
+  if (d.nlocal) fill_images_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, b, cutghost, w.nimg);
+}
+
+// ---------------------------------------------------------------- ghosts into cells (index sort)
+__global__ void ghost_cellid_kernel(const DevState d, const Grid g, const int dim, int *cellid, int *gcell_count, int *flags) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= d.nghost) return;
+  const double4 A = d.pA[d.nlocal + q];
+  bool ok;
+  int c = cell_of(g, A.x, A.y, dim == 2 ? g.lo[2] : A.z, ok);
+  if (!ok) c = -1;   // beyond the stencil reach of every owned atom: never a neighbour
+  cellid[d.nlocal + q] = c;
+  if (c >= 0) atomicAdd(&gcell_count[c], 1);
+}
+
+__global__ void ghost_scatter_kernel(const DevState d, const int *cellid, const int *gcell_start, int *cursor, int *gorder) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= d.nghost) return;
+  const int c = cellid[d.nlocal + q];
+  if (c < 0) return;
+  const int r = atomicAdd(&cursor[c], 1);
+  gorder[gcell_start[c] + r] = q;
+}
+
+void launch_bin_ghosts(const DevState &d, const Grid &g, const NeighWork &w, cudaStream_t st) {
+  cudaMemsetAsync(w.gcell_count, 0, sizeof(int) * (g.ncells + 1), st);
+  if (d.nghost) ghost_cellid_kernel<<<nblocks(d.nghost, 256), 256, 0, st>>>(d, g, g.dim, w.cellid, w.gcell_count, w.flags);
+  exclusive_scan(w.gcell_count, w.gcell_start, g.ncells + 1, w.scan_tmp, st);
+  if (!d.nghost) return;
+  cudaMemsetAsync(w.gcell_count, 0, sizeof(int) * (g.ncells + 1), st);
+  ghost_scatter_kernel<<<nblocks(d.nghost, 256), 256, 0, st>>>(d, w.cellid, w.gcell_start, w.gcell_count, w.gorder);
+  cell_order_kernel<<<nblocks(g.ncells, 256), 256, 0, st>>>(g.ncells, w.gcell_start, w.gorder);
+}
+
+// ---------------------------------------------------------------- Verlet list
+__global__ void __launch_bounds__(128)
+build_list_kernel(const DevState d, const Grid g, const __grid_constant__ Coeffs co, const int *cell_start,
+                  const int *gcell_start, const int *gorder, const double cutmaxsq, int *flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.nlocal) return;
+  const double4 Ai = d.pA[i];
+  const int ti = d.pflags[i] & 7;
+  bool ok;
+  const int ci = cell_of(g, Ai.x, Ai.y, co.dim == 2 ? g.lo[2] : Ai.z, ok);
+  const int cx = ci % g.n[0], cy = (ci / g.n[0]) % g.n[1], cz = ci / (g.n[0] * g.n[1]);
+  const double bsx = 1.0 / g.inv[0], bsy = 1.0 / g.inv[1], bsz = 1.0 / g.inv[2];
+  int n = 0;
+  int *out = d.neigh + i;
+  for (int dz = -g.s[2]; dz <= g.s[2]; dz++) {
+    const int z = cz + dz;
+    if (z < 0 || z >= g.n[2]) continue;
+    const double ddz = dz > 0 ? (dz - 1) * bsz : (dz < 0 ? (dz + 1) * bsz : 0.0);
+    for (int dy = -g.s[1]; dy <= g.s[1]; dy++) {
+      const int y = cy + dy;
+      if (y < 0 || y >= g.n[1]) continue;
+      const double ddy = dy > 0 ? (dy - 1) * bsy : (dy < 0 ? (dy + 1) * bsy : 0.0);
+      for (int dx = -g.s[0]; dx <= g.s[0]; dx++) {
+        const int x = cx + dx;
+        if (x < 0 || x >= g.n[0]) continue;
+        const double ddx = dx > 0 ? (dx - 1) * bsx : (dx < 0 ? (dx + 1) * bsx : 0.0);
+        // NStencil::bin_distance prune (nstencil.cpp:204-228)
+        if (!(ddx * ddx + ddy * ddy + ddz * ddz < cutmaxsq)) continue;
+        const int c = (z * g.n[1] + y) * g.n[0] + x;
+        for (int pass = 0; pass < 2; pass++) {
+          const int *start = pass ? gcell_start : cell_start;
+          const int a = start[c], b = start[c + 1];
+          for (int p = a; p < b; p++) {
+            const int j = pass ? d.nlocal + gorder[p] : p;
+            if (j == i) continue;
+            const double4 Aj = d.pA[j];
+            const double rsq = rsq_nofma(Ai.x - Aj.x, Ai.y - Aj.y, Ai.z - Aj.z);
+            const int fj = d.pflags[j];
+            const int tj = fj & 7;
+            if (rsq <= co.cutneighsq[ti][tj]) {
+              if (n < d.maxneigh) out[(size_t)n * d.stride] = j | (tj << NEIGH_JBITS) | (((fj >> 4) & 1) << 30);
+              n++;
+            }
+          }
+        }
+      }
+    }
+  }
+  d.numneigh[i] = n < d.maxneigh ? n : d.maxneigh;
+  atomicMax(&flags[2], n);
+}
+
+void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const NeighWork &w, cudaStream_t st) {
+  double cutmax = 0.0;
+  for (int i = 1; i <= co.ntypes; i++)
+    for (int j = 1; j <= co.ntypes; j++)
+      if (co.cutneighsq[i][j] > cutmax) cutmax = co.cutneighsq[i][j];
+  if (d.nlocal)
+    build_list_kernel<<<nblocks(d.nlocal, 128), 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
+}
+
+void launch_copy_xhold(const DevState &d, cudaStream_t st) {
+  cudaMemcpyAsync(d.xhold, d.x, sizeof(double) * 3 * (size_t)d.nlocal, cudaMemcpyDeviceToDevice, st);
+}
+
+}  // namespace sphbvf

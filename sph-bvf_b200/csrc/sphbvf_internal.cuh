@@ -1,0 +1,145 @@
+// sphbvf_internal.cuh -- shared declarations of the CUDA implementation behind include/sphbvf.h
+//
+// Data layout in HBM (all FP64 / int32, device resident for the whole run):
+//   primary state, owned atoms only, cell-sorted order, LAMMPS-compatible row layout:
+//     x v vest [n][3] | rho rhoI e [n] | C [n][S] | dev [n][9] | tag type mask solid fixed slot [n]
+//   pair outputs, owned atoms (written once per step by the pair kernel, no atomics, no memset):
+//     f nw ddv ddx [n][3] | drho phi nd rhoAux1 rhoAux2 Pnew [n] | ddev [n][9] | Q [n][S]
+//   packed pair inputs, owned + ghost atoms, 32-byte records so that a neighbour visit is three
+//   aligned 32 B loads (two LDG.128 each) instead of 13 scattered 8 B loads:
+//     pA = {x, y, z, rho}   pB = {vest.x, vest.y, vest.z, V=m/rho}   pC = {w.x, w.y, w.z, P/rho^2}
+//     with w = vest - v (momentum minus transport velocity); pD = {rhoI, art, C0, e} is only read
+//     on Shepard-filter steps / near solids / by the fsi variant; pCs [nall][S], pdev [nall][9].
+//   neighbour structure: full (both directions) Verlet list of the owned atoms, frozen between
+//   rebuilds exactly like the reference's list, stored TRANSPOSED -- entry k of atom i lives at
+//   neigh[k * stride + i] -- so the 32 lanes of a warp read 128 contiguous bytes per k.  An entry
+//   packs j (27 bits), type_j (3 bits) and solid_tag_j (1 bit): no flag gather in the hot loop.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sphbvf.h"
+
+namespace sphbvf {
+
+constexpr int MAXT = 5;  // atom types 1..4
+constexpr int MAXS = 4;  // species
+constexpr int MAXFIX = 16;
+constexpr int NEIGH_JBITS = 27;
+constexpr int NEIGH_JMASK = (1 << NEIGH_JBITS) - 1;
+
+// per-type / per-type-pair coefficients, passed to kernels by value (constant bank)
+struct Coeffs {
+  int dim, variant, nspecies, ntypes;
+  double mass[MAXT], rho0[MAXT], c0[MAXT], B[MAXT], G0[MAXT];
+  double eta[MAXT][MAXT], cut[MAXT][MAXT], cutsq[MAXT][MAXT], cutc[MAXT][MAXT];
+  double cutneighsq[MAXT][MAXT];
+  double kappa[MAXT][MAXT][MAXS];
+};
+
+// cell grid used for sorting and for the list build (covers sub-box + ghost shell)
+struct Grid {
+  double lo[3];      // grid origin
+  double inv[3];     // 1 / cell size
+  int n[3];          // cells per dimension
+  int s[3];          // stencil half-width in cells
+  int dim;
+  long ncells;
+};
+
+struct Box {
+  double lo[3], hi[3], prd[3];   // global box
+  double sublo[3], subhi[3];     // this rank's brick
+  int periodic[3];
+  int dim;
+};
+
+enum FixKind { FIX_BUOYANCY = 0, FIX_FORCING = 1, FIX_BUFFER = 2, FIX_SETFORCE = 3 };
+struct FixDesc {
+  int kind, groupbit;
+  int ia[4];
+  long step;
+  double a[6];
+};
+
+// device pointers of one context (plain struct so kernels can take it by value)
+struct DevState {
+  int nlocal, nghost, nmax, nallmax;
+  // primary
+  int *tag, *type, *mask, *solid, *fixed, *slot;
+  double *x, *v, *vest, *rho, *rhoI, *e, *C, *dev;
+  // pair outputs
+  double *f, *nw, *ddv, *ddx, *drho, *phi, *nd, *rhoAux1, *rhoAux2, *Pnew, *ddev, *Q;
+  // packed pair inputs (owned + ghost)
+  double4 *pA, *pB, *pC, *pD;
+  double *pCs, *pdev;
+  int *pflags, *ptag;
+  // rebuild bookkeeping
+  double *xhold;
+  // ghosts that image owned atoms of this rank (periodic self images)
+  int *gowner;          // owner index (owned atom) of self-image ghost g
+  double *gshift;       // [nghost][3]
+  // neighbour list
+  int *neigh;           // [maxneigh][stride]
+  int *numneigh;        // [nlocal]
+  int stride, maxneigh;
+};
+
+enum KernelFamily { K_PAIR = 0, K_INITIAL = 1, K_FINAL = 2, K_NEIGH = 3, K_PACK = 4, K_FIX = 5, K_NFAM = 6 };
+
+}  // namespace sphbvf
+
+// -------- launchers implemented in the .cu files (all asynchronous on `st`) -----------------
+namespace sphbvf {
+
+// kernels_integrate.cu
+void launch_setup_pre_force(const DevState &d, int groupbit, cudaStream_t st);
+void launch_initial_integrate(const DevState &d, const Coeffs &co, double dt, long ntimestep,
+                              int groupbit, cudaStream_t st);
+void launch_final_integrate(const DevState &d, const Coeffs &co, double dt, long ntimestep,
+                            int groupbit, cudaStream_t st);
+void launch_fix(const DevState &d, const Coeffs &co, const FixDesc &fx, int hook, long ntimestep,
+                cudaStream_t st);   // hook: 0 post_integrate, 1 post_force, 2 end_of_step
+// pack owned atoms into pA..pD (+pCs, pdev) and refresh self-image ghosts from their owners
+void launch_pack(const DevState &d, const Coeffs &co, int with_dev, cudaStream_t st);
+void launch_ghost_refresh(const DevState &d, const Coeffs &co, int with_dev, cudaStream_t st);
+
+// kernels_pair.cu
+struct PairFlags {
+  int filter_step;   // Shepard sums rhoAux1/2 are consumed this step
+  int with_dev;      // deviatoric tensors may be non-zero (elastic solids present)
+  int any_solid;     // some atom has solid_tag == 1
+  double damp;       // density-diffusion amplitude of the fsi variant (0 otherwise)
+};
+void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, cudaStream_t st);
+
+// kernels_neigh.cu
+struct NeighWork {      // scratch owned by the context
+  int *cellid;          // [nallmax]
+  int *perm;            // [nmax]  new position -> old index (owned)
+  int *cell_count;      // [ncells+1]
+  int *cell_start;      // [ncells+1]  exclusive scan over owned atoms
+  int *gcell_count, *gcell_start;   // same for ghosts
+  int *gorder;          // [nghost] ghost indices (relative to nlocal) sorted by cell
+  int *scan_tmp;        // block sums for the scan
+  long ncells_cap;
+  int *nimg;            // [nmax+1] images per owned atom and its exclusive scan
+  int *flags;           // device flags: [0] nonfinite, [1] lost, [2] max neighbours, [3] moved
+  void *tmp_perm;       // staging buffer for the permutation of one array
+  size_t tmp_perm_bytes;
+};
+// all return cudaError_t of the enqueue; results that the host needs are in w.flags
+void launch_check_distance(const DevState &d, double triggersq, int *flag_moved, cudaStream_t st);
+void launch_cell_ids(const DevState &d, const Grid &g, const Box &b, const NeighWork &w, cudaStream_t st);
+void exclusive_scan(const int *in, int *out, long n, int *tmp, cudaStream_t st);  // out has n+1 entries
+void launch_sort_owned(const DevState &d, const Grid &g, const NeighWork &w, cudaStream_t st);
+void launch_permute(void *arr, void *tmp, const int *perm, int n, int ncols, int elem_bytes, cudaStream_t st);
+void launch_count_images(const DevState &d, const Box &b, double cutghost, const NeighWork &w, cudaStream_t st);
+void launch_fill_images(const DevState &d, const Box &b, double cutghost, const NeighWork &w, cudaStream_t st);
+void launch_bin_ghosts(const DevState &d, const Grid &g, const NeighWork &w, cudaStream_t st);
+void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const NeighWork &w, cudaStream_t st);
+void launch_copy_xhold(const DevState &d, cudaStream_t st);
+long count_pairs_host(const DevState &d, cudaStream_t st);
+
+}  // namespace sphbvf
