@@ -75,6 +75,7 @@ struct orc_ctx {
   int nfix;
   orc_fix fix[MAXFIX];
   int setup_done;
+  int consistent_ghosts;
   char err[256];
 };
 
@@ -1035,7 +1036,12 @@ int orc_setup(orc_ctx *c) {
   if (init_cutoffs(c)) return -1;
   domain_pbc(c);
   if (setup_bins(c)) return -1;
-  borders(c);          /* ghosts are made BEFORE setup_pre_force: their vest/rhoI are stale at step 0 */
+  /* the reference makes ghosts BEFORE setup_pre_force (verlet.cpp:118-132), so at step 0 they
+     carry stale vest/rhoI.  With half lists + Newton that is not even
+     gather-consistent; the CUDA library deliberately does not reproduce it, and
+     orc_set_consistent_ghosts(1) gives the oracle the library's order for direct comparison. */
+  if (c->consistent_ghosts) setup_pre_force(c);
+  borders(c);
   if (neighbor_build(c)) return -1;
   c->nbuilds = 0;      /* neighbor->ncalls = 0 (verlet.cpp:128) */
   force_clear(c);
@@ -1076,6 +1082,8 @@ void orc_set_run_length(orc_ctx *c, long nsteps) {
   c->run_nsteps_user = nsteps;
   c->run_nsteps = nsteps;
 }
+
+void orc_set_consistent_ghosts(orc_ctx *c, int on) { c->consistent_ghosts = on; }
 
 int orc_nlocal(const orc_ctx *c) { return c->nlocal; }
 int orc_nghost(const orc_ctx *c) { return c->nghost; }

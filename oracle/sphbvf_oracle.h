@@ -71,6 +71,10 @@ int orc_run(orc_ctx *c, int nsteps);    /* Verlet::run    (verlet.cpp:223-354), 
  * dt*nsteps (pair_ssa_tsdpd_bvf_fsi.cpp:531-539).  Default: the argument of each orc_run. */
 void orc_set_run_length(orc_ctx *c, long nsteps);
 
+/* 0 (default): ghosts are created before setup_pre_force as in Verlet::setup, i.e. with stale
+ * vest/rhoI at step 0.  1: setup_pre_force first (what the CUDA library does). */
+void orc_set_consistent_ghosts(orc_ctx *c, int on);
+
 /* single pieces, for kernel-level tests */
 int orc_build_neighbors(orc_ctx *c);    /* pbc + ghosts + bins + list, as on a rebuild step */
 int orc_pair_compute(orc_ctx *c);       /* force_clear + PairSsaTsdpdBvf*::compute */

@@ -523,16 +523,16 @@ int sphbvf_setup(sphbvf_ctx *ctx) {
   if (!ctx->atoms_set) return ctx->fail(SPHBVF_ESTATE, "setup before set_atoms");
   cudaSetDevice(ctx->cfg.device);
   int rc;
-  // ghosts are created BEFORE setup_pre_force in Verlet::setup (verlet.cpp:118-132), so at step 0
-  // they carry the vest / rhoI their owners had then; same order here.
+  // Deliberate deviation: Verlet::setup creates ghosts BEFORE setup_pre_force sets
+  // vest = v, rhoI = rho (verlet.cpp:118-132), so the reference's ghosts hold stale vest/rhoI at
+  // step 0 -- and with its half list + Newton mirror the step-0 result is then not even
+  // gather-consistent.  Here setup_pre_force runs first, so ghosts always mirror their owners.
+  // Identical whenever the initial momentum velocity of atoms near a periodic face is zero (all
+  // shipped decks) or the run was preceded by a `run 0`.
+  launch_setup_pre_force(ctx->d, ctx->cfg.integrate_groupbit, ctx->st);
   if ((rc = sphbvf_build_neighbors(ctx))) return rc;
   ctx->nbuilds = 0;   // neighbor->ncalls = 0 (verlet.cpp:128)
   ctx->ndanger = 0;
-  launch_setup_pre_force(ctx->d, ctx->cfg.integrate_groupbit, ctx->st);
-  ctx->tic(K_PACK);
-  launch_pack(ctx->d, ctx->co, ctx->with_dev, ctx->st);
-  ctx->toc();
-  CKLAUNCH();
   ctx->setup_done = 1;
   if ((rc = sphbvf_pair_compute(ctx))) return rc;
   if ((rc = run_fixes(ctx, 1))) return rc;   // modify->setup(): FixSetForce::setup, FixSsaTsdpdBuoyancy::setup

@@ -41,6 +41,7 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p]
         L.orc_run.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_run_length.argtypes = [C.c_void_p, C.c_long]
+        L.orc_set_consistent_ghosts.argtypes = [C.c_void_p, C.c_int]
         L.orc_ntimestep.argtypes = [C.c_void_p]
         L.orc_ntimestep.restype = C.c_long
         L.orc_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
@@ -116,6 +117,9 @@ class Oracle:
 
     def set_run_length(self, n):
         lib().orc_set_run_length(self.h, n)
+
+    def set_consistent_ghosts(self, on=True):
+        lib().orc_set_consistent_ghosts(self.h, int(on))
 
     def build_neighbors(self):
         self._ck(lib().orc_build_neighbors(self.h))

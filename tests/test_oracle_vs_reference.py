@@ -31,6 +31,7 @@ def test_oracle_matches_reference(name):
     o = Oracle(meta)
     feed_atoms(o, z)
     o.set_run_length(meta["nsteps"])
+    o.set_consistent_ghosts(meta.get("consistent_ghosts", False))
     o.setup()
     step = 0
     for s in meta["steps"]:
