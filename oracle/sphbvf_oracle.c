@@ -76,6 +76,7 @@ struct orc_ctx {
   orc_fix fix[MAXFIX];
   int setup_done;
   int consistent_ghosts;
+  int symmetric_switch;
   char err[256];
 };
 
@@ -778,7 +779,13 @@ static void pair_compute(orc_ctx *c) {
             double mu = h * delVdotDelR / (rsq + 0.01 * h * h);
             fviscs = imass * jmass * wfd * (-(c->c0[itype] + c->c0[jtype]) * mu + 2.0 * mu * mu) / (rho[i] + rho[j]);
           }
-          for (int d = 0; d < 3; d++) f[3 * j + d] -= (-del[d] * fpair - del[d] * fviscs + fdev[d] + fart[d]);
+          /* reference: fpair is NOT sign-flipped for a solid j (:633), so the force on a free
+             solid from a fluid neighbour with pij < 0 depends on which of the two is `i` in the half
+             list.  symmetric_switch = 1 applies the flip, i.e. what a gather over
+             j's own neighbours computes (the CUDA library); default 0 = reference. */
+          double fpj = fpair;
+          if (c->symmetric_switch && var == ORC_TV && pij < 0. && !(c->solid[i] == 1 && c->solid[j] == 1)) fpj = -fpair;
+          for (int d = 0; d < 3; d++) f[3 * j + d] -= (-del[d] * fpj - del[d] * fviscs + fdev[d] + fart[d]);
         }
         c->drho[j] += (rho[j] * imass * delVtdotDelR * wfd / rho[i]) -
                       damp * h * rho[j] * c->c0[jtype] * imass * 2.0 * (rho[i] / rho[j] - 1.0) *
@@ -1084,6 +1091,7 @@ void orc_set_run_length(orc_ctx *c, long nsteps) {
 }
 
 void orc_set_consistent_ghosts(orc_ctx *c, int on) { c->consistent_ghosts = on; }
+void orc_set_symmetric_switch(orc_ctx *c, int on) { c->symmetric_switch = on; }
 
 int orc_nlocal(const orc_ctx *c) { return c->nlocal; }
 int orc_nghost(const orc_ctx *c) { return c->nghost; }

@@ -74,6 +74,9 @@ void orc_set_run_length(orc_ctx *c, long nsteps);
 /* 0 (default): ghosts are created before setup_pre_force as in Verlet::setup, i.e. with stale
  * vest/rhoI at step 0.  1: setup_pre_force first (what the CUDA library does). */
 void orc_set_consistent_ghosts(orc_ctx *c, int on);
+/* 0 (default): TV pressure switch on FREE solids as the reference's half list applies it
+ * (orientation dependent, pair_...transport_velocity.cpp:606 vs :633).  1: orientation-free form. */
+void orc_set_symmetric_switch(orc_ctx *c, int on);
 
 /* single pieces, for kernel-level tests */
 int orc_build_neighbors(orc_ctx *c);    /* pbc + ghosts + bins + list, as on a rebuild step */

@@ -42,6 +42,7 @@ def lib():
         L.orc_run.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_run_length.argtypes = [C.c_void_p, C.c_long]
         L.orc_set_consistent_ghosts.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_symmetric_switch.argtypes = [C.c_void_p, C.c_int]
         L.orc_ntimestep.argtypes = [C.c_void_p]
         L.orc_ntimestep.restype = C.c_long
         L.orc_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
@@ -117,6 +118,9 @@ class Oracle:
 
     def set_run_length(self, n):
         lib().orc_set_run_length(self.h, n)
+
+    def set_symmetric_switch(self, on=True):
+        lib().orc_set_symmetric_switch(self.h, int(on))
 
     def set_consistent_ghosts(self, on=True):
         lib().orc_set_consistent_ghosts(self.h, int(on))
