@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libsphbvf.so")
+LIBPATH = os.environ.get("SPHBVF_LIB") or os.path.join(HERE, "libsphbvf.so")   # override: A/B builds while tuning
 
 
 class SphbvfError(RuntimeError):

@@ -180,7 +180,6 @@ static int init_neighbor(sphbvf_ctx *ctx) {
   Grid &g = ctx->grid;
   const Box &b = ctx->box;
   const double binsize = 0.5 * ctx->cutneighmax;
-  g.ncells = 1;
   g.dim = b.dim;
   for (int k = 0; k < 3; k++) {
     if (b.dim == 2 && k == 2) {
@@ -188,6 +187,8 @@ static int init_neighbor(sphbvf_ctx *ctx) {
       g.n[k] = 1;
       g.inv[k] = 1.0 / std::max(b.subhi[k] - b.sublo[k], 1e-300);
       g.s[k] = 0;
+      g.glo[k] = 0;
+      g.ghi[k] = 0;
       continue;
     }
     const double lo = b.sublo[k] - ctx->cutneighmax, hi = b.subhi[k] + ctx->cutneighmax;
@@ -200,7 +201,18 @@ static int init_neighbor(sphbvf_ctx *ctx) {
     int s = (int)(ctx->cutneighmax * g.inv[k]);
     if (s * size < ctx->cutneighmax) s++;
     g.s[k] = s;
-    g.ncells *= n;
+    // cells strictly inside the brick cannot hold ghosts (one cell of safety margin per side)
+    g.glo[k] = (int)floor((b.sublo[k] - lo) * g.inv[k]) + 2;
+    g.ghi[k] = (int)floor((b.subhi[k] - lo) * g.inv[k]) - 2;
+  }
+  // tile-major cell numbering: 4x4x4 (3D) or 8x8x1 (2D) cells per tile
+  g.tb[0] = b.dim == 3 ? 2 : 3;
+  g.tb[1] = b.dim == 3 ? 2 : 3;
+  g.tb[2] = b.dim == 3 ? 2 : 0;
+  g.ncells = 1L << (g.tb[0] + g.tb[1] + g.tb[2]);
+  for (int k = 0; k < 3; k++) {
+    g.nt[k] = (g.n[k] + (1 << g.tb[k]) - 1) >> g.tb[k];
+    g.ncells *= g.nt[k];
   }
   if (g.ncells > 2000000000L) return ctx->fail(SPHBVF_EINVAL, "Too many neighbor bins");
   return ensure_cells(ctx, g.ncells);

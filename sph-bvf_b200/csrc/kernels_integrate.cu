@@ -264,9 +264,9 @@ pack_kernel(const DevState d, const __grid_constant__ Coeffs co, const int with_
   const double irho = 1.0 / rho;
   const double P = 7.0 * co.B[t] * (rho / co.rho0[t] - 1.0);
   const double Prr = P * irho * irho;
-  d.pA[i] = make_double4(d.x[i3], d.x[i3 + 1], d.x[i3 + 2], rho);
-  d.pB[i] = make_double4(vx, vy, vz, co.mass[t] * irho);
-  d.pC[i] = make_double4(vx - d.v[i3], vy - d.v[i3 + 1], vz - d.v[i3 + 2], Prr);
+  d.pA[i] = make_rec4(d.x[i3], d.x[i3 + 1], d.x[i3 + 2], rho);
+  d.pB[i] = make_rec4(vx, vy, vz, co.mass[t] * irho);
+  d.pC[i] = make_rec4(vx - d.v[i3], vy - d.v[i3 + 1], vz - d.v[i3 + 2], Prr);
   const int solid = d.solid[i];
   double art = 0.0;
   if (solid) {
@@ -276,7 +276,7 @@ pack_kernel(const DevState d, const __grid_constant__ Coeffs co, const int with_
     art = ts > 0.0 ? -c_art * ts * irho * irho : 0.0;
   }
   const double C0 = co.nspecies ? d.C[(size_t)i * co.nspecies] : 0.0;
-  d.pD[i] = make_double4(d.rhoI[i], art, C0, d.e[i]);
+  d.pD[i] = make_rec4(d.rhoI[i], art, C0, d.e[i]);
   d.pflags[i] = t | (solid << 4) | (d.fixed[i] << 5);
   for (int k = 0; k < co.nspecies; k++) d.pCs[(size_t)i * co.nspecies + k] = d.C[(size_t)i * co.nspecies + k];
   if (with_dev)
@@ -295,7 +295,7 @@ __global__ void ghost_refresh_kernel(const DevState d, const int S, const int wi
   const int o = d.gowner[g];
   if (o < 0) return;   // ghost owned by another rank: filled by the halo exchange
   const int q = d.nlocal + g;
-  double4 A = d.pA[o];
+  Rec4 A = d.pA[o];
   // x + shift evaluated in the reference's order: one rounded add per shifted dimension
   A.x += d.gshift[3 * (size_t)g];
   A.y += d.gshift[3 * (size_t)g + 1];

@@ -41,7 +41,7 @@ __device__ __forceinline__ int cell_of(const Grid &g, double x, double y, double
   const double fx = (x - g.lo[0]) * g.inv[0], fy = (y - g.lo[1]) * g.inv[1], fz = (z - g.lo[2]) * g.inv[2];
   int cx = (int)floor(fx), cy = (int)floor(fy), cz = (int)floor(fz);
   ok = cx >= 0 && cy >= 0 && cz >= 0 && cx < g.n[0] && cy < g.n[1] && cz < g.n[2];
-  return (cz * g.n[1] + cy) * g.n[0] + cx;
+  return ok ? cell_index(g, cx, cy, cz) : 0;
 }
 
 __global__ void pbc_cellid_kernel(const DevState d, const Box b, const Grid g, int *cellid, int *cell_count, int *flags) {
@@ -243,7 +243,7 @@ void launch_fill_images(const DevState &d, const Box &b, double cutghost, const 
 __global__ void ghost_cellid_kernel(const DevState d, const Grid g, const int dim, int *cellid, int *gcell_count, int *flags) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= d.nghost) return;
-  const double4 A = d.pA[d.nlocal + q];
+  const Rec4 A = d.pA[d.nlocal + q];
   bool ok;
   int c = cell_of(g, A.x, A.y, dim == 2 ? g.lo[2] : A.z, ok);
   if (!ok) c = -1;   // beyond the stencil reach of every owned atom: never a neighbour
@@ -261,29 +261,39 @@ __global__ void ghost_scatter_kernel(const DevState d, const int *cellid, const 
 }
 
 void launch_bin_ghosts(const DevState &d, const Grid &g, const NeighWork &w, cudaStream_t st) {
+  if (!d.nghost) return;   // the list build never opens the ghost table then
   cudaMemsetAsync(w.gcell_count, 0, sizeof(int) * (g.ncells + 1), st);
   if (d.nghost) ghost_cellid_kernel<<<nblocks(d.nghost, 256), 256, 0, st>>>(d, g, g.dim, w.cellid, w.gcell_count, w.flags);
   exclusive_scan(w.gcell_count, w.gcell_start, g.ncells + 1, w.scan_tmp, st);
-  if (!d.nghost) return;
   cudaMemsetAsync(w.gcell_count, 0, sizeof(int) * (g.ncells + 1), st);
   ghost_scatter_kernel<<<nblocks(d.nghost, 256), 256, 0, st>>>(d, w.cellid, w.gcell_start, w.gcell_count, w.gorder);
   cell_order_kernel<<<nblocks(g.ncells, 256), 256, 0, st>>>(g.ncells, w.gcell_start, w.gorder);
 }
 
 // ---------------------------------------------------------------- Verlet list
+// One thread per owned atom.  For every (dz, dy) row of the stencil the cells cx-s .. cx+s are
+// visited as at most two contiguous index ranges (cells are x-contiguous inside a tile), so the
+// cell_start table is read twice per segment instead of twice per cell.  Ghosts live in their own
+// cell table and only cells of the ghost shell are looked up there.
+template <bool UNIFORM>
 __global__ void __launch_bounds__(128)
-build_list_kernel(const DevState d, const Grid g, const __grid_constant__ Coeffs co, const int *cell_start,
-                  const int *gcell_start, const int *gorder, const double cutmaxsq, int *flags) {
+build_list_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_constant__ Coeffs co,
+                  const int *__restrict__ cell_start, const int *__restrict__ gcell_start,
+                  const int *__restrict__ gorder, const double cutmaxsq, int *flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.nlocal) return;
-  const double4 Ai = d.pA[i];
+  const Rec4 Ai = d.pA[i];
   const int ti = d.pflags[i] & 7;
   bool ok;
   const int ci = cell_of(g, Ai.x, Ai.y, co.dim == 2 ? g.lo[2] : Ai.z, ok);
-  const int cx = ci % g.n[0], cy = (ci / g.n[0]) % g.n[1], cz = ci / (g.n[0] * g.n[1]);
+  int cx, cy, cz;
+  cell_coords(g, ci, cx, cy, cz);
   const double bsx = 1.0 / g.inv[0], bsy = 1.0 / g.inv[1], bsz = 1.0 / g.inv[2];
+  const int tmask = (1 << g.tb[0]) - 1;
+  const bool have_ghosts = d.nghost > 0;
   int n = 0;
   int *out = d.neigh + i;
+  const int xlo = max(cx - g.s[0], 0), xhi = min(cx + g.s[0], g.n[0] - 1);
   for (int dz = -g.s[2]; dz <= g.s[2]; dz++) {
     const int z = cz + dz;
     if (z < 0 || z >= g.n[2]) continue;
@@ -292,29 +302,40 @@ build_list_kernel(const DevState d, const Grid g, const __grid_constant__ Coeffs
       const int y = cy + dy;
       if (y < 0 || y >= g.n[1]) continue;
       const double ddy = dy > 0 ? (dy - 1) * bsy : (dy < 0 ? (dy + 1) * bsy : 0.0);
-      for (int dx = -g.s[0]; dx <= g.s[0]; dx++) {
-        const int x = cx + dx;
-        if (x < 0 || x >= g.n[0]) continue;
-        const double ddx = dx > 0 ? (dx - 1) * bsx : (dx < 0 ? (dx + 1) * bsx : 0.0);
-        // NStencil::bin_distance prune (nstencil.cpp:204-228)
-        if (!(ddx * ddx + ddy * ddy + ddz * ddz < cutmaxsq)) continue;
-        const int c = (z * g.n[1] + y) * g.n[0] + x;
-        for (int pass = 0; pass < 2; pass++) {
+      // NStencil::bin_distance prune (nstencil.cpp:204-228), applied to the closest cell of the row
+      if (!(ddy * ddy + ddz * ddz < cutmaxsq)) continue;
+      const bool grow = have_ghosts && (y < g.glo[1] || y > g.ghi[1] || z < g.glo[2] || z > g.ghi[2]);
+      for (int x = xlo; x <= xhi;) {
+        const int xe = min(xhi, x | tmask);
+        const int c0 = cell_index(g, x, y, z), c1 = c0 + (xe - x);
+        const bool gseg = have_ghosts && (grow || x < g.glo[0] || xe > g.ghi[0]);
+        for (int pass = 0; pass < (gseg ? 2 : 1); pass++) {
           const int *start = pass ? gcell_start : cell_start;
-          const int a = start[c], b = start[c + 1];
+          const int a = start[c0], b = start[c1 + 1];
           for (int p = a; p < b; p++) {
             const int j = pass ? d.nlocal + gorder[p] : p;
             if (j == i) continue;
-            const double4 Aj = d.pA[j];
+            const Rec4 Aj = d.pA[j];
             const double rsq = rsq_nofma(Ai.x - Aj.x, Ai.y - Aj.y, Ai.z - Aj.z);
-            const int fj = d.pflags[j];
-            const int tj = fj & 7;
-            if (rsq <= co.cutneighsq[ti][tj]) {
-              if (n < d.maxneigh) out[(size_t)n * d.stride] = j | (tj << NEIGH_JBITS) | (((fj >> 4) & 1) << 30);
-              n++;
+            if (UNIFORM) {
+              if (rsq <= cutmaxsq) {
+                if (n < d.maxneigh) {
+                  const int fj = d.pflags[j];
+                  out[(size_t)n * d.stride] = j | ((fj & 7) << NEIGH_JBITS) | (((fj >> 4) & 1) << 30);
+                }
+                n++;
+              }
+            } else {
+              const int fj = d.pflags[j];
+              const int tj = fj & 7;
+              if (rsq <= co.cutneighsq[ti][tj]) {
+                if (n < d.maxneigh) out[(size_t)n * d.stride] = j | (tj << NEIGH_JBITS) | (((fj >> 4) & 1) << 30);
+                n++;
+              }
             }
           }
         }
+        x = xe + 1;
       }
     }
   }
@@ -324,11 +345,17 @@ build_list_kernel(const DevState d, const Grid g, const __grid_constant__ Coeffs
 
 void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const NeighWork &w, cudaStream_t st) {
   double cutmax = 0.0;
+  bool uniform = true;
   for (int i = 1; i <= co.ntypes; i++)
-    for (int j = 1; j <= co.ntypes; j++)
+    for (int j = 1; j <= co.ntypes; j++) {
       if (co.cutneighsq[i][j] > cutmax) cutmax = co.cutneighsq[i][j];
-  if (d.nlocal)
-    build_list_kernel<<<nblocks(d.nlocal, 128), 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
+      if (co.cutneighsq[i][j] != co.cutneighsq[1][1]) uniform = false;
+    }
+  if (!d.nlocal) return;
+  if (uniform)
+    build_list_kernel<true><<<nblocks(d.nlocal, 128), 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
+  else
+    build_list_kernel<false><<<nblocks(d.nlocal, 128), 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
 }
 
 void launch_copy_xhold(const DevState &d, cudaStream_t st) {

@@ -12,28 +12,48 @@
 // loads.  Sweep C (v_weighted_solid / a_weighted_solid) is never consumed and the
 // random stress term is omitted (reference seed is clock(); exactly zero in all decks with e=0).
 //
-// Mapping: one thread per owned atom, 128-thread CTAs.  Neighbour entries are read transposed
-// (coalesced), neighbour state through three 32-byte records; all per-particle divisions were
-// moved to the pack kernel (V = m/rho, P/rho^2), the loop body is divide-free except for species.
+// Mapping: one thread per owned atom, 128-thread CTAs, atoms in tile-major cell order so a CTA
+// covers a compact cube.  The kernel is FP64-pipe / latency bound, not HBM bound (ncu, profiles/):
+//   * the neighbour loop is software pipelined by hand: while neighbour k is evaluated, the three
+//     32-byte records of neighbour k+1 (one 256-bit LDG each) and the list entry k+2 are in
+//     flight, so an L2 round trip is overlapped with ~75 FP64 instructions of useful work;
+//   * list entries are read transposed (coalesced) and carry type_j and solid_tag_j, so the hot
+//     loop has no flag gather;
+//   * every per-particle division lives in the pack kernel (V = m/rho, P/rho^2), sqrt is a
+//     branch-free Goldschmidt iteration on MUFU.RSQ64H (7 FP64 ops, < 1 ulp);
+//   * per-type-pair coefficients: when every type pair shares h, eta and mass (all cavity decks
+//     and the synthetic lattice) they are kernel-argument constants; otherwise rows of a small
+//     shared-memory table (conflict-free broadcast) instead of divergent constant-bank reads.
+#include <string.h>
+
 #include "sphbvf_internal.cuh"
 
 namespace sphbvf {
 
+// resident CTAs per SM the pair kernel is compiled for: 3 -> 168 registers (no spills), 4 -> 128
+#ifndef PAIR_MINB
+#define PAIR_MINB 3
+#endif
+
+// one row per (type_i, type_j); 8 doubles = 64 B so a row is two LDS.128 x2
+struct __align__(16) PairRow {
+  double cutsq, h, cwfd, cwf;      // h^2, h, (1/r)dW/dr = cwfd (h-r)^2, W = cwf (h-r)^3 (h+3r)
+  double mimj, eta, iwdelta, h2eps;  // m_i m_j, eta, 1/W(delta), 0.01 h^2
+};
+
 struct PairTables {
-  double cwfd[MAXT][MAXT];   // (1/r) dW/dr = cwfd * (h-r)^2
-  double cwf[MAXT][MAXT];    // W = cwf * (h-r)^3 * (h+3r)
-  double iwdelta[MAXT][MAXT];  // 1 / W(delta)
+  PairRow row[MAXT * MAXT];
   double cwfdc[MAXT][MAXT];  // same as cwfd with h = cutc
-  double h2eps[MAXT][MAXT];  // 0.01 h^2
   double hc2eps[MAXT][MAXT]; // 0.01 cutc^2
-  double mimj[MAXT][MAXT];
   double mred2[MAXT][MAXT];  // 2 mi mj / (mi + mj)
   double geff[MAXT][MAXT];   // 2 Gi Gj / (Gi + Gj + 1e-12)
   double imass[MAXT];
 };
 
-static void make_tables(const Coeffs &co, PairTables &t) {
+static bool make_tables(const Coeffs &co, PairTables &t) {
   const double delta_fac = co.variant == SPHBVF_TV ? (1.0 / 2.6) : (1.0 / 3.0);
+  memset(&t, 0, sizeof t);
+  bool uniform = true;
   for (int i = 1; i <= co.ntypes; i++) {
     t.imass[i] = 1.0 / co.mass[i];
     for (int j = 1; j <= co.ntypes; j++) {
@@ -47,39 +67,73 @@ static void make_tables(const Coeffs &co, PairTables &t) {
           cwf = 1.591549430918954 * ihsq * ihsq * ihsq;
         }
       };
+      PairRow &r = t.row[i * MAXT + j];
       double h = co.cut[i][j], hc = co.cutc[i][j], dummy;
-      coef(h, t.cwfd[i][j], t.cwf[i][j]);
+      coef(h, r.cwfd, r.cwf);
       coef(hc > 0 ? hc : h, t.cwfdc[i][j], dummy);
       double delta = delta_fac * h, td = h - delta;
-      double wdelta = t.cwf[i][j] * td * td * td * (h + 3. * delta);
-      t.iwdelta[i][j] = 1.0 / wdelta;
-      t.h2eps[i][j] = 0.01 * h * h;
+      double wdelta = r.cwf * td * td * td * (h + 3. * delta);
+      r.cutsq = co.cutsq[i][j];
+      r.h = h;
+      r.iwdelta = 1.0 / wdelta;
+      r.h2eps = 0.01 * h * h;
+      r.mimj = co.mass[i] * co.mass[j];
+      r.eta = co.eta[i][j];
       t.hc2eps[i][j] = 0.01 * hc * hc;
-      t.mimj[i][j] = co.mass[i] * co.mass[j];
       t.mred2[i][j] = 2.0 * ((co.mass[i] * co.mass[j]) / (co.mass[i] + co.mass[j]));
       t.geff[i][j] = (2.0 * co.G0[i] * co.G0[j]) / (co.G0[i] + co.G0[j] + 1e-12);
+      const PairRow &r11 = t.row[MAXT + 1];
+      if (r.cutsq != r11.cutsq || r.h != r11.h || r.mimj != r11.mimj || r.eta != r11.eta) uniform = false;
     }
   }
+  return uniform;
+}
+
+// sqrt(x) for x > 0: MUFU.RSQ64H seed (2^-22.9) + two coupled Goldschmidt steps, branch free
+__device__ __forceinline__ double fast_sqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  return fma(g, r, g);
+}
+
+// 1/x for normal x: MUFU.RCP64H seed + two Newton steps (no slow-path call, ~1 ulp)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
 }
 
 // SOLIDS: 0 = no atom has solid_tag, 1 = solids whose deviatoric stress is identically zero
 // (rigid walls: G0 == 0, dev == 0), 2 = elastic solids (deviatoric tensors gathered)
-template <int VARIANT, bool SPECIES, int SOLIDS>
-__global__ void __launch_bounds__(128)
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER>
+__global__ void __launch_bounds__(128, PAIR_MINB)
 pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
-            const int filter, const double damp) {
+            const double damp) {
+  __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
+  if (!UNIFORM) {
+    for (int q = threadIdx.x; q < MAXT * MAXT; q += blockDim.x) srow[q] = tb.row[q];
+    __syncthreads();
+  }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.nlocal) return;
 
   const int fl = d.pflags[i];
   const int ti = fl & 7;
   const bool si = SOLIDS && ((fl >> 4) & 1);
-  const double4 Ai = d.pA[i], Bi = d.pB[i], Ci = d.pC[i];
+  const Rec4 Ai = d.pA[i], Bi = d.pB[i], Ci = d.pC[i];
   const double rhoi = Ai.w, Vi = Bi.w, Vi2 = Vi * Vi, Prri = Ci.w;
-  const double ddvc = 10.0 * 7.0 * co.B[ti];
   const double c0i = co.c0[ti];
-  double Pi = Prri * rhoi * rhoi;
-  double irhoi = Vi * tb.imass[ti];
+  const double Pi = Prri * rhoi * rhoi;
+  const double irhoi = Vi * tb.imass[ti];
+  const PairRow *myrow = srow + (UNIFORM ? 0 : ti * MAXT);
 
   double devi[9];
   double arti = 0.0;        // scalar artificial stress when dev == 0
@@ -116,24 +170,29 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
 #pragma unroll
     for (int k = 0; k < MAXS; k++) Qs[k] = 0.0;
 
-  const int nn = d.numneigh[i];
-  const int *np = d.neigh + i;
-  for (int kk = 0; kk < nn; kk++) {
-    const int ent = __ldg(np + (size_t)kk * d.stride);
+  // ------------------------------------------------------------------ one neighbour
+  auto body = [&](const int ent, const Rec4 &Aj, const Rec4 &Bj, const Rec4 &Cj) {
     const int j = ent & NEIGH_JMASK;
     const int tj = (ent >> NEIGH_JBITS) & 7;
     const bool sj = SOLIDS && ((ent >> 30) & 1);
-    const double4 Aj = d.pA[j];
     const double delx = Ai.x - Aj.x, dely = Ai.y - Aj.y, delz = Ai.z - Aj.z;
     const double rsq = delx * delx + dely * dely + delz * delz;
-    if (!(rsq < co.cutsq[ti][tj])) continue;
+    double cutsq, h, cwfd, cwf, mm, eta;
+    if (UNIFORM) {
+      const PairRow &r = tb.row[MAXT + 1];
+      cutsq = r.cutsq; h = r.h; cwfd = r.cwfd; cwf = r.cwf; mm = r.mimj; eta = r.eta;
+    } else {
+      const PairRow &r = myrow[tj];
+      cutsq = r.cutsq; h = r.h; cwfd = r.cwfd; cwf = r.cwf; mm = r.mimj; eta = r.eta;
+    }
+    if (!(rsq < cutsq)) return;
+    const double iwdelta = UNIFORM ? tb.row[MAXT + 1].iwdelta : myrow[tj].iwdelta;
+    const double h2eps = UNIFORM ? tb.row[MAXT + 1].h2eps : myrow[tj].h2eps;
 
-    const double4 Bj = d.pB[j], Cj = d.pC[j];
-    const double h = co.cut[ti][tj];
-    const double r = sqrt(rsq);
+    const double r = fast_sqrt(fmax(rsq, 1e-300));
     const double t = h - r, t2 = t * t;
-    const double wfd = tb.cwfd[ti][tj] * t2;
-    const double wf = tb.cwf[ti][tj] * t2 * t * (h + 3. * r);
+    const double wfd = cwfd * t2;
+    const double wf = cwf * t2 * t * (h + 3. * r);
     const double rhoj = Aj.w, Vj = Bj.w, Vj2 = Vj * Vj, Prrj = Cj.w;
     const double velx = Bi.x - Bj.x, vely = Bi.y - Bj.y, velz = Bi.z - Bj.z;
     const double dvr = delx * velx + dely * vely + delz * velz;
@@ -142,21 +201,17 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     const double S2 = Vi2 + Vj2;
     const double S2w = S2 * wfd;
 
-    // ---- sweep A (pair_...transport_velocity.cpp:243-254)
-    nd += Vj2 * wf;
+    // ---- sweep A (pair_...transport_velocity.cpp:243-254); ddv is scaled by 70 B_i at the end
+    const double Vj2w = Vj2 * wf;
+    nd += Vj2w;
     rA2 += wf;
-    if (filter) rA1 += d.pD[j].x * wf;
-    {
-      const double cc = ddvc * S2w;
-      ddvx += cc * delx; ddvy += cc * dely; ddvz += cc * delz;
-    }
+    if (FILTER) rA1 += d.pD[j].x * wf;
+    ddvx += S2w * delx; ddvy += S2w * dely; ddvz += S2w * delz;
     if (VARIANT != SPHBVF_TV) {   // ..._mechanics.cpp:250-252
-      const double cc = -Vj2 * wf;
-      ddxx += cc * velx; ddxy += cc * vely; ddxz += cc * velz;
+      ddxx -= Vj2w * velx; ddxy -= Vj2w * vely; ddxz -= Vj2w * velz;
     }
 
     // ---- pressure force (:396-399 / mechanics :408)
-    const double mm = tb.mimj[ti][tj];
     const double mmw = mm * wfd;
     const double pij = Prrj + Prri;
     double fpair;
@@ -165,15 +220,12 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
 
     // ---- artificial stress (:454-494)
     double fartx = 0, farty = 0, fartz = 0;
-    if (SOLIDS) {
+    if (SOLIDS == 1) {
       if (si || sj) {
-        const double q = wf * tb.iwdelta[ti][tj], q2 = q * q;
-        const double pre = mmw * q2 * q2;
-        if (SOLIDS == 1) {
-          const double artj = sj ? d.pD[j].y : 0.0;
-          const double cc = pre * (arti + artj);
-          fartx = cc * delx; farty = cc * dely; fartz = cc * delz;
-        }
+        const double q = wf * iwdelta, q2 = q * q;
+        const double artj = sj ? d.pD[j].y : 0.0;
+        const double cc = mmw * q2 * q2 * (arti + artj);
+        fartx = cc * delx; farty = cc * dely; fartz = cc * delz;
       }
     }
 
@@ -185,7 +237,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
         for (int k = 0; k < 9; k++) devj[k] = sj ? d.pdev[9 * (size_t)j + k] : 0.0;
         const double Pj = Prrj * rhoj * rhoj;
         const double Psj = VARIANT == SPHBVF_MECHANICS ? fabs(Pj) : Pj;
-        const double q = wf * tb.iwdelta[ti][tj], q2 = q * q;
+        const double q = wf * iwdelta, q2 = q * q;
         const double pre = mmw * q2 * q2;
         double R[9];
 #pragma unroll
@@ -233,17 +285,17 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
 
     // ---- momentum (:497-529)
     if (!si) {
-      const double fvisc = S2w * co.eta[ti][tj];
+      const double fvisc = S2w * eta;
       const double s = -0.5 * S2w;
-      const double pi_ = rhoi * ai, pj_ = rhoj * aj;
-      fx += -delx * fpair + fvisc * velx + s * (pi_ * Bi.x + pj_ * Bj.x) + fartx;
-      fy += -dely * fpair + fvisc * vely + s * (pi_ * Bi.y + pj_ * Bj.y) + farty;
-      fz += -delz * fpair + fvisc * velz + s * (pi_ * Bi.z + pj_ * Bj.z) + fartz;
+      const double pi_ = s * (rhoi * ai), pj_ = s * (rhoj * aj);
+      fx += fvisc * velx - delx * fpair + (pi_ * Bi.x + pj_ * Bj.x) + fartx;
+      fy += fvisc * vely - dely * fpair + (pi_ * Bi.y + pj_ * Bj.y) + farty;
+      fz += fvisc * velz - delz * fpair + (pi_ * Bi.z + pj_ * Bj.z) + fartz;
     } else {
       double fviscs = 0.;
       if (dvr < 0.) {
-        const double mu = h * dvr / (rsq + tb.h2eps[ti][tj]);
-        fviscs = mmw * (-(c0i + co.c0[tj]) * mu + 2.0 * mu * mu) / (rhoi + rhoj);
+        const double mu = h * dvr * fast_rcp(rsq + h2eps);
+        fviscs = mmw * (-(c0i + co.c0[tj]) * mu + 2.0 * mu * mu) * fast_rcp(rhoi + rhoj);
       }
       const double cc = -(fpair + fviscs);
       fx += cc * delx + fartx;
@@ -262,13 +314,13 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     {
       double inner = rhoi * (dvr - ai + aj) - (rhoi * ai + rhoj * aj);
       if (VARIANT == SPHBVF_FSI)
-        inner -= damp * 2.0 * h * c0i * (rhoj - rhoi) * (rsq / (rsq + tb.h2eps[ti][tj]));
+        inner -= damp * 2.0 * h * c0i * (rhoj - rhoi) * (rsq / (rsq + h2eps));
       drho += wfd * Vj * inner;
     }
 
     // ---- BVF (:563-576)
     if (SOLIDS && !si && sj) {
-      phi += Vj2 * wf;
+      phi += Vj2w;
       const double cc = wfd * Vj2;
       nwx += cc * delx; nwy += cc * dely; nwz += cc * delz;
     }
@@ -289,8 +341,40 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
         }
       }
     }
+  };
+
+  // ------------------------------------------------------------------ pipelined traversal
+  // entry k+2 and the records of neighbour k+1 are requested before neighbour k is evaluated
+  const int nn = d.numneigh[i];
+  const int *np = d.neigh + i;
+  const size_t stride = d.stride;
+  int e0 = nn > 0 ? __ldg(np) : 0;
+  int e1 = nn > 1 ? __ldg(np + stride) : 0;
+  np += 2 * stride;
+  Rec4 A0, B0, C0, A1, B1, C1;
+  {
+    const int j = e0 & NEIGH_JMASK;
+    A0 = d.pA[j]; B0 = d.pB[j]; C0 = d.pC[j];
+  }
+  for (int kk = 0; kk < nn; kk += 2) {
+    {
+      const int j = e1 & NEIGH_JMASK;
+      A1 = d.pA[j]; B1 = d.pB[j]; C1 = d.pC[j];
+    }
+    const int e2 = kk + 2 < nn ? __ldg(np) : 0;
+    body(e0, A0, B0, C0);
+    {
+      const int j = e2 & NEIGH_JMASK;
+      A0 = d.pA[j]; B0 = d.pB[j]; C0 = d.pC[j];
+    }
+    const int e3 = kk + 3 < nn ? __ldg(np + stride) : 0;
+    np += 2 * stride;
+    if (kk + 1 < nn) body(e1, A1, B1, C1);
+    e0 = e2;
+    e1 = e3;
   }
 
+  const double ddvc = 10.0 * 7.0 * co.B[ti];
   const size_t i3 = 3 * (size_t)i;
   d.f[i3] = fx; d.f[i3 + 1] = fy; d.f[i3 + 2] = fz;
   d.drho[i] = drho;
@@ -299,7 +383,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   d.rhoAux2[i] = rA2;
   d.phi[i] = phi;
   d.nw[i3] = nwx; d.nw[i3 + 1] = nwy; d.nw[i3 + 2] = nwz;
-  d.ddv[i3] = ddvx; d.ddv[i3 + 1] = ddvy; d.ddv[i3 + 2] = ddvz;
+  d.ddv[i3] = ddvc * ddvx; d.ddv[i3 + 1] = ddvc * ddvy; d.ddv[i3 + 2] = ddvc * ddvz;
   if (VARIANT != SPHBVF_TV) {
     d.ddx[i3] = ddxx; d.ddx[i3 + 1] = ddxy; d.ddx[i3 + 2] = ddxz;
     d.Pnew[i] = Pi;   // pair_ssa_tsdpd_bvf_mechanics.cpp:188
@@ -311,32 +395,44 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     for (int k = 0; k < co.nspecies; k++) d.Q[(size_t)i * co.nspecies + k] = Qs[k];
 }
 
-template <int VARIANT, bool SPECIES>
-static void launch_solids(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf,
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM>
+static void launch_filter(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf,
                           cudaStream_t st) {
   const int threads = 128;
   const int blocks = (d.nlocal + threads - 1) / threads;
-  if (blocks == 0) return;
+  if (pf.filter_step) pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, true><<<blocks, threads, 0, st>>>(d, co, tb, pf.damp);
+  else pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, false><<<blocks, threads, 0, st>>>(d, co, tb, pf.damp);
+}
+
+template <int VARIANT, bool SPECIES>
+static void launch_solids(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf,
+                          bool uniform, cudaStream_t st) {
+  if (d.nlocal == 0) return;
   const int solids = !pf.any_solid ? 0 : (pf.with_dev ? 2 : 1);
-  if (solids == 0) pair_kernel<VARIANT, SPECIES, 0><<<blocks, threads, 0, st>>>(d, co, tb, pf.filter_step, pf.damp);
-  else if (solids == 1) pair_kernel<VARIANT, SPECIES, 1><<<blocks, threads, 0, st>>>(d, co, tb, pf.filter_step, pf.damp);
-  else pair_kernel<VARIANT, SPECIES, 2><<<blocks, threads, 0, st>>>(d, co, tb, pf.filter_step, pf.damp);
+  // the constant-coefficient fast path is instantiated for the rigid-wall / no-solid cases only
+  if (solids == 0) {
+    if (uniform) launch_filter<VARIANT, SPECIES, 0, true>(d, co, tb, pf, st);
+    else launch_filter<VARIANT, SPECIES, 0, false>(d, co, tb, pf, st);
+  } else if (solids == 1) {
+    if (uniform) launch_filter<VARIANT, SPECIES, 1, true>(d, co, tb, pf, st);
+    else launch_filter<VARIANT, SPECIES, 1, false>(d, co, tb, pf, st);
+  } else launch_filter<VARIANT, SPECIES, 2, false>(d, co, tb, pf, st);
 }
 
 template <int VARIANT>
 static void launch_species(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf,
-                           cudaStream_t st) {
-  if (co.nspecies > 0) launch_solids<VARIANT, true>(d, co, tb, pf, st);
-  else launch_solids<VARIANT, false>(d, co, tb, pf, st);
+                           bool uniform, cudaStream_t st) {
+  if (co.nspecies > 0) launch_solids<VARIANT, true>(d, co, tb, pf, uniform, st);
+  else launch_solids<VARIANT, false>(d, co, tb, pf, uniform, st);
 }
 
 void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, cudaStream_t st) {
   PairTables tb;
-  make_tables(co, tb);
+  const bool uniform = make_tables(co, tb);
   switch (co.variant) {
-    case SPHBVF_TV: launch_species<SPHBVF_TV>(d, co, tb, pf, st); break;
-    case SPHBVF_MECHANICS: launch_species<SPHBVF_MECHANICS>(d, co, tb, pf, st); break;
-    default: launch_species<SPHBVF_FSI>(d, co, tb, pf, st); break;
+    case SPHBVF_TV: launch_species<SPHBVF_TV>(d, co, tb, pf, uniform, st); break;
+    case SPHBVF_MECHANICS: launch_species<SPHBVF_MECHANICS>(d, co, tb, pf, uniform, st); break;
+    default: launch_species<SPHBVF_FSI>(d, co, tb, pf, uniform, st); break;
   }
 }
 
