@@ -13,6 +13,8 @@
 // interacting pairs is the reference's: rsq <= cutneighsq[itype][jtype] at rebuild time, with rsq
 // evaluated without FMA contraction in the reference's operation order, so the lists compare
 // bit-exactly as sorted tag pairs.
+#include <stdlib.h>
+
 #include "sphbvf_internal.cuh"
 
 namespace sphbvf {
@@ -275,8 +277,16 @@ void launch_bin_ghosts(const DevState &d, const Grid &g, const NeighWork &w, cud
 // visited as at most two contiguous index ranges (cells are x-contiguous inside a tile), so the
 // cell_start table is read twice per segment instead of twice per cell.  Ghosts live in their own
 // cell table and only cells of the ghost shell are looked up there.
-template <bool UNIFORM>
-__global__ void __launch_bounds__(128)
+// Entry order: the pair kernel gathers three 32-byte records per entry, and the 32 lanes of a
+// warp do so for 32 different atoms j at once.  A record sits at offset 32*(j mod 4) of its
+// 128-byte line, and the L1 data stage serialises lanes that hit the same 32-byte slice of
+// different lines.  The entries of each atom are therefore emitted so that entry k of lane l has
+// (j mod 4) == (l + k) mod 4 whenever the atom still has such a neighbour: every gather then
+// spreads its lanes evenly over the four slices (ncu: l1tex data-pipe wavefronts, profiles/).
+constexpr int LIST_CAP = 192;   // entries per atom ordered this way; any beyond keep traversal order
+
+template <bool UNIFORM, bool BALANCE>
+__global__ void __launch_bounds__(128, 6)
 build_list_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_constant__ Coeffs co,
                   const int *__restrict__ cell_start, const int *__restrict__ gcell_start,
                   const int *__restrict__ gorder, const double cutmaxsq, int *flags) {
@@ -288,25 +298,45 @@ build_list_kernel(const DevState d, const __grid_constant__ Grid g, const __grid
   const int ci = cell_of(g, Ai.x, Ai.y, co.dim == 2 ? g.lo[2] : Ai.z, ok);
   int cx, cy, cz;
   cell_coords(g, ci, cx, cy, cz);
-  const double bsx = 1.0 / g.inv[0], bsy = 1.0 / g.inv[1], bsz = 1.0 / g.inv[2];
+  const double bsy = 1.0 / g.inv[1], bsz = 1.0 / g.inv[2];
   const int tmask = (1 << g.tb[0]) - 1;
   const bool have_ghosts = d.nghost > 0;
   int n = 0;
   int *out = d.neigh + i;
+  int loc[LIST_CAP];
+  int cnt[4] = {0, 0, 0, 0};
+  auto emit = [&](int ent) {
+    if (BALANCE && n < LIST_CAP) {
+      loc[n] = ent;
+      cnt[ent & 3]++;
+    } else if (n < d.maxneigh) out[(size_t)n * d.stride] = ent;
+    n++;
+  };
   const int xlo = max(cx - g.s[0], 0), xhi = min(cx + g.s[0], g.n[0] - 1);
+  const double xi = Ai.x, yi = Ai.y, zi = co.dim == 2 ? g.lo[2] : Ai.z;
+  const double cutpad = cutmaxsq * (1.0 + 1e-10);
   for (int dz = -g.s[2]; dz <= g.s[2]; dz++) {
     const int z = cz + dz;
     if (z < 0 || z >= g.n[2]) continue;
-    const double ddz = dz > 0 ? (dz - 1) * bsz : (dz < 0 ? (dz + 1) * bsz : 0.0);
+    // distance from the atom to the slab of cells z (0 inside); NStencil::bin_distance
+    // (nstencil.cpp:204-228) measures from the atom's CELL, this prunes from the atom itself
+    const double zc = g.lo[2] + z * bsz;
+    const double ddz = fmax(0.0, fmax(zc - zi, zi - (zc + bsz)));
     for (int dy = -g.s[1]; dy <= g.s[1]; dy++) {
       const int y = cy + dy;
       if (y < 0 || y >= g.n[1]) continue;
-      const double ddy = dy > 0 ? (dy - 1) * bsy : (dy < 0 ? (dy + 1) * bsy : 0.0);
-      // NStencil::bin_distance prune (nstencil.cpp:204-228), applied to the closest cell of the row
-      if (!(ddy * ddy + ddz * ddz < cutmaxsq)) continue;
+      const double yc = g.lo[1] + y * bsy;
+      const double ddy = fmax(0.0, fmax(yc - yi, yi - (yc + bsy)));
+      const double rem = cutpad - ddy * ddy - ddz * ddz;
+      if (!(rem > 0.0)) continue;
+      // cells of this row that can hold an atom within the cutoff: same floor() map as cell_of,
+      // which is monotone, so the range is a superset whatever the rounding
+      const double rx = sqrt(rem);
+      const int xa = max(xlo, (int)floor((xi - rx - g.lo[0]) * g.inv[0]));
+      const int xb = min(xhi, (int)floor((xi + rx - g.lo[0]) * g.inv[0]));
       const bool grow = have_ghosts && (y < g.glo[1] || y > g.ghi[1] || z < g.glo[2] || z > g.ghi[2]);
-      for (int x = xlo; x <= xhi;) {
-        const int xe = min(xhi, x | tmask);
+      for (int x = xa; x <= xb;) {
+        const int xe = min(xb, x | tmask);
         const int c0 = cell_index(g, x, y, z), c1 = c0 + (xe - x);
         const bool gseg = have_ghosts && (grow || x < g.glo[0] || xe > g.ghi[0]);
         for (int pass = 0; pass < (gseg ? 2 : 1); pass++) {
@@ -319,19 +349,13 @@ build_list_kernel(const DevState d, const __grid_constant__ Grid g, const __grid
             const double rsq = rsq_nofma(Ai.x - Aj.x, Ai.y - Aj.y, Ai.z - Aj.z);
             if (UNIFORM) {
               if (rsq <= cutmaxsq) {
-                if (n < d.maxneigh) {
-                  const int fj = d.pflags[j];
-                  out[(size_t)n * d.stride] = j | ((fj & 7) << NEIGH_JBITS) | (((fj >> 4) & 1) << 30);
-                }
-                n++;
+                const int fj = d.pflags[j];
+                emit(j | ((fj & 7) << NEIGH_JBITS) | (((fj >> 4) & 1) << 30));
               }
             } else {
               const int fj = d.pflags[j];
               const int tj = fj & 7;
-              if (rsq <= co.cutneighsq[ti][tj]) {
-                if (n < d.maxneigh) out[(size_t)n * d.stride] = j | (tj << NEIGH_JBITS) | (((fj >> 4) & 1) << 30);
-                n++;
-              }
+              if (rsq <= co.cutneighsq[ti][tj]) emit(j | (tj << NEIGH_JBITS) | (((fj >> 4) & 1) << 30));
             }
           }
         }
@@ -341,6 +365,34 @@ build_list_kernel(const DevState d, const __grid_constant__ Grid g, const __grid
   }
   d.numneigh[i] = n < d.maxneigh ? n : d.maxneigh;
   atomicMax(&flags[2], n);
+  if (!BALANCE) return;
+  // counting sort of the staged entries by (j mod 4), then slice-balanced emission
+  const int m = n < LIST_CAP ? n : LIST_CAP;
+  const int mo = m < d.maxneigh ? m : d.maxneigh;
+  int srt[LIST_CAP];
+  int off[4] = {0, cnt[0], cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]};
+  int end[4] = {off[1], off[2], off[3], m};
+  {
+    int cur[4] = {off[0], off[1], off[2], off[3]};
+    for (int k = 0; k < m; k++) {
+      const int e = loc[k], c = e & 3;
+      const int pos = c == 0 ? cur[0]++ : (c == 1 ? cur[1]++ : (c == 2 ? cur[2]++ : cur[3]++));
+      srt[pos] = e;
+    }
+  }
+  const int lane = threadIdx.x & 3;
+  for (int k = 0; k < mo; k++) {
+    int e = 0;
+    bool got = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int c = (lane + k + q) & 3;
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++)
+        if (!got && c == cc && off[cc] < end[cc]) { e = srt[off[cc]++]; got = true; }
+    }
+    out[(size_t)k * d.stride] = e;
+  }
 }
 
 void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const NeighWork &w, cudaStream_t st) {
@@ -352,10 +404,12 @@ void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const
       if (co.cutneighsq[i][j] != co.cutneighsq[1][1]) uniform = false;
     }
   if (!d.nlocal) return;
-  if (uniform)
-    build_list_kernel<true><<<nblocks(d.nlocal, 128), 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
-  else
-    build_list_kernel<false><<<nblocks(d.nlocal, 128), 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
+  static const int balance = [] { const char *e = getenv("SPHBVF_SLICE_ORDER"); return e ? atoi(e) : 0; }();
+  const int nb = nblocks(d.nlocal, 128);
+#define BL(U, B) build_list_kernel<U, B><<<nb, 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags)
+  if (uniform) { if (balance) BL(true, true); else BL(true, false); }
+  else { if (balance) BL(false, true); else BL(false, false); }
+#undef BL
 }
 
 void launch_copy_xhold(const DevState &d, cudaStream_t st) {

@@ -111,6 +111,13 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(y, e, y);
 }
 
+constexpr int RING = 12;  // list-entry prefetch depth (rows); even
+
+__device__ __forceinline__ void cp_async4(int *smem_dst, const int *gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+
 // SOLIDS: 0 = no atom has solid_tag, 1 = solids whose deviatoric stress is identically zero
 // (rigid walls: G0 == 0, dev == 0), 2 = elastic solids (deviatoric tensors gathered)
 template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER>
@@ -118,6 +125,7 @@ __global__ void __launch_bounds__(128, PAIR_MINB)
 pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
             const double damp) {
   __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
+  __shared__ int ring[RING][128];
   if (!UNIFORM) {
     for (int q = threadIdx.x; q < MAXT * MAXT; q += blockDim.x) srow[q] = tb.row[q];
     __syncthreads();
@@ -139,7 +147,9 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   double arti = 0.0;        // scalar artificial stress when dev == 0
   double Ri[9];             // artificial stress tensor when dev != 0
   const double c_art = VARIANT == SPHBVF_FSI ? 0.1 : 0.35;
-  if (SOLIDS == 1) arti = d.pD[i].y;
+  // stress-free solid (dev == 0): R = -c_art max(0, -Psigma)/rho^2 = c_art P/rho^2 where P < 0 (TV, fsi);
+  // mechanics uses |P| (:471,487) so the bracket is never positive
+  if (SOLIDS == 1) arti = (si && VARIANT != SPHBVF_MECHANICS && Prri < 0.0) ? c_art * Prri : 0.0;
   if (SOLIDS == 2) {
 #pragma unroll
     for (int k = 0; k < 9; k++) devi[k] = si ? d.pdev[9 * (size_t)i + k] : 0.0;
@@ -189,7 +199,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     const double iwdelta = UNIFORM ? tb.row[MAXT + 1].iwdelta : myrow[tj].iwdelta;
     const double h2eps = UNIFORM ? tb.row[MAXT + 1].h2eps : myrow[tj].h2eps;
 
-    const double r = fast_sqrt(fmax(rsq, 1e-300));
+    const double r = fast_sqrt(rsq + 1e-300);   // rsq == 0 (coincident atoms) must not give NaN
     const double t = h - r, t2 = t * t;
     const double wfd = cwfd * t2;
     const double wf = cwf * t2 * t * (h + 3. * r);
@@ -223,7 +233,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     if (SOLIDS == 1) {
       if (si || sj) {
         const double q = wf * iwdelta, q2 = q * q;
-        const double artj = sj ? d.pD[j].y : 0.0;
+        const double artj = (sj && VARIANT != SPHBVF_MECHANICS && Prrj < 0.0) ? c_art * Prrj : 0.0;
         const double cc = mmw * q2 * q2 * (arti + artj);
         fartx = cc * delx; farty = cc * dely; fartz = cc * delz;
       }
@@ -344,13 +354,24 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   };
 
   // ------------------------------------------------------------------ pipelined traversal
-  // entry k+2 and the records of neighbour k+1 are requested before neighbour k is evaluated
+  // List entries stream from DRAM (4 B per neighbour, read once): each thread copies its own
+  // entries RING rows ahead into a shared-memory ring with cp.async (no registers, no barrier:
+  // a thread only ever reads the slots it wrote).  The records of neighbour k+1 are requested
+  // before neighbour k is evaluated.
   const int nn = d.numneigh[i];
   const int *np = d.neigh + i;
   const size_t stride = d.stride;
-  int e0 = nn > 0 ? __ldg(np) : 0;
-  int e1 = nn > 1 ? __ldg(np + stride) : 0;
-  np += 2 * stride;
+  int *myring = &ring[0][threadIdx.x];
+  auto fetch2 = [&](int k) {   // entries k, k+1 -> ring slots k % RING, (k+1) % RING; one group
+    if (k < nn) cp_async4(myring + (k % RING) * 128, np + (size_t)k * stride);
+    if (k + 1 < nn) cp_async4(myring + ((k + 1) % RING) * 128, np + (size_t)(k + 1) * stride);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int k = 0; k < RING; k += 2) fetch2(k);
+  asm volatile("cp.async.wait_group %0;" ::"n"(RING / 2 - 2) : "memory");   // entries 0..3 landed
+  int e0 = nn > 0 ? myring[0] : 0;
+  int e1 = nn > 1 ? myring[128] : 0;
   Rec4 A0, B0, C0, A1, B1, C1;
   {
     const int j = e0 & NEIGH_JMASK;
@@ -361,14 +382,15 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
       const int j = e1 & NEIGH_JMASK;
       A1 = d.pA[j]; B1 = d.pB[j]; C1 = d.pC[j];
     }
-    const int e2 = kk + 2 < nn ? __ldg(np) : 0;
+    fetch2(kk + RING);   // slots of entries kk, kk+1: already in e0, e1
+    asm volatile("cp.async.wait_group %0;" ::"n"(RING / 2 - 2) : "memory");   // entries <= kk+5 landed
+    const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * 128] : 0;
+    const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * 128] : 0;
     body(e0, A0, B0, C0);
     {
       const int j = e2 & NEIGH_JMASK;
       A0 = d.pA[j]; B0 = d.pB[j]; C0 = d.pC[j];
     }
-    const int e3 = kk + 3 < nn ? __ldg(np + stride) : 0;
-    np += 2 * stride;
     if (kk + 1 < nn) body(e1, A1, B1, C1);
     e0 = e2;
     e1 = e3;
