@@ -159,6 +159,10 @@ int sphbvf_comm_unique_id(void *id128);       /* ncclGetUniqueId; rank 0 broadca
 int sphbvf_comm_init(sphbvf_ctx *ctx, const void *id128);
 /* host-side brick plan, usable without a GPU: sub-domain of `rank` in `procgrid` */
 int sphbvf_brick_bounds(const sphbvf_config *cfg, int rank, double sublo[3], double subhi[3]);
+/* host-side halo plan, usable without a GPU (CommBrick::setup, comm_brick.cpp:161-410): for each
+ * of the 27 directions code = (dx+1) + 3 (dy+1) + 9 (dz+1) the rank owning the adjacent brick
+ * (-1 = none) and the periodic shift [27][3] added to positions sent in that direction */
+int sphbvf_comm_plan(const sphbvf_config *cfg, int rank, int *peer, double *shift);
 /* procmap.cpp-style factorisation of nranks into a grid minimising brick surface */
 int sphbvf_proc_grid(int nranks, int dim, const double prd[3], int grid[3]);
 

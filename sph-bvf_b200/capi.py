@@ -38,7 +38,8 @@ SYMBOLS = ["sphbvf_version", "sphbvf_device_count", "sphbvf_create", "sphbvf_des
            "sphbvf_post_force", "sphbvf_final_integrate", "sphbvf_end_of_step", "sphbvf_build_neighbors",
            "sphbvf_nlocal", "sphbvf_nghost", "sphbvf_ntimestep", "sphbvf_nbuilds", "sphbvf_ndanger",
            "sphbvf_get_pairs", "sphbvf_sync", "sphbvf_launch_count", "sphbvf_set_profiling", "sphbvf_kernel_ms",
-           "sphbvf_stream", "sphbvf_comm_unique_id", "sphbvf_comm_init", "sphbvf_brick_bounds", "sphbvf_proc_grid"]
+           "sphbvf_stream", "sphbvf_comm_unique_id", "sphbvf_comm_init", "sphbvf_brick_bounds", "sphbvf_proc_grid",
+           "sphbvf_comm_plan"]
 
 
 def lib():
@@ -89,6 +90,7 @@ def lib():
     L.sphbvf_comm_init.argtypes = [vp, vp]
     L.sphbvf_brick_bounds.argtypes = [C.POINTER(Config), ci, C.POINTER(cd * 3), C.POINTER(cd * 3)]
     L.sphbvf_proc_grid.argtypes = [ci, ci, C.POINTER(cd * 3), C.POINTER(ci * 3)]
+    L.sphbvf_comm_plan.argtypes = [C.POINTER(Config), ci, C.POINTER(ci * 27), C.POINTER(cd * 81)]
     _lib = L
     return L
 

@@ -224,15 +224,15 @@ static int fetch_flags(sphbvf_ctx *ctx) {
   return 0;
 }
 
-// pbc + (migration) + sort + ghosts + Verlet list: the rebuild branch of verlet.cpp:268-296
-static int rebuild(sphbvf_ctx *ctx) {
+// ---- pieces of the rebuild branch of verlet.cpp:268-296, shared by the single-rank path below and
+// the brick-decomposed path in comm_nccl.cu -----------------------------------------------------
+
+// Domain::pbc + cell ids + counting sort + permutation of every primary array into cell order
+int rebuild_sort(sphbvf_ctx *ctx) {
   DevState &d = ctx->d;
   NeighWork &w = ctx->w;
   cudaStream_t st = ctx->st;
   const Coeffs &co = ctx->co;
-  int rc;
-  ctx->tic(K_NEIGH, 40);
-  CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * 8, st));
   launch_cell_ids(d, ctx->grid, ctx->box, w, st);
   launch_sort_owned(d, ctx->grid, w, st);
   const int n = d.nlocal, S = co.nspecies;
@@ -246,25 +246,18 @@ static int rebuild(sphbvf_ctx *ctx) {
   if (ctx->with_dev) launch_permute(d.dev, w.tmp_perm, w.perm, n, 9, 8, st);
   for (int *p : {d.tag, d.type, d.mask, d.solid, d.fixed, d.slot}) launch_permute(p, w.tmp_perm, w.perm, n, 1, 4, st);
   CKLAUNCH();
+  return 0;
+}
 
-  // ghosts: periodic self images (single rank per periodic dimension)
-  launch_count_images(d, ctx->box, ctx->cutneighmax, w, st);
-  int nghost = 0;
-  CK(cudaMemcpyAsync(&ctx->h_flags[8], w.nimg + n, sizeof(int), cudaMemcpyDeviceToHost, st));
-  if ((rc = fetch_flags(ctx))) return rc;
-  nghost = ctx->h_flags[8];
-  if (ctx->h_flags[0]) return ctx->fail(SPHBVF_ENONFINITE, "Non-numeric positions - simulation unstable");
-  if (ctx->h_flags[1]) return ctx->fail(SPHBVF_ELOST, "Lost atoms: an owned atom left the non-periodic box");
-  if (d.nlocal + nghost > d.nallmax)
-    if ((rc = ensure_capacity(ctx, d.nmax, d.nlocal + nghost + nghost / 4 + 1024))) return rc;
-  d.nghost = nghost;
-  launch_fill_images(d, ctx->box, ctx->cutneighmax, w, st);
-  CK(cudaMemcpyAsync(d.ptag, d.tag, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
-  launch_pack(d, co, ctx->with_dev, st);
-  launch_ghost_refresh(d, co, ctx->with_dev, st);
+// ghosts are in place (packed records of owned + ghost atoms written): bin ghosts, Verlet list, xhold
+int rebuild_finish(sphbvf_ctx *ctx) {
+  DevState &d = ctx->d;
+  NeighWork &w = ctx->w;
+  cudaStream_t st = ctx->st;
+  const Coeffs &co = ctx->co;
+  int rc;
   launch_bin_ghosts(d, ctx->grid, w, st);
   CKLAUNCH();
-
   for (int attempt = 0; attempt < 3; attempt++) {
     if (d.maxneigh == 0) {
       // first guess from the number density: neighbours within cutneighmax of a uniform fluid
@@ -285,9 +278,42 @@ static int rebuild(sphbvf_ctx *ctx) {
   }
   ctx->maxneigh_seen = ctx->h_flags[2];
   launch_copy_xhold(d, st);
-  ctx->toc();
   ctx->ago = 0;
   ctx->nbuilds++;
+  return 0;
+}
+
+int ctx_ensure_capacity(sphbvf_ctx *ctx, int nmax, int nallmax) { return ensure_capacity(ctx, nmax, nallmax); }
+int ctx_fetch_flags(sphbvf_ctx *ctx) { return fetch_flags(ctx); }
+
+// single rank: ghosts are periodic self images
+static int rebuild(sphbvf_ctx *ctx) {
+  DevState &d = ctx->d;
+  NeighWork &w = ctx->w;
+  cudaStream_t st = ctx->st;
+  const Coeffs &co = ctx->co;
+  int rc;
+  ctx->tic(K_NEIGH, 40);
+  CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * 8, st));
+  if ((rc = rebuild_sort(ctx))) return rc;
+  const int n = d.nlocal;
+  launch_count_images(d, ctx->box, ctx->cutneighmax, w, st);
+  int nghost = 0;
+  CK(cudaMemcpyAsync(&ctx->h_flags[8], w.nimg + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if ((rc = fetch_flags(ctx))) return rc;
+  nghost = ctx->h_flags[8];
+  if (ctx->h_flags[0]) return ctx->fail(SPHBVF_ENONFINITE, "Non-numeric positions - simulation unstable");
+  if (ctx->h_flags[1]) return ctx->fail(SPHBVF_ELOST, "Lost atoms: an owned atom left the non-periodic box");
+  if (d.nlocal + nghost > d.nallmax)
+    if ((rc = ensure_capacity(ctx, d.nmax, d.nlocal + nghost + nghost / 4 + 1024))) return rc;
+  d.nghost = nghost;
+  launch_fill_images(d, ctx->box, ctx->cutneighmax, w, st);
+  CK(cudaMemcpyAsync(d.ptag, d.tag, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
+  launch_pack(d, co, ctx->with_dev, st);
+  launch_ghost_refresh(d, co, ctx->with_dev, st);
+  CKLAUNCH();
+  if ((rc = rebuild_finish(ctx))) return rc;
+  ctx->toc();
   return 0;
 }
 
@@ -542,6 +568,12 @@ int sphbvf_setup(sphbvf_ctx *ctx) {
   // Identical whenever the initial momentum velocity of atoms near a periodic face is zero (all
   // shipped decks) or the run was preceded by a `run 0`.
   launch_setup_pre_force(ctx->d, ctx->cfg.integrate_groupbit, ctx->st);
+  if (ctx->cfg.nranks > 1) {
+    // kernel specialisation and halo record width must agree on every brick
+    int v[3] = {ctx->any_solid, ctx->with_dev, ctx->e_nonzero};
+    if ((rc = comm_allreduce_max(ctx, v, 3))) return rc;
+    ctx->any_solid = v[0]; ctx->with_dev = v[1]; ctx->e_nonzero = v[2];
+  }
   if ((rc = sphbvf_build_neighbors(ctx))) return rc;
   ctx->nbuilds = 0;   // neighbor->ncalls = 0 (verlet.cpp:128)
   ctx->ndanger = 0;

@@ -51,6 +51,36 @@ int sphbvf_proc_grid(int nranks, int dim, const double prd[3], int grid[3]) {
   return 0;
 }
 
+// CommBrick::setup (comm_brick.cpp:161-410) for a one-hop halo: for each of the 27 directions
+// code = (dx+1) + 3 (dy+1) + 9 (dz+1) the rank owning the adjacent brick (-1: none, i.e. a fixed
+// boundary, the centre, or dz != 0 in 2D) and the shift added to positions sent that way
+// (-d_k * prd_k when the step crosses a periodic face, as pack_comm does with pbc flags).
+int sphbvf_comm_plan(const sphbvf_config *cfg, int rank, int *peer, double *shift) {
+  int pg[3];
+  for (int k = 0; k < 3; k++) pg[k] = cfg->procgrid[k] < 1 ? 1 : cfg->procgrid[k];
+  if (rank < 0 || rank >= pg[0] * pg[1] * pg[2]) return SPHBVF_EINVAL;
+  const int loc[3] = {rank % pg[0], (rank / pg[0]) % pg[1], rank / (pg[0] * pg[1])};
+  for (int code = 0; code < 27; code++) {
+    const int s[3] = {code % 3 - 1, (code / 3) % 3 - 1, code / 9 - 1};
+    int t[3];
+    bool ok = code != 13 && !(cfg->dim == 2 && s[2] != 0);
+    for (int k = 0; k < 3; k++) {
+      shift[3 * code + k] = 0.0;
+      t[k] = loc[k] + s[k];
+      if (t[k] < 0 || t[k] >= pg[k]) {
+        if (!cfg->periodic[k]) ok = false;
+        else {
+          t[k] = (t[k] + pg[k]) % pg[k];
+          shift[3 * code + k] = -s[k] * (cfg->boxhi[k] - cfg->boxlo[k]);
+        }
+      }
+    }
+    peer[code] = ok ? t[0] + pg[0] * (t[1] + pg[1] * t[2]) : -1;
+    if (!ok) shift[3 * code] = shift[3 * code + 1] = shift[3 * code + 2] = 0.0;
+  }
+  return 0;
+}
+
 }  // extern "C"
 
 // ---- NCCL halo (implemented in comm_nccl.cu when built with NCCL) ----------------------------
@@ -58,6 +88,7 @@ int sphbvf_proc_grid(int nranks, int dim, const double prd[3], int grid[3]) {
 int comm_rebuild(sphbvf_ctx *ctx) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
 int comm_forward(sphbvf_ctx *ctx) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
 int comm_vote(sphbvf_ctx *ctx, int *) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
+int comm_allreduce_max(sphbvf_ctx *ctx, int *, int) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
 void comm_destroy(sphbvf_ctx *) {}
 extern "C" int sphbvf_comm_unique_id(void *) { return SPHBVF_ECOMM; }
 extern "C" int sphbvf_comm_init(sphbvf_ctx *ctx, const void *) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }

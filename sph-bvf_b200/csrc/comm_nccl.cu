@@ -1,0 +1,526 @@
+// comm_nccl.cu -- brick decomposition across the GPUs of one box, one process per GPU, NCCL
+// point-to-point over NVLink 5 / NVSwitch.
+//
+// Replaces CommBrick::{setup,exchange,borders,forward_comm} + AtomVecSsaTsdpdAtomic::{pack,unpack}_
+// {exchange,border,comm} (comm_brick.cpp:161-880, atom_vec_ssa_tsdpd_atomic.cpp:426-1638) and the
+// MPI_Allreduce of the rebuild vote (neighbor.cpp:1997).  Differences that are deliberate:
+//   * every peer is one NVSwitch hop away at full bandwidth, so the reference's three staged
+//     sweeps (x, then y, then z, each forwarding ghosts of ghosts) become ONE exchange with up to
+//     26 neighbour bricks (7 on a 2x2x2 grid), posted as a single NCCL group;
+//   * no reverse communication: each rank gathers over the full neighbour set of the atoms it
+//     owns, so ghosts are read-only and only the 16 (+S, +9) doubles the pair
+//     kernel reads travel per ghost per step;
+//   * migration moves the primary state only (the pair outputs are recomputed before use).
+// A brick that is its own neighbour across a periodic face (one brick in that dimension)
+// exchanges with itself through a device copy; the arithmetic x + shift is the reference's
+// (atom_vec_ssa_tsdpd_atomic.cpp:487-500).
+#include <nccl.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "context.cuh"
+
+using namespace sphbvf;
+
+namespace {
+
+constexpr int ND = 27;       // directions (dx+1) + 3 (dy+1) + 9 (dz+1); 13 = stay
+constexpr int NHALO = 16;    // pA pB pC pD
+struct DirTable {
+  int peer[ND];
+  int off[ND + 1];           // first slot of each direction in the send list / ghost slab
+  double shift[ND][3];
+};
+
+}  // namespace
+
+struct CommState {
+  ncclComm_t comm = nullptr;
+  DirTable send{}, recv{};
+  int nsend = 0;
+  int *sendidx = nullptr;    // [nsend] owned atom of each send slot, grouped by direction
+  int send_cap = 0;
+  double *sendbuf = nullptr, *recvbuf = nullptr;
+  size_t buf_cap = 0;        // doubles
+  int *d_counts = nullptr;   // [ND] local counters | [ND] cursors | [ND * nranks] gathered | [1] vote
+  int *h_counts = nullptr;   // pinned mirror
+  int *d_dir = nullptr;      // [nmax] migration direction of each owned atom
+  int dir_cap = 0;
+  int *d_keep = nullptr, *d_pos = nullptr;
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return ctx->fail(SPHBVF_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t r_ = (call);                                                                      \
+    if (r_ != ncclSuccess)                                                                         \
+      return ctx->fail(SPHBVF_ECOMM, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(r_), __FILE__, __LINE__); \
+  } while (0)
+
+static inline int nblocks(long n, int t) { return (int)((n + t - 1) / t); }
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+struct BrickGeom {
+  double lo[3], hi[3], prd[3], sublo[3], subhi[3];
+  int periodic[3], pg[3], loc[3], dim;
+};
+
+__device__ __forceinline__ void brick_bounds_dev(const BrickGeom &b, int k, int t, double &lo, double &hi) {
+  lo = b.lo[k] + b.prd[k] * ((double)t / b.pg[k]);
+  hi = t == b.pg[k] - 1 ? b.hi[k] : b.lo[k] + b.prd[k] * ((double)(t + 1) / b.pg[k]);
+}
+
+// Domain::pbc + the owner test of CommBrick::exchange (comm_brick.cpp:585-700): direction of the
+// brick that owns the atom now.  flags[1] = atom more than one brick away / outside a fixed box.
+__global__ void classify_kernel(const DevState d, const BrickGeom b, int *dir, int *counts, int *flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.nlocal) return;
+  int code = 0, mul = 1;
+  for (int k = 0; k < 3; k++, mul *= 3) {
+    double xk = d.x[3 * (size_t)i + k];
+    if (!isfinite(xk)) { flags[0] = 1; xk = b.sublo[k]; }
+    int delta = 0;
+    if (!(b.dim == 2 && k == 2)) {
+      if (b.periodic[k]) {
+        if (xk < b.lo[k]) xk += b.prd[k];
+        if (xk >= b.hi[k]) {
+          xk -= b.prd[k];
+          xk = xk > b.lo[k] ? xk : b.lo[k];
+        }
+        d.x[3 * (size_t)i + k] = xk;
+      }
+      const int p = b.pg[k], loc = b.loc[k];
+      if (p > 1 && (xk < b.sublo[k] || xk >= b.subhi[k])) {
+        if (xk >= b.subhi[k]) delta = loc < p - 1 ? 1 : (b.periodic[k] ? -1 : 0);
+        else delta = loc > 0 ? -1 : (b.periodic[k] ? 1 : 0);
+        // wrapped across the periodic face: the owner is the brick at the other end
+        if (b.periodic[k] && loc == p - 1 && xk < b.sublo[k]) {
+          double l0, h0;
+          brick_bounds_dev(b, k, 0, l0, h0);
+          if (xk < h0) delta = 1;
+        }
+        if (b.periodic[k] && loc == 0 && xk >= b.subhi[k]) {
+          double l0, h0;
+          brick_bounds_dev(b, k, p - 1, l0, h0);
+          if (xk >= l0) delta = -1;
+        }
+        if (delta) {
+          const int t = (loc + delta + p) % p;
+          double tl, th;
+          brick_bounds_dev(b, k, t, tl, th);
+          if (xk < tl || xk >= th) flags[1] = 1;   // moved further than the adjacent brick
+        }
+      }
+    }
+    code += (delta + 1) * mul;
+  }
+  dir[i] = code;
+  if (code != 13) atomicAdd(&counts[code], 1);
+}
+
+// keep[i] = atom stays on this rank
+__global__ void keep_flag_kernel(int n, const int *dir, int *keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n) keep[i] = i < n ? dir[i] == 13 : 0;
+}
+
+// stayers -> perm (new -> old, order preserved); leavers -> migration records
+//   record: tag type mask solid fixed | x3 v3 vest3 rho rhoI e | C[S] | dev[9]   (ints as doubles)
+__global__ void pack_leavers_kernel(const DevState d, const int S, const int *dir, const int *pos, int *perm,
+                                    const DirTable t, int *cursor, double *buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.nlocal) return;
+  const int code = dir[i];
+  if (code == 13) { perm[pos[i]] = i; return; }
+  const int NM = 26 + S;
+  double *r = buf + (size_t)(t.off[code] + atomicAdd(&cursor[code], 1)) * NM;
+  r[0] = d.tag[i]; r[1] = d.type[i]; r[2] = d.mask[i]; r[3] = d.solid[i]; r[4] = d.fixed[i];
+  const size_t i3 = 3 * (size_t)i;
+  for (int k = 0; k < 3; k++) { r[5 + k] = d.x[i3 + k]; r[8 + k] = d.v[i3 + k]; r[11 + k] = d.vest[i3 + k]; }
+  r[14] = d.rho[i]; r[15] = d.rhoI[i]; r[16] = d.e[i];
+  for (int k = 0; k < S; k++) r[17 + k] = d.C[(size_t)i * S + k];
+  for (int k = 0; k < 9; k++) r[17 + S + k] = d.dev[9 * (size_t)i + k];
+}
+
+__global__ void unpack_arrivals_kernel(const DevState d, const int S, const int first, const int n, const double *buf) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int NM = 26 + S;
+  const double *r = buf + (size_t)q * NM;
+  const int i = first + q;
+  d.tag[i] = (int)r[0]; d.type[i] = (int)r[1]; d.mask[i] = (int)r[2]; d.solid[i] = (int)r[3]; d.fixed[i] = (int)r[4];
+  d.slot[i] = -1;
+  const size_t i3 = 3 * (size_t)i;
+  for (int k = 0; k < 3; k++) { d.x[i3 + k] = r[5 + k]; d.v[i3 + k] = r[8 + k]; d.vest[i3 + k] = r[11 + k]; }
+  d.rho[i] = r[14]; d.rhoI[i] = r[15]; d.e[i] = r[16];
+  for (int k = 0; k < S; k++) d.C[(size_t)i * S + k] = r[17 + k];
+  for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] = r[17 + S + k];
+}
+
+// CommBrick::borders slab test (comm_brick.cpp:765-770) for all 26 directions at once:
+// atom i is a ghost of the brick in direction (dx,dy,dz) iff it lies within cutghost of every
+// face that direction crosses.
+__device__ __forceinline__ void slab_flags(const BrickGeom &b, const double cut, const double *x, int lo[3], int hi[3]) {
+  for (int k = 0; k < 3; k++) {
+    const bool use = !(b.dim == 2 && k == 2);
+    lo[k] = use && x[k] <= b.sublo[k] + cut;
+    hi[k] = use && x[k] >= b.subhi[k] - cut;
+  }
+}
+
+template <bool FILL>
+__global__ void border_kernel(const DevState d, const BrickGeom b, const double cut, const DirTable t, int *counts,
+                              int *sendidx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.nlocal) return;
+  int lo[3], hi[3];
+  slab_flags(b, cut, &d.x[3 * (size_t)i], lo, hi);
+  if (!(lo[0] | hi[0] | lo[1] | hi[1] | lo[2] | hi[2])) return;
+  for (int code = 0; code < ND; code++) {
+    if (code == 13 || t.peer[code] < 0) continue;
+    const int s[3] = {code % 3 - 1, (code / 3) % 3 - 1, code / 9 - 1};
+    bool need = true;
+    for (int k = 0; k < 3; k++)
+      if ((s[k] == -1 && !lo[k]) || (s[k] == 1 && !hi[k])) need = false;
+    if (!need) continue;
+    const int r = atomicAdd(&counts[code], 1);
+    if (FILL) sendidx[t.off[code] + r] = i;
+  }
+}
+
+// pack_comm / pack_border: the records the pair kernel reads, position shifted by the periodic image
+//   record: pA(4) pB(4) pC(4) pD(4) | pCs[S] | pdev[9] (with_dev) | flags tag (border)
+__global__ void halo_pack_kernel(const DevState d, const int S, const int with_dev, const int border, const int nsend,
+                                 const int *sendidx, const DirTable t, double *buf) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsend) return;
+  int code = 0;
+  while (s >= t.off[code + 1]) code++;
+  const int i = sendidx[s];
+  const int R = NHALO + S + (with_dev ? 9 : 0) + (border ? 2 : 0);
+  double *r = buf + (size_t)s * R;
+  Rec4 A = d.pA[i];
+  // x + shift in the reference's order: one rounded add per shifted dimension
+  A.x += t.shift[code][0]; A.y += t.shift[code][1]; A.z += t.shift[code][2];
+  const Rec4 B = d.pB[i], C = d.pC[i], D = d.pD[i];
+  r[0] = A.x; r[1] = A.y; r[2] = A.z; r[3] = A.w;
+  r[4] = B.x; r[5] = B.y; r[6] = B.z; r[7] = B.w;
+  r[8] = C.x; r[9] = C.y; r[10] = C.z; r[11] = C.w;
+  r[12] = D.x; r[13] = D.y; r[14] = D.z; r[15] = D.w;
+  int q = NHALO;
+  for (int k = 0; k < S; k++) r[q++] = d.pCs[(size_t)i * S + k];
+  if (with_dev)
+    for (int k = 0; k < 9; k++) r[q++] = d.pdev[9 * (size_t)i + k];
+  if (border) { r[q++] = d.pflags[i]; r[q++] = d.tag[i]; }
+}
+
+__global__ void halo_unpack_kernel(const DevState d, const int S, const int with_dev, const int border,
+                                   const DirTable t, const double *buf) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= d.nghost) return;
+  const int R = NHALO + S + (with_dev ? 9 : 0) + (border ? 2 : 0);
+  const double *r = buf + (size_t)g * R;
+  const int j = d.nlocal + g;
+  d.pA[j] = make_rec4(r[0], r[1], r[2], r[3]);
+  d.pB[j] = make_rec4(r[4], r[5], r[6], r[7]);
+  d.pC[j] = make_rec4(r[8], r[9], r[10], r[11]);
+  d.pD[j] = make_rec4(r[12], r[13], r[14], r[15]);
+  int q = NHALO;
+  for (int k = 0; k < S; k++) d.pCs[(size_t)j * S + k] = r[q++];
+  if (with_dev)
+    for (int k = 0; k < 9; k++) d.pdev[9 * (size_t)j + k] = r[q++];
+  if (border) {
+    d.pflags[j] = (int)r[q++];
+    d.ptag[j] = (int)r[q++];
+    int code = 0;
+    while (g >= t.off[code + 1]) code++;
+    d.gowner[g] = -1;
+    for (int k = 0; k < 3; k++) d.gshift[3 * (size_t)g + k] = t.shift[code][k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+extern "C" int sphbvf_comm_plan(const sphbvf_config *cfg, int rank, int *peer, double *shift);
+
+static BrickGeom geom(const sphbvf_ctx *ctx) {
+  BrickGeom g;
+  const Box &b = ctx->box;
+  for (int k = 0; k < 3; k++) {
+    g.lo[k] = b.lo[k]; g.hi[k] = b.hi[k]; g.prd[k] = b.prd[k];
+    g.sublo[k] = b.sublo[k]; g.subhi[k] = b.subhi[k];
+    g.periodic[k] = b.periodic[k];
+    g.pg[k] = ctx->cfg.procgrid[k];
+  }
+  const int r = ctx->cfg.rank;
+  g.loc[0] = r % g.pg[0];
+  g.loc[1] = (r / g.pg[0]) % g.pg[1];
+  g.loc[2] = r / (g.pg[0] * g.pg[1]);
+  g.dim = b.dim;
+  return g;
+}
+
+static int ensure_buf(sphbvf_ctx *ctx, size_t doubles) {
+  CommState *c = ctx->comm;
+  if (doubles <= c->buf_cap) return 0;
+  CK(cudaStreamSynchronize(ctx->st));
+  if (c->sendbuf) cudaFree(c->sendbuf);
+  if (c->recvbuf) cudaFree(c->recvbuf);
+  c->buf_cap = doubles + doubles / 4 + 4096;
+  CK(cudaMalloc((void **)&c->sendbuf, sizeof(double) * c->buf_cap));
+  CK(cudaMalloc((void **)&c->recvbuf, sizeof(double) * c->buf_cap));
+  return 0;
+}
+
+static int ensure_dir(sphbvf_ctx *ctx, int n) {
+  CommState *c = ctx->comm;
+  if (n + 1 <= c->dir_cap) return 0;
+  for (int **p : {&c->d_dir, &c->d_keep, &c->d_pos}) {
+    if (*p) cudaFree(*p);
+    CK(cudaMalloc((void **)p, sizeof(int) * (size_t)(ctx->d.nmax + 2)));
+  }
+  c->dir_cap = ctx->d.nmax + 2;
+  return 0;
+}
+
+// all ranks learn every rank's per-direction counts: recvcnt[d'] = what peer(d') sends towards -d'
+static int exchange_counts(sphbvf_ctx *ctx, const int *d_local, int *sendcnt, int *recvcnt) {
+  CommState *c = ctx->comm;
+  const int P = ctx->cfg.nranks;
+  int *gathered = c->d_counts + 2 * ND;
+  NK(ncclAllGather(d_local, gathered, ND, ncclInt, c->comm, ctx->st));
+  CK(cudaMemcpyAsync(c->h_counts, gathered, sizeof(int) * ND * P, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  for (int dcode = 0; dcode < ND; dcode++) {
+    sendcnt[dcode] = c->send.peer[dcode] >= 0 ? c->h_counts[ctx->cfg.rank * ND + dcode] : 0;
+    const int p = c->recv.peer[dcode];
+    recvcnt[dcode] = p >= 0 ? c->h_counts[p * ND + (ND - 1 - dcode)] : 0;
+  }
+  sendcnt[13] = recvcnt[13] = 0;
+  return 0;
+}
+
+// one NCCL group: sends in ascending direction order, receives in descending order, so that
+// several messages between the same two ranks pair up in the order NCCL matches them; a brick
+// that neighbours itself copies on the device.
+static int exchange_payload(sphbvf_ctx *ctx, const int *sendcnt, const int *sendoff, const int *recvcnt,
+                            const int *recvoff, int width) {
+  CommState *c = ctx->comm;
+  const int me = ctx->cfg.rank;
+  bool any = false;
+  for (int dcode = 0; dcode < ND; dcode++) {
+    if (sendcnt[dcode] && c->send.peer[dcode] == me) {
+      const int rd = ND - 1 - dcode;   // arrives as "from direction -d"
+      CK(cudaMemcpyAsync(c->recvbuf + (size_t)recvoff[rd] * width, c->sendbuf + (size_t)sendoff[dcode] * width,
+                         sizeof(double) * (size_t)sendcnt[dcode] * width, cudaMemcpyDeviceToDevice, ctx->st));
+    } else if (sendcnt[dcode] || (recvcnt[dcode] && c->recv.peer[dcode] != me)) any = true;
+  }
+  if (!any) return 0;
+  NK(ncclGroupStart());
+  for (int dcode = 0; dcode < ND; dcode++)
+    if (sendcnt[dcode] && c->send.peer[dcode] != me)
+      NK(ncclSend(c->sendbuf + (size_t)sendoff[dcode] * width, (size_t)sendcnt[dcode] * width, ncclDouble,
+                  c->send.peer[dcode], c->comm, ctx->st));
+  for (int dcode = ND - 1; dcode >= 0; dcode--)
+    if (recvcnt[dcode] && c->recv.peer[dcode] != me)
+      NK(ncclRecv(c->recvbuf + (size_t)recvoff[dcode] * width, (size_t)recvcnt[dcode] * width, ncclDouble,
+                  c->recv.peer[dcode], c->comm, ctx->st));
+  NK(ncclGroupEnd());
+  return 0;
+}
+
+static int halo(sphbvf_ctx *ctx, int border) {
+  CommState *c = ctx->comm;
+  DevState &d = ctx->d;
+  const int S = ctx->co.nspecies;
+  const int R = NHALO + S + (ctx->with_dev ? 9 : 0) + (border ? 2 : 0);
+  int rc;
+  if ((rc = ensure_buf(ctx, (size_t)std::max(c->nsend, d.nghost) * R + 64))) return rc;
+  if (c->nsend)
+    halo_pack_kernel<<<nblocks(c->nsend, 256), 256, 0, ctx->st>>>(d, S, ctx->with_dev, border, c->nsend, c->sendidx,
+                                                                   c->send, c->sendbuf);
+  int sendcnt[ND], recvcnt[ND];
+  for (int k = 0; k < ND; k++) {
+    sendcnt[k] = c->send.off[k + 1] - c->send.off[k];
+    recvcnt[k] = c->recv.off[k + 1] - c->recv.off[k];
+  }
+  if ((rc = exchange_payload(ctx, sendcnt, c->send.off, recvcnt, c->recv.off, R))) return rc;
+  if (d.nghost)
+    halo_unpack_kernel<<<nblocks(d.nghost, 256), 256, 0, ctx->st>>>(d, S, ctx->with_dev, border, c->recv, c->recvbuf);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int comm_forward(sphbvf_ctx *ctx) {
+  if (!ctx->comm) return ctx->fail(SPHBVF_ECOMM, "sphbvf_comm_init has not been called");
+  ctx->launches_fam[K_PACK] += 2;
+  return halo(ctx, 0);
+}
+
+// max over ranks of up to 8 ints: the rebuild vote (neighbor.cpp:1997) and the per-run flags
+int comm_allreduce_max(sphbvf_ctx *ctx, int *vals, int n) {
+  CommState *c = ctx->comm;
+  if (!c) return ctx->fail(SPHBVF_ECOMM, "sphbvf_comm_init has not been called");
+  if (n > 8) return ctx->fail(SPHBVF_EINVAL, "comm_allreduce_max: n > 8");
+  int *v = c->d_counts + 2 * ND + ND * ctx->cfg.nranks;
+  for (int k = 0; k < n; k++) c->h_counts[k] = vals[k];
+  CK(cudaMemcpyAsync(v, c->h_counts, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->st));
+  NK(ncclAllReduce(v, v, n, ncclInt, ncclMax, c->comm, ctx->st));
+  CK(cudaMemcpyAsync(c->h_counts, v, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  for (int k = 0; k < n; k++) vals[k] = c->h_counts[k];
+  return 0;
+}
+
+int comm_vote(sphbvf_ctx *ctx, int *flag) { return comm_allreduce_max(ctx, flag, 1); }
+
+// the rebuild branch of verlet.cpp:268-296 on a brick: pbc, exchange, sort, borders, list
+int comm_rebuild(sphbvf_ctx *ctx) {
+  CommState *c = ctx->comm;
+  if (!c) return ctx->fail(SPHBVF_ECOMM, "sphbvf_comm_init has not been called");
+  DevState &d = ctx->d;
+  NeighWork &w = ctx->w;
+  cudaStream_t st = ctx->st;
+  const int S = ctx->co.nspecies;
+  const BrickGeom bg = geom(ctx);
+  int rc;
+  ctx->tic(K_NEIGH, 48);
+  CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * 8, st));
+
+  // ---- migration (Comm::exchange)
+  if ((rc = ensure_dir(ctx, d.nlocal))) return rc;
+  int *cnt = c->d_counts, *cur = c->d_counts + ND;
+  CK(cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * ND, st));
+  if (d.nlocal) classify_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, bg, c->d_dir, cnt, w.flags);
+  int sendcnt[ND], recvcnt[ND], sendoff[ND + 1], recvoff[ND + 1];
+  if ((rc = exchange_counts(ctx, cnt, sendcnt, recvcnt))) return rc;
+  if ((rc = ctx_fetch_flags(ctx))) return rc;
+  if (ctx->h_flags[0]) return ctx->fail(SPHBVF_ENONFINITE, "Non-numeric positions - simulation unstable");
+  if (ctx->h_flags[1]) return ctx->fail(SPHBVF_ELOST, "Lost atoms: an atom moved further than the neighbouring brick");
+  sendoff[0] = recvoff[0] = 0;
+  for (int k = 0; k < ND; k++) {
+    sendoff[k + 1] = sendoff[k] + sendcnt[k];
+    recvoff[k + 1] = recvoff[k] + recvcnt[k];
+  }
+  const int nleave = sendoff[ND], narrive = recvoff[ND];
+  if (nleave || narrive) {
+    const int NM = 26 + S;
+    const int nstay = d.nlocal - nleave;
+    if ((rc = ensure_buf(ctx, (size_t)std::max(nleave, narrive) * NM + 64))) return rc;
+    if (nstay + narrive > d.nmax) {
+      if ((rc = ctx_ensure_capacity(ctx, nstay + narrive + (nstay + narrive) / 8 + 1024, d.nallmax))) return rc;
+      if ((rc = ensure_dir(ctx, d.nmax))) return rc;
+    }
+    if (nleave) {
+      DirTable t = c->send;
+      for (int k = 0; k <= ND; k++) t.off[k] = sendoff[k];
+      keep_flag_kernel<<<nblocks(d.nlocal + 1, 256), 256, 0, st>>>(d.nlocal, c->d_dir, c->d_keep);
+      exclusive_scan(c->d_keep, c->d_pos, d.nlocal + 1, w.scan_tmp, st);
+      pack_leavers_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, S, c->d_dir, c->d_pos, w.perm, t, cur, c->sendbuf);
+      // compaction of the stayers, order preserved
+      launch_permute(d.x, w.tmp_perm, w.perm, nstay, 3, 8, st);
+      launch_permute(d.v, w.tmp_perm, w.perm, nstay, 3, 8, st);
+      launch_permute(d.vest, w.tmp_perm, w.perm, nstay, 3, 8, st);
+      launch_permute(d.rho, w.tmp_perm, w.perm, nstay, 1, 8, st);
+      launch_permute(d.rhoI, w.tmp_perm, w.perm, nstay, 1, 8, st);
+      launch_permute(d.e, w.tmp_perm, w.perm, nstay, 1, 8, st);
+      if (S) launch_permute(d.C, w.tmp_perm, w.perm, nstay, S, 8, st);
+      launch_permute(d.dev, w.tmp_perm, w.perm, nstay, 9, 8, st);
+      for (int *p : {d.tag, d.type, d.mask, d.solid, d.fixed, d.slot}) launch_permute(p, w.tmp_perm, w.perm, nstay, 1, 4, st);
+    }
+    if ((rc = exchange_payload(ctx, sendcnt, sendoff, recvcnt, recvoff, NM))) return rc;
+    d.nlocal = nstay;
+    if (narrive) unpack_arrivals_kernel<<<nblocks(narrive, 256), 256, 0, st>>>(d, S, nstay, narrive, c->recvbuf);
+    d.nlocal = nstay + narrive;
+    ctx->migrated = 1;
+    CK(cudaGetLastError());
+  }
+
+  // ---- sort into cell order
+  if ((rc = rebuild_sort(ctx))) return rc;
+
+  // ---- borders: who is a ghost of which neighbour brick (frozen until the next rebuild)
+  CK(cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * ND, st));
+  if (d.nlocal) border_kernel<false><<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, bg, ctx->cutneighmax, c->send, cnt, nullptr);
+  if ((rc = exchange_counts(ctx, cnt, sendcnt, recvcnt))) return rc;
+  if ((rc = ctx_fetch_flags(ctx))) return rc;
+  if (ctx->h_flags[1]) return ctx->fail(SPHBVF_ELOST, "Lost atoms: an owned atom left the cell grid of its brick");
+  c->send.off[0] = c->recv.off[0] = 0;
+  for (int k = 0; k < ND; k++) {
+    c->send.off[k + 1] = c->send.off[k] + sendcnt[k];
+    c->recv.off[k + 1] = c->recv.off[k] + recvcnt[k];
+  }
+  c->nsend = c->send.off[ND];
+  const int nghost = c->recv.off[ND];
+  if (c->nsend > c->send_cap) {
+    if (c->sendidx) cudaFree(c->sendidx);
+    c->send_cap = c->nsend + c->nsend / 4 + 1024;
+    CK(cudaMalloc((void **)&c->sendidx, sizeof(int) * (size_t)c->send_cap));
+  }
+  if (d.nlocal + nghost > d.nallmax)
+    if ((rc = ctx_ensure_capacity(ctx, d.nmax, d.nlocal + nghost + nghost / 4 + 1024))) return rc;
+  d.nghost = nghost;
+  if (c->nsend) border_kernel<true><<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, bg, ctx->cutneighmax, c->send, cur, c->sendidx);
+  CK(cudaMemcpyAsync(d.ptag, d.tag, sizeof(int) * (size_t)d.nlocal, cudaMemcpyDeviceToDevice, st));
+  launch_pack(d, ctx->co, ctx->with_dev, st);
+  if ((rc = halo(ctx, 1))) return rc;
+
+  if ((rc = rebuild_finish(ctx))) return rc;
+  ctx->toc();
+  return 0;
+}
+
+void comm_destroy(sphbvf_ctx *ctx) {
+  CommState *c = ctx->comm;
+  if (!c) return;
+  if (c->comm) ncclCommDestroy(c->comm);
+  for (void *p : {(void *)c->sendidx, (void *)c->sendbuf, (void *)c->recvbuf, (void *)c->d_counts, (void *)c->d_dir,
+                  (void *)c->d_keep, (void *)c->d_pos})
+    if (p) cudaFree(p);
+  if (c->h_counts) cudaFreeHost(c->h_counts);
+  delete c;
+  ctx->comm = nullptr;
+}
+
+extern "C" int sphbvf_comm_unique_id(void *id128) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  return ncclGetUniqueId((ncclUniqueId *)id128) == ncclSuccess ? 0 : SPHBVF_ECOMM;
+}
+
+extern "C" int sphbvf_comm_init(sphbvf_ctx *ctx, const void *id128) {
+  if (ctx->comm) return ctx->fail(SPHBVF_ESTATE, "sphbvf_comm_init called twice");
+  const int P = ctx->cfg.nranks;
+  if (ctx->cfg.procgrid[0] * ctx->cfg.procgrid[1] * ctx->cfg.procgrid[2] != P)
+    return ctx->fail(SPHBVF_EINVAL, "procgrid %d x %d x %d does not match %d ranks", ctx->cfg.procgrid[0],
+                     ctx->cfg.procgrid[1], ctx->cfg.procgrid[2], P);
+  cudaSetDevice(ctx->cfg.device);
+  CommState *c = new CommState();
+  ctx->comm = c;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NK(ncclCommInitRank(&c->comm, P, id, ctx->cfg.rank));
+  CK(cudaMalloc((void **)&c->d_counts, sizeof(int) * (2 * ND + ND * P + 8)));
+  CK(cudaMallocHost((void **)&c->h_counts, sizeof(int) * (ND * P + 8)));
+  double shift[ND * 3];
+  int rc = sphbvf_comm_plan(&ctx->cfg, ctx->cfg.rank, c->send.peer, shift);
+  if (rc) return ctx->fail(rc, "sphbvf_comm_plan failed");
+  for (int k = 0; k < ND; k++) {
+    for (int q = 0; q < 3; q++) {
+      c->send.shift[k][q] = shift[3 * k + q];
+      // what arrives from direction k was sent by that peer towards -k with the opposite wrap
+      c->recv.shift[k][q] = shift[3 * k + q] == 0.0 ? 0.0 : -shift[3 * k + q];
+    }
+    c->recv.peer[k] = c->send.peer[k];
+  }
+  return 0;
+}

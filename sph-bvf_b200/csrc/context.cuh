@@ -47,8 +47,15 @@ struct sphbvf_ctx {
   void drain_events();
 };
 
-// comm.cu: brick decomposition over NCCL (one rank per GPU)
+// capi.cu: rebuild pieces shared with the brick-decomposed path
+int rebuild_sort(sphbvf_ctx *ctx);       // pbc + cell sort + permutation of the primary arrays
+int rebuild_finish(sphbvf_ctx *ctx);     // ghost binning + Verlet list + xhold
+int ctx_ensure_capacity(sphbvf_ctx *ctx, int nmax, int nallmax);
+int ctx_fetch_flags(sphbvf_ctx *ctx);    // w.flags -> h_flags[0..8), synchronises the stream
+
+// comm.cu / comm_nccl.cu: brick decomposition over NCCL (one rank per GPU)
 int comm_rebuild(sphbvf_ctx *ctx);        // pbc + migration + sort + borders + list
 int comm_forward(sphbvf_ctx *ctx);        // per-step halo of the packed records
 int comm_vote(sphbvf_ctx *ctx, int *flag); // rebuild vote: max over ranks
+int comm_allreduce_max(sphbvf_ctx *ctx, int *vals, int n);   // n <= 8
 void comm_destroy(sphbvf_ctx *ctx);

@@ -150,15 +150,16 @@ __global__ void scatter_kernel(const int n, const int *cellid, const int *cell_s
   perm[cell_start[c] + r] = i;
 }
 
-// restore determinism: within each cell order by previous index (cells hold a handful of atoms)
-__global__ void cell_order_kernel(const long ncells, const int *cell_start, int *perm) {
+// restore determinism: within each cell order by atom tag (cells hold a handful of atoms), so
+// that neither the atomics above nor the arrival order of migrated / ghost atoms shows in results
+__global__ void cell_order_kernel(const long ncells, const int *cell_start, int *perm, const int *key) {
   const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncells) return;
   const int a = cell_start[c], b = cell_start[c + 1];
   for (int p = a + 1; p < b; p++) {
-    const int v = perm[p];
+    const int v = perm[p], kv = key[v];
     int q = p - 1;
-    while (q >= a && perm[q] > v) { perm[q + 1] = perm[q]; q--; }
+    while (q >= a && (key[perm[q]] > kv || (key[perm[q]] == kv && perm[q] > v))) { perm[q + 1] = perm[q]; q--; }
     perm[q + 1] = v;
   }
 }
@@ -169,7 +170,7 @@ void launch_sort_owned(const DevState &d, const Grid &g, const NeighWork &w, cud
   cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (g.ncells + 1), st);
   if (!d.nlocal) return;
   scatter_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d.nlocal, w.cellid, w.cell_start, w.cell_count, w.perm);
-  cell_order_kernel<<<nblocks(g.ncells, 256), 256, 0, st>>>(g.ncells, w.cell_start, w.perm);
+  cell_order_kernel<<<nblocks(g.ncells, 256), 256, 0, st>>>(g.ncells, w.cell_start, w.perm, d.tag);
 }
 
 template <typename T>
@@ -269,7 +270,7 @@ void launch_bin_ghosts(const DevState &d, const Grid &g, const NeighWork &w, cud
   exclusive_scan(w.gcell_count, w.gcell_start, g.ncells + 1, w.scan_tmp, st);
   cudaMemsetAsync(w.gcell_count, 0, sizeof(int) * (g.ncells + 1), st);
   ghost_scatter_kernel<<<nblocks(d.nghost, 256), 256, 0, st>>>(d, w.cellid, w.gcell_start, w.gcell_count, w.gorder);
-  cell_order_kernel<<<nblocks(g.ncells, 256), 256, 0, st>>>(g.ncells, w.gcell_start, w.gorder);
+  cell_order_kernel<<<nblocks(g.ncells, 256), 256, 0, st>>>(g.ncells, w.gcell_start, w.gorder, d.ptag + d.nlocal);
 }
 
 // ---------------------------------------------------------------- Verlet list
