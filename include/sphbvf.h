@@ -119,6 +119,10 @@ int sphbvf_add_setforce(sphbvf_ctx *ctx, int groupbit, double fx, double fy, dou
  * iterations of Verlet::run (verlet.cpp:240-353) entirely on the device. */
 int sphbvf_setup(sphbvf_ctx *ctx);
 int sphbvf_run(sphbvf_ctx *ctx, int nsteps);
+/* the neighbour part of Verlet::setup only (verlet.cpp:100-128: pbc, exchange, borders,
+ * neighbor->build, ncalls = 0) for hosts that call the hooks below themselves: vest/rhoI must have
+ * been uploaded, pair_compute and post_force follow through their own entry points */
+int sphbvf_setup_neighbors(sphbvf_ctx *ctx);
 
 /* the same step in the pieces the /cuda host classes are called with by Verlet/Modify */
 int sphbvf_initial_integrate(sphbvf_ctx *ctx); /* Fix*::initial_integrate (fix_...transport_velocity.cpp:99) */

@@ -34,6 +34,7 @@ SYMBOLS = ["sphbvf_version", "sphbvf_device_count", "sphbvf_create", "sphbvf_des
            "sphbvf_set_type", "sphbvf_set_pair", "sphbvf_set_dt", "sphbvf_set_timestep", "sphbvf_set_run_length",
            "sphbvf_set_atoms", "sphbvf_upload", "sphbvf_download", "sphbvf_download_local", "sphbvf_add_buoyancy",
            "sphbvf_add_forcing", "sphbvf_add_buffer", "sphbvf_add_setforce", "sphbvf_setup", "sphbvf_run",
+           "sphbvf_setup_neighbors",
            "sphbvf_initial_integrate", "sphbvf_post_integrate", "sphbvf_neighbor", "sphbvf_pair_compute",
            "sphbvf_post_force", "sphbvf_final_integrate", "sphbvf_end_of_step", "sphbvf_build_neighbors",
            "sphbvf_nlocal", "sphbvf_nghost", "sphbvf_ntimestep", "sphbvf_nbuilds", "sphbvf_ndanger",
@@ -70,7 +71,7 @@ def lib():
     L.sphbvf_add_forcing.argtypes = [vp, ci, ci, cl, ci, ci, cd, cd, cd, cd, cd]
     L.sphbvf_add_buffer.argtypes = [vp, ci, ci, ci, cl, ci, cd, cd, cd, cd, cd]
     L.sphbvf_add_setforce.argtypes = [vp, ci, cd, cd, cd]
-    for f in ("setup", "initial_integrate", "post_integrate", "pair_compute", "post_force", "final_integrate",
+    for f in ("setup", "setup_neighbors", "initial_integrate", "post_integrate", "pair_compute", "post_force", "final_integrate",
               "end_of_step", "build_neighbors", "nlocal", "nghost", "nbuilds", "ndanger", "sync"):
         getattr(L, "sphbvf_" + f).argtypes = [vp]
     L.sphbvf_run.argtypes = [vp, ci]

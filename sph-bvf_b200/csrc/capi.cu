@@ -584,6 +584,22 @@ int sphbvf_setup(sphbvf_ctx *ctx) {
   return 0;
 }
 
+int sphbvf_setup_neighbors(sphbvf_ctx *ctx) {
+  if (!ctx->atoms_set) return ctx->fail(SPHBVF_ESTATE, "setup before set_atoms");
+  cudaSetDevice(ctx->cfg.device);
+  int rc;
+  if (ctx->cfg.nranks > 1) {
+    int v[3] = {ctx->any_solid, ctx->with_dev, ctx->e_nonzero};
+    if ((rc = comm_allreduce_max(ctx, v, 3))) return rc;
+    ctx->any_solid = v[0]; ctx->with_dev = v[1]; ctx->e_nonzero = v[2];
+  }
+  if ((rc = sphbvf_build_neighbors(ctx))) return rc;
+  ctx->nbuilds = 0;
+  ctx->ndanger = 0;
+  ctx->setup_done = 1;
+  return 0;
+}
+
 int sphbvf_initial_integrate(sphbvf_ctx *ctx) {
   ctx->tic(K_INITIAL);
   launch_initial_integrate(ctx->d, ctx->co, ctx->cfg.dt, ctx->ntimestep, ctx->cfg.integrate_groupbit, ctx->st);

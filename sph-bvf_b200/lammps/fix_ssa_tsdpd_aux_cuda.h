@@ -1,0 +1,60 @@
+/* -*- c++ -*- ----------------------------------------------------------
+   fix ssa_tsdpd/buoyancy/cuda, ssa_tsdpd/forcing/cuda, ssa_tsdpd/buffer/cuda, setforce/cuda
+
+   Twins of FixSsaTsdpdBuoyancy (fix_ssa_tsdpd_buoyancy.cpp:28-140), FixSsaTsdpdForcing
+   (fix_ssa_tsdpd_forcing.cpp:38-176), FixSsaTsdpdBuffer (fix_ssa_tsdpd_buffer.cpp:32-240) and of
+   FixSetForce with constant components (fix_setforce.cpp:40-290), with the same arguments.
+   They own no arithmetic: init() registers the parsed parameters with the device engine, and
+   the integrator fix ssa_tsdpd/bvf/<style>/cuda executes them inside the matching hook in Modify order.
+------------------------------------------------------------------------- */
+
+#ifdef FIX_CLASS
+
+FixStyle(ssa_tsdpd/buoyancy/cuda,FixSsaTsdpdBuoyancyCuda)
+FixStyle(ssa_tsdpd/forcing/cuda,FixSsaTsdpdForcingCuda)
+FixStyle(ssa_tsdpd/buffer/cuda,FixSsaTsdpdBufferCuda)
+FixStyle(setforce/cuda,FixSetForceCuda)
+
+#else
+
+#ifndef LMP_FIX_SSA_TSDPD_AUX_CUDA_H
+#define LMP_FIX_SSA_TSDPD_AUX_CUDA_H
+
+#include "fix.h"
+#include "sphbvf_lmp.h"
+
+namespace LAMMPS_NS {
+
+class FixSphbvfRegistered : public Fix {
+ public:
+  FixSphbvfRegistered(class LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg) { memset(&desc, 0, sizeof desc); }
+  int setmask() { return 0; }      // executed by the integrator fix on the device
+  void init();
+ protected:
+  SphbvfLmp::FixDesc desc;
+};
+
+class FixSsaTsdpdBuoyancyCuda : public FixSphbvfRegistered {
+ public:
+  FixSsaTsdpdBuoyancyCuda(class LAMMPS *, int, char **);
+};
+
+class FixSsaTsdpdForcingCuda : public FixSphbvfRegistered {
+ public:
+  FixSsaTsdpdForcingCuda(class LAMMPS *, int, char **);
+};
+
+class FixSsaTsdpdBufferCuda : public FixSphbvfRegistered {
+ public:
+  FixSsaTsdpdBufferCuda(class LAMMPS *, int, char **);
+};
+
+class FixSetForceCuda : public FixSphbvfRegistered {
+ public:
+  FixSetForceCuda(class LAMMPS *, int, char **);
+};
+
+}
+
+#endif
+#endif

@@ -1,0 +1,122 @@
+/* ----------------------------------------------------------------------
+   fix ssa_tsdpd/bvf/<style>/cuda -- host side of the integrator (csrc/kernels_integrate.cu).
+   Hook order per step is Verlet::run's (verlet.cpp:240-353):
+     initial_integrate -> post_integrate -> [pair/cuda: neighbour + pair kernel] -> post_force
+     -> final_integrate -> end_of_step
+   The host arrays of class Atom are refreshed only when LAMMPS is about to read them: on
+   timesteps with thermo / dump output (output->next) and at the end of the run.
+------------------------------------------------------------------------- */
+
+#include <string.h>
+#include "fix_ssa_tsdpd_bvf_cuda.h"
+#include "sphbvf_lmp.h"
+#include "atom.h"
+#include "error.h"
+#include "force.h"
+#include "output.h"
+#include "pair.h"
+#include "update.h"
+
+using namespace LAMMPS_NS;
+using namespace FixConst;
+
+/* ---------------------------------------------------------------------- */
+
+FixSsaTsdpdBvfCuda::FixSsaTsdpdBvfCuda(LAMMPS *lmp, int narg, char **arg, int variant_in) : Fix(lmp, narg, arg)
+{
+  if ((atom->e_flag != 1) || (atom->rho_flag != 1))
+    error->all(FLERR, "fix ssa_tsdpd/bvf command requires atom_style with both energy and density");
+  if (narg != 3) error->all(FLERR, "Illegal number of arguments for fix ssa_tsdpd/bvf command");
+  time_integrate = 1;
+  variant = variant_in;
+  engine = SphbvfLmp::get(lmp);
+}
+
+/* ---------------------------------------------------------------------- */
+
+int FixSsaTsdpdBvfCuda::setmask()
+{
+  int mask = 0;
+  mask |= INITIAL_INTEGRATE;
+  mask |= POST_INTEGRATE;
+  mask |= PRE_FORCE;        // setup_pre_force only, like the reference (mask bit without a pre_force body)
+  mask |= POST_FORCE;
+  mask |= FINAL_INTEGRATE;
+  mask |= END_OF_STEP;
+  return mask;
+}
+
+/* ---------------------------------------------------------------------- */
+
+void FixSsaTsdpdBvfCuda::init()
+{
+  engine = SphbvfLmp::get(lmp);
+  if (!force->pair || !strstr(force->pair_style, "/cuda"))
+    error->all(FLERR, "fix ssa_tsdpd/bvf/<style>/cuda requires pair_style ssa_tsdpd/bvf/<style>/cuda");
+  if (engine->variant != variant)
+    error->all(FLERR, "fix ssa_tsdpd/bvf/<style>/cuda and pair_style ssa_tsdpd/bvf/<style>/cuda must be the same variant");
+  engine->integrate_groupbit = groupbit;
+}
+
+/* ----------------------------------------------------------------------
+   vest = v, rhoI = rho on the host, before the atoms are uploaded by the first Pair::compute
+   (fix_ssa_tsdpd_bvf_transport_velocity.cpp:76-95)
+------------------------------------------------------------------------- */
+
+void FixSsaTsdpdBvfCuda::setup_pre_force(int)
+{
+  engine->stop();   // a previous run's context, if any: host arrays are authoritative between runs
+  double **v = atom->v;
+  double **vest = atom->vest;
+  double *rhoI = atom->rhoI;
+  double *rho = atom->rho;
+  int *mask = atom->mask;
+  int nlocal = atom->nlocal;
+  if (igroup == atom->firstgroup) nlocal = atom->nfirst;
+  for (int i = 0; i < nlocal; i++) {
+    if (mask[i] & groupbit) {
+      vest[i][0] = v[i][0];
+      vest[i][1] = v[i][1];
+      vest[i][2] = v[i][2];
+      rhoI[i] = rho[i];
+    }
+  }
+}
+
+/* modify->setup(): post_force of the registered fixes once (FixSetForce::setup, FixSsaTsdpdBuoyancy::setup) */
+
+void FixSsaTsdpdBvfCuda::setup(int vflag)
+{
+  post_force(vflag);
+  engine->to_host();   // thermo output of step 0 reads the host arrays
+}
+
+/* ---------------------------------------------------------------------- */
+
+void FixSsaTsdpdBvfCuda::initial_integrate(int)
+{
+  engine->check(sphbvf_set_timestep(engine->ctx, (long)update->ntimestep));
+  engine->check(sphbvf_initial_integrate(engine->ctx));
+  engine->mark_dirty();
+}
+
+void FixSsaTsdpdBvfCuda::post_integrate() { engine->check(sphbvf_post_integrate(engine->ctx)); }
+
+void FixSsaTsdpdBvfCuda::post_force(int) { engine->check(sphbvf_post_force(engine->ctx)); }
+
+void FixSsaTsdpdBvfCuda::final_integrate() { engine->check(sphbvf_final_integrate(engine->ctx)); }
+
+void FixSsaTsdpdBvfCuda::end_of_step()
+{
+  engine->check(sphbvf_end_of_step(engine->ctx));
+  if (update->ntimestep == output->next) engine->to_host();
+}
+
+void FixSsaTsdpdBvfCuda::post_run() { engine->stop(); }
+
+/* ---------------------------------------------------------------------- */
+
+void FixSsaTsdpdBvfCuda::reset_dt()
+{
+  if (engine->active()) engine->check(sphbvf_set_dt(engine->ctx, update->dt));
+}

@@ -1,0 +1,56 @@
+/* -*- c++ -*- ----------------------------------------------------------
+   sphbvf_lmp.h -- glue between the LAMMPS-style "/cuda" classes of this directory and the C ABI
+   of libsphbvf.so (include/sphbvf.h).  One engine per LAMMPS instance: it owns the sphbvf_ctx,
+   uploads the atoms of class Atom when a run starts, and copies device state back into the
+   host arrays only when LAMMPS is about to read them (thermo / dump steps, end of run).
+
+   These files are meant to be dropped into the reference's src/ (see INTEGRATION.md): they use
+   only LAMMPS' public class interfaces of the 22Aug2018 fork and the C ABI -- no CUDA headers.
+------------------------------------------------------------------------- */
+
+#ifndef LMP_SPHBVF_LMP_H
+#define LMP_SPHBVF_LMP_H
+
+#include "pointers.h"
+#include "sphbvf.h"
+
+namespace LAMMPS_NS {
+
+class SphbvfLmp : protected Pointers {
+ public:
+  static SphbvfLmp *get(class LAMMPS *);   // created on first use, destroyed with the pair style
+  static void release(class LAMMPS *);
+
+  SphbvfLmp(class LAMMPS *);
+  ~SphbvfLmp();
+
+  // ---- filled by the style classes before a run starts
+  int variant;                       // enum sphbvf_variant, set by the pair style
+  class Pair *pair;                  // the /cuda pair style (owner of the coefficient arrays)
+  double *rho0, *soundspeed, *G0;    // [ntypes+1], owned by the pair style
+  double **viscosity, **cut, **cutc; // [ntypes+1][ntypes+1]
+  double ***kappa;                   // [ntypes+1][ntypes+1][S]
+  int integrate_groupbit;            // set by the integrator fix
+  int nfixdesc;
+  struct FixDesc { int kind, groupbit, ia[4]; bigint step; double a[6]; } fixdesc[16];
+
+  void reset_fixes() { nfixdesc = 0; }         // Pair::init_style (force->init precedes modify->init)
+  void add_fix(const FixDesc &);               // Fix::init of the auxiliary /cuda fixes, in Modify order
+
+  // ---- the hooks, called by the pair style and the integrator fix
+  void start();                 // first Pair::compute of a run: create ctx, upload, neighbour setup
+  void stop();                  // end of run (Fix::post_run) or destruction: download, destroy ctx
+  bool active() const { return ctx != NULL; }
+  void check(int rc);           // rc != 0 -> error->one(FLERR, sphbvf_last_error())
+  void to_host();               // device -> class Atom arrays (all fields the package owns)
+  void mark_dirty() { host_current = 0; }
+  sphbvf_ctx *ctx;
+
+ private:
+  int host_current;
+  int nlocal_uploaded;
+};
+
+}
+
+#endif

