@@ -41,6 +41,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 B_ALG_PAIR = 240.0      # algorithmic bytes / atom-step of the pair pass
 B_ALG_STEP = 616.0      # whole step
 F_ALG_PAIR = 1.2e4      # FP64 flop / atom-step, 3D bulk (2.8e3 + 9.2e3)
+TRAFFIC_PAIR_B_PER_ATOM = 532.0   # measured DRAM bytes / atom of pair_kernel (profiles/r01c_*: 895 MB + 221 MB for 2.10 M atoms)
 WEAK_N = {1: 200, 2: 252, 4: 318, 8: 400}
 
 
@@ -214,7 +215,7 @@ def measured_peaks():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--n", type=int, default=0, help="lattice edge (default: weak-scaling table)")
     ap.add_argument("--impl", default="ours")
@@ -314,44 +315,60 @@ def main():
     pair_ms = fam["pair"]["ms"] / max(K, 1)
     peaks, peak_kind = measured_peaks()
     achieved = B_ALG_PAIR * eng.nlocal / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
-    fp64_peak = float(os.environ.get("SPHBVF_FP64_PEAK_TFLOPS", "0") or 0)
+    # FP64 vector peak: 64 FMA/clk/SM (ncu sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained
+    # = 9472 inst/cycle on 148 SMs) x 2 flop x max SM clock
+    fp64_peak = float(os.environ.get("SPHBVF_FP64_PEAK_TFLOPS", "0") or 0) or 148 * 64 * 2 * 1.965e9 / 1e12
     roof = {"bound": "hbm", "kernel": "pair_kernel (fused density/BVF + force pass)", "achieved": achieved,
-            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/): 532 B/atom
+            "traffic": TRAFFIC_PAIR_B_PER_ATOM * eng.nlocal,
             "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650 GB/s",
             "algorithmic_bytes_per_atom_step": B_ALG_PAIR, "pair_ms_per_step": pair_ms,
             "fp64_tflops_algorithmic": F_ALG_PAIR * eng.nlocal / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0,
-            "note": "the pair pass is FP64-pipe bound (AI ~ 50 flop/B, SURVEY.md 8d); HBM fraction reported as the contract asks"}
+            "note": "the pair pass is FP64-pipe / gather-latency bound (AI ~ 50 flop/B, SURVEY.md 8d); HBM fraction reported "
+                    "as the contract asks, fp64_frac is the meaningful roof"}
     if fp64_peak:
         roof["fp64_peak_tflops"] = fp64_peak
         roof["fp64_frac"] = roof["fp64_tflops_algorithmic"] / fp64_peak
 
-    # e2e: host-authoritative stepping through the C ABI with pinned host buffers
+    # e2e: host-authoritative stepping through the C ABI with pinned host buffers, every rank: per
+    # step the integrator/pair inputs go host->device and the step's results device->host (rows in
+    # device order, which the download of the previous step established)
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         F = pkg.FIELDS
         ins = ["x", "v", "vest", "rho", "rhoI"]
         outs = ["x", "v", "vest", "rho", "rhoI", "f", "drho", "phi"]
         ncol = {"x": 3, "v": 3, "vest": 3, "f": 3}
-        hbuf = {k: torch.empty((nloc0, ncol.get(k, 1)), dtype=torch.float64).pin_memory() for k in set(ins + outs)}
+        cap = eng.nlocal + eng.nlocal // 8 + 4096
+        hbuf = {k: torch.empty((cap, ncol.get(k, 1)), dtype=torch.float64).pin_memory() for k in set(ins + outs)}
         for k in ins:
-            eng.download_ptr(F[k], hbuf[k].data_ptr())
+            eng.download_local_ptr(F[k], hbuf[k].data_ptr(), cap)
+        moved = [0, 0]
 
         def e2e_steps(steps):
             for _ in range(steps):
+                nl = eng.nlocal
                 for k in ins:
-                    eng.upload_ptr(F[k], hbuf[k].data_ptr())
+                    eng.upload_local_ptr(F[k], hbuf[k].data_ptr(), nl)
                 eng.step_pieces()
+                nl = eng.nlocal
                 for k in outs:
-                    eng.download_ptr(F[k], hbuf[k].data_ptr())
+                    eng.download_local_ptr(F[k], hbuf[k].data_ptr(), cap)
+                moved[0] += sum(8 * nl * ncol.get(k, 1) for k in ins)
+                moved[1] += sum(8 * nl * ncol.get(k, 1) for k in outs)
 
         ke = max(3, min(K, 10))
         e2e_steps(2)
+        moved[:] = [0, 0]
         ms_e = timed(e2e_steps, ke)
-        bi = sum(8 * nloc0 * ncol.get(k, 1) for k in ins)
-        bo = sum(8 * nloc0 * ncol.get(k, 1) for k in outs)
-        e2e = {"value": natoms * ke / (ms_e * 1e-3), "unit": "atom-steps/s", "h2d_bytes_per_step": bi,
-               "d2h_bytes_per_step": bo, "steps": ke, "mode": "host-authoritative: upload x,v,vest,rho,rhoI -> one device step "
-               "-> download x,v,vest,rho,rhoI,f,drho,phi, pinned host memory, every step"}
+        tot = torch.tensor(moved, device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot)
+        e2e = {"value": natoms * ke / (ms_e * 1e-3), "unit": "atom-steps/s", "h2d_bytes_per_step": int(tot[0].item() / ke),
+               "d2h_bytes_per_step": int(tot[1].item() / ke), "steps": ke,
+               "mode": "host-authoritative through the C ABI: upload x,v,vest,rho,rhoI -> one device step (hooks) -> "
+                       "download x,v,vest,rho,rhoI,f,drho,phi; pinned host memory; every step, every rank"}
 
     cpu = None
     if rank == 0 and not args.no_cpu and world == 1:

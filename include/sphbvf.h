@@ -98,6 +98,9 @@ int sphbvf_upload(sphbvf_ctx *ctx, int field, const void *host);
 int sphbvf_download(sphbvf_ctx *ctx, int field, void *host);
 /* multi-rank: atoms migrate, so rows come in device order; pair with SPHBVF_F_TAG */
 int sphbvf_download_local(sphbvf_ctx *ctx, int field, void *host, int cap_rows);
+/* overwrite one field with rows in device order, i.e. the order of the last download_local (valid
+ * until the next neighbour rebuild reorders the atoms); nrows must equal sphbvf_nlocal */
+int sphbvf_upload_local(sphbvf_ctx *ctx, int field, const void *host, int nrows);
 
 /* ---- auxiliary fixes (registered once, executed inside the matching hook in the order added,
  * modify.cpp:385-480).  The /cuda fix classes may instead call the *_now entry points. */

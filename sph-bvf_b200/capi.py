@@ -32,7 +32,7 @@ _lib = None
 # every symbol include/sphbvf.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["sphbvf_version", "sphbvf_device_count", "sphbvf_create", "sphbvf_destroy", "sphbvf_last_error",
            "sphbvf_set_type", "sphbvf_set_pair", "sphbvf_set_dt", "sphbvf_set_timestep", "sphbvf_set_run_length",
-           "sphbvf_set_atoms", "sphbvf_upload", "sphbvf_download", "sphbvf_download_local", "sphbvf_add_buoyancy",
+           "sphbvf_set_atoms", "sphbvf_upload", "sphbvf_download", "sphbvf_download_local", "sphbvf_upload_local", "sphbvf_add_buoyancy",
            "sphbvf_add_forcing", "sphbvf_add_buffer", "sphbvf_add_setforce", "sphbvf_setup", "sphbvf_run",
            "sphbvf_setup_neighbors",
            "sphbvf_initial_integrate", "sphbvf_post_integrate", "sphbvf_neighbor", "sphbvf_pair_compute",
@@ -67,6 +67,7 @@ def lib():
     L.sphbvf_upload.argtypes = [vp, ci, vp]
     L.sphbvf_download.argtypes = [vp, ci, vp]
     L.sphbvf_download_local.argtypes = [vp, ci, vp, ci]
+    L.sphbvf_upload_local.argtypes = [vp, ci, vp, ci]
     L.sphbvf_add_buoyancy.argtypes = [vp, ci, ci, cd, ci, ci, cd]
     L.sphbvf_add_forcing.argtypes = [vp, ci, ci, cl, ci, ci, cd, cd, cd, cd, cd]
     L.sphbvf_add_buffer.argtypes = [vp, ci, ci, ci, cl, ci, cd, cd, cd, cd, cd]
@@ -219,6 +220,12 @@ class Engine:
 
     def download_ptr(self, field_id, ptr):
         self._ck(lib().sphbvf_download(self.h, field_id, ptr))
+
+    def upload_local_ptr(self, field_id, ptr, nrows):
+        self._ck(lib().sphbvf_upload_local(self.h, field_id, ptr, nrows))
+
+    def download_local_ptr(self, field_id, ptr, cap_rows):
+        self._ck(lib().sphbvf_download_local(self.h, field_id, ptr, cap_rows))
 
     def pairs(self):
         n = lib().sphbvf_get_pairs(self.h, None, 0)

@@ -789,6 +789,19 @@ int sphbvf_download_local(sphbvf_ctx *ctx, int field, void *host, int cap_rows) 
   return 0;
 }
 
+int sphbvf_upload_local(sphbvf_ctx *ctx, int field, const void *host, int nrows) {
+  void *p;
+  int nc, is_int;
+  if (!field_info(ctx, field, &p, &nc, &is_int)) return ctx->fail(SPHBVF_EINVAL, "unknown field %d", field);
+  const int n = ctx->d.nlocal;
+  if (nrows != n) return ctx->fail(SPHBVF_EINVAL, "upload_local: %d rows given, %d atoms owned", nrows, n);
+  if (!n || !nc) return 0;
+  cudaSetDevice(ctx->cfg.device);
+  CK(cudaMemcpyAsync(p, host, (is_int ? 4 : 8) * (size_t)n * nc, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
 int sphbvf_upload(sphbvf_ctx *ctx, int field, const void *host) {
   void *p;
   int nc, is_int, rc;

@@ -14,7 +14,8 @@
 // A brick that is its own neighbour across a periodic face (one brick in that dimension)
 // exchanges with itself through a device copy; the arithmetic x + shift is the reference's
 // (atom_vec_ssa_tsdpd_atomic.cpp:487-500).
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is bound at run time, see NcclApi
 #include <string.h>
 
 #include <algorithm>
@@ -25,6 +26,39 @@
 using namespace sphbvf;
 
 namespace {
+
+// libnccl.so.2 is dlopen'ed on first use instead of being a link-time dependency: single-GPU and
+// CPU-only processes never load it, and a process that already holds an NCCL (PyTorch bundles its
+// own libnccl.so.2) gets that same copy instead of a second one with clashing symbols.
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId;
+  decltype(&ncclCommInitRank) CommInitRank;
+  decltype(&ncclCommDestroy) CommDestroy;
+  decltype(&ncclGetErrorString) GetErrorString;
+  decltype(&ncclGroupStart) GroupStart;
+  decltype(&ncclGroupEnd) GroupEnd;
+  decltype(&ncclSend) Send;
+  decltype(&ncclRecv) Recv;
+  decltype(&ncclAllGather) AllGather;
+  decltype(&ncclAllReduce) AllReduce;
+  bool ok = false;
+};
+
+NcclApi *nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.ok ? &api : nullptr;
+  tried = true;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return nullptr;
+#define BIND(name) api.name = (decltype(api.name))dlsym(h, "nccl" #name); if (!api.name) return nullptr
+  BIND(GetUniqueId); BIND(CommInitRank); BIND(CommDestroy); BIND(GetErrorString); BIND(GroupStart); BIND(GroupEnd);
+  BIND(Send); BIND(Recv); BIND(AllGather); BIND(AllReduce);
+#undef BIND
+  api.ok = true;
+  return &api;
+}
 
 constexpr int ND = 27;       // directions (dx+1) + 3 (dy+1) + 9 (dz+1); 13 = stay
 constexpr int NHALO = 16;    // pA pB pC pD
@@ -61,7 +95,7 @@ struct CommState {
   do {                                                                                             \
     ncclResult_t r_ = (call);                                                                      \
     if (r_ != ncclSuccess)                                                                         \
-      return ctx->fail(SPHBVF_ECOMM, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(r_), __FILE__, __LINE__); \
+      return ctx->fail(SPHBVF_ECOMM, "%s failed: %s (%s:%d)", #call, nccl_api()->GetErrorString(r_), __FILE__, __LINE__); \
   } while (0)
 
 static inline int nblocks(long n, int t) { return (int)((n + t - 1) / t); }
@@ -298,7 +332,7 @@ static int exchange_counts(sphbvf_ctx *ctx, const int *d_local, int *sendcnt, in
   CommState *c = ctx->comm;
   const int P = ctx->cfg.nranks;
   int *gathered = c->d_counts + 2 * ND;
-  NK(ncclAllGather(d_local, gathered, ND, ncclInt, c->comm, ctx->st));
+  NK(nccl_api()->AllGather(d_local, gathered, ND, ncclInt, c->comm, ctx->st));
   CK(cudaMemcpyAsync(c->h_counts, gathered, sizeof(int) * ND * P, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   for (int dcode = 0; dcode < ND; dcode++) {
@@ -326,16 +360,16 @@ static int exchange_payload(sphbvf_ctx *ctx, const int *sendcnt, const int *send
     } else if (sendcnt[dcode] || (recvcnt[dcode] && c->recv.peer[dcode] != me)) any = true;
   }
   if (!any) return 0;
-  NK(ncclGroupStart());
+  NK(nccl_api()->GroupStart());
   for (int dcode = 0; dcode < ND; dcode++)
     if (sendcnt[dcode] && c->send.peer[dcode] != me)
-      NK(ncclSend(c->sendbuf + (size_t)sendoff[dcode] * width, (size_t)sendcnt[dcode] * width, ncclDouble,
+      NK(nccl_api()->Send(c->sendbuf + (size_t)sendoff[dcode] * width, (size_t)sendcnt[dcode] * width, ncclDouble,
                   c->send.peer[dcode], c->comm, ctx->st));
   for (int dcode = ND - 1; dcode >= 0; dcode--)
     if (recvcnt[dcode] && c->recv.peer[dcode] != me)
-      NK(ncclRecv(c->recvbuf + (size_t)recvoff[dcode] * width, (size_t)recvcnt[dcode] * width, ncclDouble,
+      NK(nccl_api()->Recv(c->recvbuf + (size_t)recvoff[dcode] * width, (size_t)recvcnt[dcode] * width, ncclDouble,
                   c->recv.peer[dcode], c->comm, ctx->st));
-  NK(ncclGroupEnd());
+  NK(nccl_api()->GroupEnd());
   return 0;
 }
 
@@ -375,7 +409,7 @@ int comm_allreduce_max(sphbvf_ctx *ctx, int *vals, int n) {
   int *v = c->d_counts + 2 * ND + ND * ctx->cfg.nranks;
   for (int k = 0; k < n; k++) c->h_counts[k] = vals[k];
   CK(cudaMemcpyAsync(v, c->h_counts, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->st));
-  NK(ncclAllReduce(v, v, n, ncclInt, ncclMax, c->comm, ctx->st));
+  NK(nccl_api()->AllReduce(v, v, n, ncclInt, ncclMax, c->comm, ctx->st));
   CK(cudaMemcpyAsync(c->h_counts, v, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   for (int k = 0; k < n; k++) vals[k] = c->h_counts[k];
@@ -483,7 +517,7 @@ int comm_rebuild(sphbvf_ctx *ctx) {
 void comm_destroy(sphbvf_ctx *ctx) {
   CommState *c = ctx->comm;
   if (!c) return;
-  if (c->comm) ncclCommDestroy(c->comm);
+  if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
   for (void *p : {(void *)c->sendidx, (void *)c->sendbuf, (void *)c->recvbuf, (void *)c->d_counts, (void *)c->d_dir,
                   (void *)c->d_keep, (void *)c->d_pos})
     if (p) cudaFree(p);
@@ -494,11 +528,14 @@ void comm_destroy(sphbvf_ctx *ctx) {
 
 extern "C" int sphbvf_comm_unique_id(void *id128) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
-  return ncclGetUniqueId((ncclUniqueId *)id128) == ncclSuccess ? 0 : SPHBVF_ECOMM;
+  NcclApi *api = nccl_api();
+  if (!api) return SPHBVF_ECOMM;
+  return api->GetUniqueId((ncclUniqueId *)id128) == ncclSuccess ? 0 : SPHBVF_ECOMM;
 }
 
 extern "C" int sphbvf_comm_init(sphbvf_ctx *ctx, const void *id128) {
   if (ctx->comm) return ctx->fail(SPHBVF_ESTATE, "sphbvf_comm_init called twice");
+  if (!nccl_api()) return ctx->fail(SPHBVF_ECOMM, "libnccl.so.2 could not be loaded: %s", dlerror());
   const int P = ctx->cfg.nranks;
   if (ctx->cfg.procgrid[0] * ctx->cfg.procgrid[1] * ctx->cfg.procgrid[2] != P)
     return ctx->fail(SPHBVF_EINVAL, "procgrid %d x %d x %d does not match %d ranks", ctx->cfg.procgrid[0],
@@ -508,7 +545,7 @@ extern "C" int sphbvf_comm_init(sphbvf_ctx *ctx, const void *id128) {
   ctx->comm = c;
   ncclUniqueId id;
   memcpy(&id, id128, sizeof id);
-  NK(ncclCommInitRank(&c->comm, P, id, ctx->cfg.rank));
+  NK(nccl_api()->CommInitRank(&c->comm, P, id, ctx->cfg.rank));
   CK(cudaMalloc((void **)&c->d_counts, sizeof(int) * (2 * ND + ND * P + 8)));
   CK(cudaMallocHost((void **)&c->h_counts, sizeof(int) * (ND * P + 8)));
   double shift[ND * 3];
