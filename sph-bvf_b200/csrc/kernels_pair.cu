@@ -91,8 +91,11 @@ static bool make_tables(const Coeffs &co, PairTables &t) {
 
 // sqrt(x) for x > 0: MUFU.RSQ64H seed (2^-22.9) + two coupled Goldschmidt steps, branch free
 __device__ __forceinline__ double fast_sqrt(double x) {
+  // MUFU.RSQ64H reads the high word only; clamping it away from 0 (an integer op) keeps x == 0
+  // (coincident atoms) from producing inf * 0: then g = 0 * y = 0 and the result is exactly 0
+  const double xs = __hiloint2double(max(__double2hiint(x), 0x00200000), 0);
   double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
   double g = x * y, h = 0.5 * y;
   double r = fma(-g, h, 0.5);
   g = fma(g, r, g);
@@ -111,7 +114,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(y, e, y);
 }
 
-constexpr int RING = 12;  // list-entry prefetch depth (rows); even
+constexpr int RING = 16;  // list-entry prefetch depth (rows); power of two
 
 __device__ __forceinline__ void cp_async4(int *smem_dst, const int *gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -171,6 +174,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   double fx = 0, fy = 0, fz = 0, drho = 0, nd = 0, rA1 = 0, rA2 = 0, phi = 0;
   double ddvx = 0, ddvy = 0, ddvz = 0, nwx = 0, nwy = 0, nwz = 0;
   double ddxx = 0, ddxy = 0, ddxz = 0;
+  double spi = 0;           // sum_j s_ij rho_i a_i: the i-side transport term is vest_i times this
   double ddev[9];
   double Qs[MAXS];
   if (SOLIDS == 2)
@@ -199,7 +203,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     const double iwdelta = UNIFORM ? tb.row[MAXT + 1].iwdelta : myrow[tj].iwdelta;
     const double h2eps = UNIFORM ? tb.row[MAXT + 1].h2eps : myrow[tj].h2eps;
 
-    const double r = fast_sqrt(rsq + 1e-300);   // rsq == 0 (coincident atoms) must not give NaN
+    const double r = fast_sqrt(rsq);
     const double t = h - r, t2 = t * t;
     const double wfd = cwfd * t2;
     const double wf = cwf * t2 * t * (h + 3. * r);
@@ -208,17 +212,18 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     const double dvr = delx * velx + dely * vely + delz * velz;
     const double ai = Ci.x * delx + Ci.y * dely + Ci.z * delz;   // (v_i - vt_i) . del
     const double aj = Cj.x * delx + Cj.y * dely + Cj.z * delz;
+    const double qi = rhoi * ai, qj = rhoj * aj;
     const double S2 = Vi2 + Vj2;
     const double S2w = S2 * wfd;
 
     // ---- sweep A (pair_...transport_velocity.cpp:243-254); ddv is scaled by 70 B_i at the end
-    const double Vj2w = Vj2 * wf;
-    nd += Vj2w;
+    nd = fma(Vj2, wf, nd);
     rA2 += wf;
-    if (FILTER) rA1 += d.pD[j].x * wf;
-    ddvx += S2w * delx; ddvy += S2w * dely; ddvz += S2w * delz;
+    if (FILTER) rA1 = fma(d.pD[j].x, wf, rA1);
+    ddvx = fma(S2w, delx, ddvx); ddvy = fma(S2w, dely, ddvy); ddvz = fma(S2w, delz, ddvz);
     if (VARIANT != SPHBVF_TV) {   // ..._mechanics.cpp:250-252
-      ddxx -= Vj2w * velx; ddxy -= Vj2w * vely; ddxz -= Vj2w * velz;
+      const double Vj2w = Vj2 * wf;
+      ddxx = fma(-Vj2w, velx, ddxx); ddxy = fma(-Vj2w, vely, ddxy); ddxz = fma(-Vj2w, velz, ddxz);
     }
 
     // ---- pressure force (:396-399 / mechanics :408)
@@ -295,12 +300,16 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
 
     // ---- momentum (:497-529)
     if (!si) {
+      // chained FMAs into the accumulators (4 per component instead of 7 separately rounded ops);
+      // the i-side transport term s rho_i a_i vest_i has a per-atom constant vector: summed as a scalar
       const double fvisc = S2w * eta;
       const double s = -0.5 * S2w;
-      const double pi_ = s * (rhoi * ai), pj_ = s * (rhoj * aj);
-      fx += fvisc * velx - delx * fpair + (pi_ * Bi.x + pj_ * Bj.x) + fartx;
-      fy += fvisc * vely - dely * fpair + (pi_ * Bi.y + pj_ * Bj.y) + farty;
-      fz += fvisc * velz - delz * fpair + (pi_ * Bi.z + pj_ * Bj.z) + fartz;
+      const double pj_ = s * qj;
+      spi = fma(s, qi, spi);
+      fx = fma(fvisc, velx, fx); fy = fma(fvisc, vely, fy); fz = fma(fvisc, velz, fz);
+      fx = fma(-fpair, delx, fx); fy = fma(-fpair, dely, fy); fz = fma(-fpair, delz, fz);
+      fx = fma(pj_, Bj.x, fx); fy = fma(pj_, Bj.y, fy); fz = fma(pj_, Bj.z, fz);
+      if (SOLIDS) { fx += fartx; fy += farty; fz += fartz; }
     } else {
       double fviscs = 0.;
       if (dvr < 0.) {
@@ -322,17 +331,18 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
 
     // ---- density rate (:548-555); (vt_i - vt_j).del = dvr - ai + aj
     {
-      double inner = rhoi * (dvr - ai + aj) - (rhoi * ai + rhoj * aj);
+      // rho_i (dvr - a_i + a_j) - (rho_i a_i + rho_j a_j) = rho_i (dvr + a_j) - 2 q_i - q_j
+      double inner = fma(-2.0, qi, fma(rhoi, dvr + aj, -qj));
       if (VARIANT == SPHBVF_FSI)
-        inner -= damp * 2.0 * h * c0i * (rhoj - rhoi) * (rsq / (rsq + h2eps));
-      drho += wfd * Vj * inner;
+        inner -= damp * 2.0 * h * c0i * (rhoj - rhoi) * (rsq * fast_rcp(rsq + h2eps));
+      drho = fma(wfd * Vj, inner, drho);
     }
 
     // ---- BVF (:563-576)
     if (SOLIDS && !si && sj) {
-      phi += Vj2w;
+      phi = fma(Vj2, wf, phi);
       const double cc = wfd * Vj2;
-      nwx += cc * delx; nwy += cc * dely; nwz += cc * delz;
+      nwx = fma(cc, delx, nwx); nwy = fma(cc, dely, nwy); nwz = fma(cc, delz, nwz);
     }
 
     // ---- species (:678-720)
@@ -398,7 +408,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
 
   const double ddvc = 10.0 * 7.0 * co.B[ti];
   const size_t i3 = 3 * (size_t)i;
-  d.f[i3] = fx; d.f[i3 + 1] = fy; d.f[i3 + 2] = fz;
+  d.f[i3] = fma(spi, Bi.x, fx); d.f[i3 + 1] = fma(spi, Bi.y, fy); d.f[i3 + 2] = fma(spi, Bi.z, fz);
   d.drho[i] = drho;
   d.nd[i] = nd;
   d.rhoAux1[i] = rA1;
