@@ -131,7 +131,7 @@ static int ensure_capacity(sphbvf_ctx *ctx, int nmax, int nallmax) {
   if (nallmax > d.nallmax) {
     const size_t o = d.nallmax, n = nallmax;
 #define RE(p, w) CK(dev_realloc(p, o *(w), n *(w), st, true, true))
-    RE(d.pA, 1); RE(d.pB, 1); RE(d.pC, 1); RE(d.pD, 1); RE(d.pCs, S); RE(d.pdev, 9); RE(d.pflags, 1); RE(d.ptag, 1);
+    RE(d.prec, 1); RE(d.pD, 1); RE(d.pCs, S); RE(d.pdev, 9); RE(d.pflags, 1); RE(d.ptag, 1);
     RE(d.gowner, 1); RE(d.gshift, 3); RE(ctx->w.cellid, 1); RE(ctx->w.gorder, 1);
 #undef RE
     d.nallmax = nallmax;
@@ -201,6 +201,7 @@ static int init_neighbor(sphbvf_ctx *ctx) {
     int s = (int)(ctx->cutneighmax * g.inv[k]);
     if (s * size < ctx->cutneighmax) s++;
     g.s[k] = s;
+    if (s > 2) return ctx->fail(SPHBVF_EINVAL, "internal: stencil half-width %d > 2 (cells are cutneigh/2 or larger)", s);
     // cells strictly inside the brick cannot hold ghosts (one cell of safety margin per side)
     g.glo[k] = (int)floor((b.sublo[k] - lo) * g.inv[k]) + 2;
     g.ghi[k] = (int)floor((b.subhi[k] - lo) * g.inv[k]) - 2;
@@ -405,7 +406,7 @@ void sphbvf_destroy(sphbvf_ctx *ctx) {
   DevState &d = ctx->d;
   void *ptrs[] = {d.tag, d.type, d.mask, d.solid, d.fixed, d.slot, d.x, d.v, d.vest, d.rho, d.rhoI, d.e, d.C, d.dev,
                   d.f, d.nw, d.ddv, d.ddx, d.drho, d.phi, d.nd, d.rhoAux1, d.rhoAux2, d.Pnew, d.ddev, d.Q,
-                  d.pA, d.pB, d.pC, d.pD, d.pCs, d.pdev, d.pflags, d.ptag, d.xhold, d.gowner, d.gshift, d.neigh,
+                  d.prec, d.pD, d.pCs, d.pdev, d.pflags, d.ptag, d.xhold, d.gowner, d.gshift, d.neigh,
                   d.numneigh, ctx->w.cellid, ctx->w.perm, ctx->w.cell_count, ctx->w.cell_start, ctx->w.gcell_count,
                   ctx->w.gcell_start, ctx->w.gorder, ctx->w.scan_tmp, ctx->w.nimg, ctx->w.flags, ctx->w.tmp_perm};
   for (void *p : ptrs) if (p) cudaFree(p);

@@ -242,10 +242,11 @@ __global__ void halo_pack_kernel(const DevState d, const int S, const int with_d
   const int i = sendidx[s];
   const int R = NHALO + S + (with_dev ? 9 : 0) + (border ? 2 : 0);
   double *r = buf + (size_t)s * R;
-  Rec4 A = d.pA[i];
+  const Prec P = d.prec[i];
+  Rec4 A = P.A;
   // x + shift in the reference's order: one rounded add per shifted dimension
   A.x += t.shift[code][0]; A.y += t.shift[code][1]; A.z += t.shift[code][2];
-  const Rec4 B = d.pB[i], C = d.pC[i], D = d.pD[i];
+  const Rec4 B = P.B, C = P.C, D = d.pD[i];
   r[0] = A.x; r[1] = A.y; r[2] = A.z; r[3] = A.w;
   r[4] = B.x; r[5] = B.y; r[6] = B.z; r[7] = B.w;
   r[8] = C.x; r[9] = C.y; r[10] = C.z; r[11] = C.w;
@@ -264,9 +265,11 @@ __global__ void halo_unpack_kernel(const DevState d, const int S, const int with
   const int R = NHALO + S + (with_dev ? 9 : 0) + (border ? 2 : 0);
   const double *r = buf + (size_t)g * R;
   const int j = d.nlocal + g;
-  d.pA[j] = make_rec4(r[0], r[1], r[2], r[3]);
-  d.pB[j] = make_rec4(r[4], r[5], r[6], r[7]);
-  d.pC[j] = make_rec4(r[8], r[9], r[10], r[11]);
+  Prec P;
+  P.A = make_rec4(r[0], r[1], r[2], r[3]);
+  P.B = make_rec4(r[4], r[5], r[6], r[7]);
+  P.C = make_rec4(r[8], r[9], r[10], r[11]);
+  d.prec[j] = P;
   d.pD[j] = make_rec4(r[12], r[13], r[14], r[15]);
   int q = NHALO;
   for (int k = 0; k < S; k++) d.pCs[(size_t)j * S + k] = r[q++];

@@ -32,58 +32,70 @@ __device__ __forceinline__ void damp_factors(int variant, long ntimestep, double
   else dampSolid = tnow <= 1.0 ? 0.0 : 1.0;                              // ..._fsi.cpp:150-152
 }
 
+// Both integrators are pure streaming (HBM bound).  Every array an atom may need is loaded
+// UNCONDITIONALLY at the top of the kernel, before any branch on solid_tag / fixed_tag: with the
+// loads inside the branches the kernels ran at 23-30 % of HBM peak, all warps waiting on one
+// dependent round trip after another (ncu long_scoreboard 90 %, profiles/); the deviatoric tensors
+// (solids only) stay behind their branch.
 template <int VARIANT>
 __global__ void __launch_bounds__(256)
 initial_integrate_kernel(const DevState d, const __grid_constant__ Coeffs co, const double dtv, const long ntimestep,
                          const int groupbit) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.nlocal || !(d.mask[i] & groupbit)) return;
-  const double dtf = 0.5 * dtv;
-  const double dtfm = dtf / co.mass[d.type[i]];
+  if (i >= d.nlocal) return;
   const size_t i3 = 3 * (size_t)i;
+  const int mask = d.mask[i], type = d.type[i], solid = d.solid[i], fixed = d.fixed[i];
+  const double rho = d.rho[i], drho = d.drho[i];
+  double v[3], f[3], ddv[3], x[3], ddx[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 3; k++) { v[k] = d.v[i3 + k]; f[k] = d.f[i3 + k]; ddv[k] = d.ddv[i3 + k]; x[k] = d.x[i3 + k]; }
+  double ndi = 1.0;
+  if (VARIANT != SPHBVF_TV) {
+    ndi = d.nd[i];
+#pragma unroll
+    for (int k = 0; k < 3; k++) ddx[k] = d.ddx[i3 + k];
+  }
+  if (!(mask & groupbit)) return;
+  const double dtf = 0.5 * dtv;
+  const double dtfm = dtf / co.mass[type];
   double damp, dampSolid;
   damp_factors(VARIANT, ntimestep, damp, dampSolid);
-  const int solid = d.solid[i], fixed = d.fixed[i];
   if (fixed == 0) {
-    const double ndi = VARIANT != SPHBVF_TV ? d.nd[i] : 1.0;
     if (solid == 0) {
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         double vest;
-        if (VARIANT == SPHBVF_TV) vest = d.v[i3 + k] + dtfm * d.f[i3 + k];
-        else vest = d.v[i3 + k] + dtfm * d.f[i3 + k] * damp + 0.001 * d.ddx[i3 + k] / ndi;
-        const double v = vest - dtfm * d.ddv[i3 + k];
+        if (VARIANT == SPHBVF_TV) vest = v[k] + dtfm * f[k];
+        else vest = v[k] + dtfm * f[k] * damp + 0.001 * ddx[k] / ndi;
+        const double vn = vest - dtfm * ddv[k];
         d.vest[i3 + k] = vest;
-        d.v[i3 + k] = v;
-        d.x[i3 + k] += dtv * v;
+        d.v[i3 + k] = vn;
+        d.x[i3 + k] = x[k] + dtv * vn;
       }
     } else {
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        double vest, v = d.v[i3 + k];
-        const double fk = d.f[i3 + k];
-        if (VARIANT == SPHBVF_TV) vest = v + 2.0 * dtfm * fk;
-        else vest = v + 2.0 * dtfm * fk + 0.001 * d.ddx[i3 + k] / ndi;
-        v += dtfm * fk;
-        if (VARIANT != SPHBVF_TV) { vest *= dampSolid; v *= dampSolid; }
+        double vest, vn = v[k];
+        if (VARIANT == SPHBVF_TV) vest = vn + 2.0 * dtfm * f[k];
+        else vest = vn + 2.0 * dtfm * f[k] + 0.001 * ddx[k] / ndi;
+        vn += dtfm * f[k];
+        if (VARIANT != SPHBVF_TV) { vest *= dampSolid; vn *= dampSolid; }
         d.vest[i3 + k] = vest;
-        d.v[i3 + k] = v;
-        d.x[i3 + k] += dtf * v;     // sic: dtf (fix_...transport_velocity.cpp:183-185)
+        d.v[i3 + k] = vn;
+        d.x[i3 + k] = x[k] + dtf * vn;     // sic: dtf (fix_...transport_velocity.cpp:183-185)
       }
       const double cdev = VARIANT == SPHBVF_TV ? 0.5 * dtv : dtf;
       for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] += cdev * d.ddev[9 * (size_t)i + k];
     }
-    const double rho = d.rho[i];
     d.rhoI[i] = rho;
-    d.rho[i] = rho + dtf * d.drho[i];
+    d.rho[i] = rho + dtf * drho;
   } else {
     if (solid == 0) {
-      const double rho = d.rho[i];
       d.rhoI[i] = rho;
-      d.rho[i] = rho + dtf * d.drho[i];
+      d.rho[i] = rho + dtf * drho;
     } else {
       for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] += dtf * d.ddev[9 * (size_t)i + k];
-      d.rhoI[i] = d.rho[i];
+      d.rhoI[i] = rho;
     }
   }
   for (int k = 0; k < co.nspecies; k++) {
@@ -107,65 +119,73 @@ __global__ void __launch_bounds__(256)
 final_integrate_kernel(const DevState d, const __grid_constant__ Coeffs co, const double dtv, const long ntimestep,
                        const int groupbit) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.nlocal || !(d.mask[i] & groupbit)) return;
-  const double dtf = 0.5 * dtv;
-  const double dtfm = dtf / co.mass[d.type[i]];
+  if (i >= d.nlocal) return;
   const size_t i3 = 3 * (size_t)i;
   // freqFilter 20 (TV :287, mechanics :311); fsi: 1e16 -> INT_MAX, never fires (..._fsi.cpp:304)
   const bool filter = VARIANT == SPHBVF_FSI ? (ntimestep % 2147483647L) == 0 : (ntimestep % 20) == 0;
+  const int mask = d.mask[i], type = d.type[i], solid = d.solid[i], fixed = d.fixed[i];
+  const double nd = d.nd[i], phi0 = d.phi[i], drho = d.drho[i], rhoI = d.rhoI[i];
+  double nw[3], v[3], vest[3], f[3], ddx[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 3; k++) { nw[k] = d.nw[i3 + k]; v[k] = d.v[i3 + k]; vest[k] = d.vest[i3 + k]; f[k] = d.f[i3 + k]; }
+  if (VARIANT != SPHBVF_TV) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) ddx[k] = d.ddx[i3 + k];
+  }
+  double shep = 0.0;
+  if (filter) shep = d.rhoAux1[i] / d.rhoAux2[i];
+  if (!(mask & groupbit)) return;
+  const double dtf = 0.5 * dtv;
+  const double dtfm = dtf / co.mass[type];
   double damp, dampSolid;
   damp_factors(VARIANT, ntimestep, damp, dampSolid);
-  const int solid = d.solid[i], fixed = d.fixed[i];
-  const double nd = d.nd[i];
-  const double phi = d.phi[i] / nd;
+  const double phi = phi0 / nd;
   d.phi[i] = phi;
-  double nw[3];
 #pragma unroll
-  for (int k = 0; k < 3; k++) { nw[k] = d.nw[i3 + k] / nd; d.nw[i3 + k] = nw[k]; }
-  const double drho = d.drho[i], rhoI = d.rhoI[i];
+  for (int k = 0; k < 3; k++) { nw[k] = nw[k] / nd; d.nw[i3 + k] = nw[k]; }
   double rho;
   if (fixed == 0) {
     if (solid == 0) {
       if (phi > 0.5) {   // BVF wall reflection (fix_...transport_velocity.cpp:310-342)
-        double x[3], v[3];
+        double x[3], vr[3];
 #pragma unroll
-        for (int k = 0; k < 3; k++) { v[k] = d.v[i3 + k]; x[k] = d.x[i3 + k] - dtv * v[k]; }
+        for (int k = 0; k < 3; k++) { vr[k] = v[k]; x[k] = d.x[i3 + k] - dtv * vr[k]; }
         const double norm = sqrt(nw[0] * nw[0] + nw[1] * nw[1] + nw[2] * nw[2]);
         const double en[3] = {-nw[0] / norm, -nw[1] / norm, -nw[2] / norm};
-        const double vdot = v[0] * en[0] + v[1] * en[1] + v[2] * en[2];
+        const double vdot = vr[0] * en[0] + vr[1] * en[1] + vr[2] * en[2];
         const double mx = vdot > 0.0 ? vdot : 0.0;   // std::max(0.0, v_dot_en)
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-          v[k] = -v[k] + 2.0 * mx * en[k];
-          d.x[i3 + k] = x[k] + dtv * v[k];
+          vr[k] = -vr[k] + 2.0 * mx * en[k];
+          d.x[i3 + k] = x[k] + dtv * vr[k];
         }
       }
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        if (VARIANT == SPHBVF_TV) d.v[i3 + k] = d.vest[i3 + k] + dtfm * d.f[i3 + k];
-        else d.v[i3 + k] = d.vest[i3 + k] + dtfm * d.f[i3 + k] * damp + 0.001 * d.ddx[i3 + k] / nd;
+        if (VARIANT == SPHBVF_TV) d.v[i3 + k] = vest[k] + dtfm * f[k];
+        else d.v[i3 + k] = vest[k] + dtfm * f[k] * damp + 0.001 * ddx[k] / nd;
       }
-      if (VARIANT == SPHBVF_TV) rho = filter ? d.rhoAux1[i] / d.rhoAux2[i] + dtf * drho : rhoI + dtf * drho;
-      else rho = filter ? d.rhoAux1[i] / d.rhoAux2[i] + dtf * drho : rhoI + dtv * drho;
+      if (VARIANT == SPHBVF_TV) rho = filter ? shep + dtf * drho : rhoI + dtf * drho;
+      else rho = filter ? shep + dtf * drho : rhoI + dtv * drho;
     } else {
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        double v = d.v[i3 + k];
-        if (VARIANT == SPHBVF_TV) v += dtfm * d.f[i3 + k];
-        else { v += dtfm * d.f[i3 + k] + 0.001 * d.ddx[i3 + k] / nd; v *= dampSolid; }
-        d.v[i3 + k] = v;
+        double vn = v[k];
+        if (VARIANT == SPHBVF_TV) vn += dtfm * f[k];
+        else { vn += dtfm * f[k] + 0.001 * ddx[k] / nd; vn *= dampSolid; }
+        d.v[i3 + k] = vn;
       }
       const double cdev = VARIANT == SPHBVF_TV ? 0.5 * dtv : dtf;
       for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] += cdev * d.ddev[9 * (size_t)i + k];
-      if (VARIANT == SPHBVF_TV) rho = filter ? d.rhoAux1[i] / d.rhoAux2[i] + dtf * drho : rhoI + dtf * drho;
+      if (VARIANT == SPHBVF_TV) rho = filter ? shep + dtf * drho : rhoI + dtf * drho;
       else rho = rhoI + dtv * drho;
     }
   } else {
     if (solid == 0) {
-      rho = filter ? d.rhoAux1[i] / d.rhoAux2[i] + dtv * drho : rhoI + dtv * drho;
+      rho = filter ? shep + dtv * drho : rhoI + dtv * drho;
     } else {
       for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] += dtf * d.ddev[9 * (size_t)i + k];
-      rho = filter ? d.rhoAux1[i] / d.rhoAux2[i] : rhoI;
+      rho = filter ? shep : rhoI;
     }
   }
   d.rho[i] = rho;
@@ -264,9 +284,11 @@ pack_kernel(const DevState d, const __grid_constant__ Coeffs co, const int with_
   const double irho = 1.0 / rho;
   const double P = 7.0 * co.B[t] * (rho / co.rho0[t] - 1.0);
   const double Prr = P * irho * irho;
-  d.pA[i] = make_rec4(d.x[i3], d.x[i3 + 1], d.x[i3 + 2], rho);
-  d.pB[i] = make_rec4(vx, vy, vz, co.mass[t] * irho);
-  d.pC[i] = make_rec4(vx - d.v[i3], vy - d.v[i3 + 1], vz - d.v[i3 + 2], Prr);
+  Prec r;
+  r.A = make_rec4(d.x[i3], d.x[i3 + 1], d.x[i3 + 2], rho);
+  r.B = make_rec4(vx, vy, vz, co.mass[t] * irho);
+  r.C = make_rec4(vx - d.v[i3], vy - d.v[i3 + 1], vz - d.v[i3 + 2], Prr);
+  d.prec[i] = r;
   const int solid = d.solid[i];
   double art = 0.0;
   if (solid) {
@@ -295,14 +317,12 @@ __global__ void ghost_refresh_kernel(const DevState d, const int S, const int wi
   const int o = d.gowner[g];
   if (o < 0) return;   // ghost owned by another rank: filled by the halo exchange
   const int q = d.nlocal + g;
-  Rec4 A = d.pA[o];
+  Prec r = d.prec[o];
   // x + shift evaluated in the reference's order: one rounded add per shifted dimension
-  A.x += d.gshift[3 * (size_t)g];
-  A.y += d.gshift[3 * (size_t)g + 1];
-  A.z += d.gshift[3 * (size_t)g + 2];
-  d.pA[q] = A;
-  d.pB[q] = d.pB[o];
-  d.pC[q] = d.pC[o];
+  r.A.x += d.gshift[3 * (size_t)g];
+  r.A.y += d.gshift[3 * (size_t)g + 1];
+  r.A.z += d.gshift[3 * (size_t)g + 2];
+  d.prec[q] = r;
   d.pD[q] = d.pD[o];
   d.pflags[q] = d.pflags[o];
   for (int k = 0; k < S; k++) d.pCs[(size_t)q * S + k] = d.pCs[(size_t)o * S + k];

@@ -246,7 +246,7 @@ void launch_fill_images(const DevState &d, const Box &b, double cutghost, const 
 __global__ void ghost_cellid_kernel(const DevState d, const Grid g, const int dim, int *cellid, int *gcell_count, int *flags) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= d.nghost) return;
-  const Rec4 A = d.pA[d.nlocal + q];
+  const Rec4 A = d.prec[d.nlocal + q].A;
   bool ok;
   int c = cell_of(g, A.x, A.y, dim == 2 ? g.lo[2] : A.z, ok);
   if (!ok) c = -1;   // beyond the stencil reach of every owned atom: never a neighbour
@@ -293,7 +293,7 @@ build_list_kernel(const DevState d, const __grid_constant__ Grid g, const __grid
                   const int *__restrict__ gorder, const double cutmaxsq, int *flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.nlocal) return;
-  const Rec4 Ai = d.pA[i];
+  const Rec4 Ai = d.prec[i].A;
   const int ti = d.pflags[i] & 7;
   bool ok;
   const int ci = cell_of(g, Ai.x, Ai.y, co.dim == 2 ? g.lo[2] : Ai.z, ok);
@@ -346,7 +346,7 @@ build_list_kernel(const DevState d, const __grid_constant__ Grid g, const __grid
           for (int p = a; p < b; p++) {
             const int j = pass ? d.nlocal + gorder[p] : p;
             if (j == i) continue;
-            const Rec4 Aj = d.pA[j];
+            const Rec4 Aj = d.prec[j].A;
             const double rsq = rsq_nofma(Ai.x - Aj.x, Ai.y - Aj.y, Ai.z - Aj.z);
             if (UNIFORM) {
               if (rsq <= cutmaxsq) {

@@ -139,7 +139,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   const int fl = d.pflags[i];
   const int ti = fl & 7;
   const bool si = SOLIDS && ((fl >> 4) & 1);
-  const Rec4 Ai = d.pA[i], Bi = d.pB[i], Ci = d.pC[i];
+  const Rec4 Ai = d.prec[i].A, Bi = d.prec[i].B, Ci = d.prec[i].C;
   const double rhoi = Ai.w, Vi = Bi.w, Vi2 = Vi * Vi, Prri = Ci.w;
   const double c0i = co.c0[ti];
   const double Pi = Prri * rhoi * rhoi;
@@ -384,13 +384,13 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   int e1 = nn > 1 ? myring[128] : 0;
   Rec4 A0, B0, C0, A1, B1, C1;
   {
-    const int j = e0 & NEIGH_JMASK;
-    A0 = d.pA[j]; B0 = d.pB[j]; C0 = d.pC[j];
+    const Prec *p = d.prec + (e0 & NEIGH_JMASK);
+    A0 = p->A; B0 = p->B; C0 = p->C;
   }
   for (int kk = 0; kk < nn; kk += 2) {
     {
-      const int j = e1 & NEIGH_JMASK;
-      A1 = d.pA[j]; B1 = d.pB[j]; C1 = d.pC[j];
+      const Prec *p = d.prec + (e1 & NEIGH_JMASK);
+      A1 = p->A; B1 = p->B; C1 = p->C;
     }
     fetch2(kk + RING);   // slots of entries kk, kk+1: already in e0, e1
     asm volatile("cp.async.wait_group %0;" ::"n"(RING / 2 - 2) : "memory");   // entries <= kk+5 landed
@@ -398,8 +398,8 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * 128] : 0;
     body(e0, A0, B0, C0);
     {
-      const int j = e2 & NEIGH_JMASK;
-      A0 = d.pA[j]; B0 = d.pB[j]; C0 = d.pC[j];
+      const Prec *p = d.prec + (e2 & NEIGH_JMASK);
+      A0 = p->A; B0 = p->B; C0 = p->C;
     }
     if (kk + 1 < nn) body(e1, A1, B1, C1);
     e0 = e2;

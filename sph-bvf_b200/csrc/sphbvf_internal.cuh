@@ -48,6 +48,12 @@ __host__ __device__ __forceinline__ Rec4 make_rec4(double x, double y, double z,
   return r;
 }
 
+// the three records the pair kernel reads for every neighbour, contiguous: 96 bytes, 32-byte aligned
+// (1.33 particles per 128-byte line, no padding), so a visit touches 1-2 lines instead of 3
+struct __align__(32) Prec {
+  Rec4 A, B, C;
+};
+
 // cell grid used for sorting and for the list build (covers sub-box + ghost shell).
 // Cells are numbered TILE-major: the grid is cut into tiles of 2^tb[0] x 2^tb[1] x 2^tb[2] cells
 // (4x4x4 in 3D, 8x8x1 in 2D = 64 cells, about one CTA's worth of atoms), tiles x-fastest, cells
@@ -104,7 +110,8 @@ struct DevState {
   // pair outputs
   double *f, *nw, *ddv, *ddx, *drho, *phi, *nd, *rhoAux1, *rhoAux2, *Pnew, *ddev, *Q;
   // packed pair inputs (owned + ghost)
-  Rec4 *pA, *pB, *pC, *pD;
+  Prec *prec;
+  Rec4 *pD;
   double *pCs, *pdev;
   int *pflags, *ptag;
   // rebuild bookkeeping
