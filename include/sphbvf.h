@@ -83,6 +83,15 @@ int sphbvf_set_pair(sphbvf_ctx *ctx, int itype, int jtype, double eta, double h,
                     const double *kappa);
 /* reset_dt() of the integrator fixes (fix_ssa_tsdpd_bvf_transport_velocity.cpp:465-468) */
 int sphbvf_set_dt(sphbvf_ctx *ctx, double dt);
+/* the stochastic stress term (pair_ssa_tsdpd_bvf_transport_velocity.cpp:403-431), active when some
+ * atom has ssa_tsdpd/e != 0: kboltz = force->boltz of the unit system, seed = any 64-bit number.
+ * The reference seeds a sequential Marsaglia generator from clock() (:957-959) and draws d*d
+ * Gaussians per half-list pair, so its random forces are neither reproducible nor independent of
+ * the list orientation; here the symmetric traceless matrix of a pair is a pure function of
+ * (seed, timestep, min tag, max tag) (Philox-4x32-10 + Box-Muller), hence identical for both
+ * partners (momentum conserving without Newton mirroring), independent of decomposition and
+ * reproducible; e_ij = (e_i + e_j)/2.  Not calling this leaves the term switched off. */
+int sphbvf_set_random(sphbvf_ctx *ctx, double kboltz, unsigned long long seed);
 /* update->ntimestep / update->nsteps as seen by the styles */
 int sphbvf_set_timestep(sphbvf_ctx *ctx, long ntimestep);
 int sphbvf_set_run_length(sphbvf_ctx *ctx, long nsteps);

@@ -31,7 +31,7 @@ _lib = None
 
 # every symbol include/sphbvf.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["sphbvf_version", "sphbvf_device_count", "sphbvf_create", "sphbvf_destroy", "sphbvf_last_error",
-           "sphbvf_set_type", "sphbvf_set_pair", "sphbvf_set_dt", "sphbvf_set_timestep", "sphbvf_set_run_length",
+           "sphbvf_set_type", "sphbvf_set_pair", "sphbvf_set_dt", "sphbvf_set_random", "sphbvf_set_timestep", "sphbvf_set_run_length",
            "sphbvf_set_atoms", "sphbvf_upload", "sphbvf_download", "sphbvf_download_local", "sphbvf_upload_local", "sphbvf_add_buoyancy",
            "sphbvf_add_forcing", "sphbvf_add_buffer", "sphbvf_add_setforce", "sphbvf_setup", "sphbvf_run",
            "sphbvf_setup_neighbors",
@@ -61,6 +61,7 @@ def lib():
     L.sphbvf_set_type.argtypes = [vp, ci, cd, cd, cd, cd]
     L.sphbvf_set_pair.argtypes = [vp, ci, ci, cd, cd, cd, vp]
     L.sphbvf_set_dt.argtypes = [vp, cd]
+    L.sphbvf_set_random.argtypes = [vp, cd, C.c_ulonglong]
     L.sphbvf_set_timestep.argtypes = [vp, cl]
     L.sphbvf_set_run_length.argtypes = [vp, cl]
     L.sphbvf_set_atoms.argtypes = [vp, ci] + [vp] * 11
@@ -161,6 +162,9 @@ class Engine:
                 f64(Cc) if self.S else None, f64(dev)]
         self.n = len(keep[0])
         self._ck(lib().sphbvf_set_atoms(self.h, self.n, *[_p(a) for a in keep]))
+
+    def set_random(self, kboltz, seed):
+        self._ck(lib().sphbvf_set_random(self.h, kboltz, seed))
 
     def set_run_length(self, n):
         self._ck(lib().sphbvf_set_run_length(self.h, n))

@@ -328,6 +328,10 @@ static PairFlags pair_flags(const sphbvf_ctx *ctx) {
   // (pair_ssa_tsdpd_bvf_fsi.cpp:531-539)
   const double tnow = ctx->ntimestep * ctx->cfg.dt, tmax = ctx->cfg.dt * ctx->run_nsteps;
   pf.damp = (var == SPHBVF_FSI && tnow <= tmax) ? 0.1 : 0.0;
+  pf.random = ctx->e_nonzero && ctx->random_set;
+  pf.rand_pref = 4.0 * ctx->kboltz / ctx->cfg.dt;
+  pf.seed = ctx->seed;
+  pf.ntimestep = ctx->ntimestep;
   return pf;
 }
 
@@ -445,6 +449,13 @@ int sphbvf_set_pair(sphbvf_ctx *ctx, int i, int j, double eta, double h, double 
 }
 
 int sphbvf_set_dt(sphbvf_ctx *ctx, double dt) { ctx->cfg.dt = dt; return 0; }
+int sphbvf_set_random(sphbvf_ctx *ctx, double kboltz, unsigned long long seed) {
+  if (!(kboltz >= 0.0)) return ctx->fail(SPHBVF_EINVAL, "set_random: kboltz must be >= 0");
+  ctx->kboltz = kboltz;
+  ctx->seed = seed;
+  ctx->random_set = 1;
+  return 0;
+}
 int sphbvf_set_timestep(sphbvf_ctx *ctx, long n) { ctx->ntimestep = n; return 0; }
 int sphbvf_set_run_length(sphbvf_ctx *ctx, long n) { ctx->run_nsteps_user = n; ctx->run_nsteps = n; return 0; }
 

@@ -28,6 +28,9 @@ struct sphbvf_ctx {
   int ago = 0, nbuilds = 0, ndanger = 0, maxneigh_seen = 0;
   int atoms_set = 0, setup_done = 0, with_dev = 0, any_solid = 0, e_nonzero = 0, migrated = 0;
   double cutneighmax = 0.0, triggersq = 0.0;
+  int random_set = 0;
+  double kboltz = 0.0;
+  unsigned long long seed = 0;
   long scan_cap = 0;
   int *h_flags = nullptr;      // pinned, 16 ints
   void *h_stage = nullptr;     // pinned staging (halo counts)

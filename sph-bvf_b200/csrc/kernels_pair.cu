@@ -121,12 +121,35 @@ __device__ __forceinline__ void cp_async4(int *smem_dst, const int *gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
 }
 
+// ---- counter-based randomness for the stochastic stress term: Philox-4x32-10 (Salmon et al. 2011)
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// two independent standard normals from 64 random bits (Box-Muller; u1 in (0, 1])
+__device__ __forceinline__ void gauss2(unsigned a, unsigned b, double &g0, double &g1) {
+  const double u1 = ((double)a + 1.0) * (1.0 / 4294967296.0), u2 = (double)b * (1.0 / 4294967296.0);
+  const double rad = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  g0 = rad * cs;
+  g1 = rad * sn;
+}
+
 // SOLIDS: 0 = no atom has solid_tag, 1 = solids whose deviatoric stress is identically zero
 // (rigid walls: G0 == 0, dev == 0), 2 = elastic solids (deviatoric tensors gathered)
-template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER>
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM>
 __global__ void __launch_bounds__(128, PAIR_MINB)
 pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
-            const double damp) {
+            const double damp, const double rand_pref, const unsigned long long seed, const long ntimestep) {
   __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
   __shared__ int ring[RING][128];
   if (!UNIFORM) {
@@ -168,6 +191,8 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   double Cspec_i[MAXS];
   if (SPECIES)
     for (int k = 0; k < co.nspecies; k++) Cspec_i[k] = d.pCs[(size_t)i * co.nspecies + k];
+  const double ei = RANDOM ? d.pD[i].w : 0.0;
+  const int tagi = RANDOM ? d.ptag[i] : 0;
   double G0i = co.G0[ti];
   if (VARIANT == SPHBVF_FSI && SPECIES) G0i = co.G0[ti] * (1.0 - 0.99 * Cspec_i[0]);
 
@@ -310,6 +335,40 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
       fx = fma(-fpair, delx, fx); fy = fma(-fpair, dely, fy); fz = fma(-fpair, delz, fz);
       fx = fma(pj_, Bj.x, fx); fy = fma(pj_, Bj.y, fy); fz = fma(pj_, Bj.z, fz);
       if (SOLIDS) { fx += fartx; fy += farty; fz += fartz; }
+      if (RANDOM) {
+        // f_rand = sqrt(-4 kB e m_i m_j wfd / (rho_i rho_j dt)) / (r + 0.01 h) * (Wn . del)   (:403-431), with
+        // Wn the symmetric traceless part of a d x d Gaussian matrix: off-diagonals N(0, 1/2), diagonal
+        // g_ll - mean(g).  The matrix depends on (seed, step, min tag, max tag) only, so the partner
+        // computes the same one with del -> -del: equal and opposite forces.
+        const double eij = 0.5 * (ei + d.pD[j].w);
+        const int tagj = d.ptag[j];
+        const double pref = sqrt(fmax(-rand_pref * eij * (Vi * Vj) * wfd, 0.0)) * fast_rcp(r + 0.01 * h);
+        const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+        const unsigned tlo = (unsigned)min(tagi, tagj), thi = (unsigned)max(tagi, tagj);
+        const uint4 r0 = philox4x32(make_uint4(tlo, thi, (unsigned)ntimestep, (unsigned)(ntimestep >> 32) << 1), key);
+        double g0, g1, g2, g3;
+        gauss2(r0.x, r0.y, g0, g1);
+        gauss2(r0.z, r0.w, g2, g3);
+        double wxx, wyy, wzz, wxy, wxz = 0.0, wyz = 0.0;
+        if (co.dim == 2) {
+          // trace / dimension with the zz entry zero: Wxx = (gxx - gyy)/2 = -Wyy, Wzz irrelevant (delz = 0)
+          wxx = 0.5 * (g0 - g1); wyy = -wxx; wzz = 0.0;
+          wxy = 0.5 * (g2 + g3);
+        } else {
+          const uint4 r1 = philox4x32(make_uint4(tlo, thi, (unsigned)ntimestep, ((unsigned)(ntimestep >> 32) << 1) | 1u), key);
+          double g4, g5, g6, g7;
+          gauss2(r1.x, r1.y, g4, g5);
+          gauss2(r1.z, r1.w, g6, g7);
+          const double mean = (g0 + g1 + g2) * (1.0 / 3.0);
+          wxx = g0 - mean; wyy = g1 - mean; wzz = g2 - mean;
+          const double isq2 = 0.70710678118654752440;   // (g_lm + g_ml)/2 ~ N(0, 1/2)
+          wxy = isq2 * g3; wxz = isq2 * g4; wyz = isq2 * g5;
+          (void)g6; (void)g7;
+        }
+        fx += pref * (wxx * delx + wxy * dely + wxz * delz);
+        fy += pref * (wxy * delx + wyy * dely + wyz * delz);
+        fz += pref * (wxz * delx + wyz * dely + wzz * delz);
+      }
     } else {
       double fviscs = 0.;
       if (dvr < 0.) {
@@ -432,8 +491,12 @@ static void launch_filter(const DevState &d, const Coeffs &co, const PairTables 
                           cudaStream_t st) {
   const int threads = 128;
   const int blocks = (d.nlocal + threads - 1) / threads;
-  if (pf.filter_step) pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, true><<<blocks, threads, 0, st>>>(d, co, tb, pf.damp);
-  else pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, false><<<blocks, threads, 0, st>>>(d, co, tb, pf.damp);
+#define PK(F, R) pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, F, R><<<blocks, threads, 0, st>>>(d, co, tb, pf.damp, pf.rand_pref, pf.seed, pf.ntimestep)
+  // the stochastic variant always carries the Shepard numerator (one instantiation less per case)
+  if (pf.random) PK(true, true);
+  else if (pf.filter_step) PK(true, false);
+  else PK(false, false);
+#undef PK
 }
 
 template <int VARIANT, bool SPECIES>

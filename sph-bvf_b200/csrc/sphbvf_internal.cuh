@@ -151,6 +151,10 @@ struct PairFlags {
   int with_dev;      // deviatoric tensors may be non-zero (elastic solids present)
   int any_solid;     // some atom has solid_tag == 1
   double damp;       // density-diffusion amplitude of the fsi variant (0 otherwise)
+  int random;        // stochastic stress term on (some e != 0 and sphbvf_set_random was called)
+  double rand_pref;  // 4 kB / dt
+  unsigned long long seed;
+  long ntimestep;
 };
 void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, cudaStream_t st);
 

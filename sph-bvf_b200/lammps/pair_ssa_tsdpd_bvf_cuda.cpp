@@ -156,12 +156,6 @@ void PairSsaTsdpdBvfCuda::init_style()
   engine->cutc = cutc;
   engine->kappa = kappa;
   engine->reset_fixes();
-  if (comm->me == 0 && atom->nlocal) {
-    double emax = 0.0;
-    for (int i = 0; i < atom->nlocal; i++) emax = MAX(emax, atom->e[i]);
-    if (emax != 0.0)
-      error->warning(FLERR, "ssa_tsdpd/bvf/<style>/cuda: the stochastic stress term (ssa_tsdpd/e != 0) is not applied");
-  }
 }
 
 /* ---------------------------------------------------------------------- */

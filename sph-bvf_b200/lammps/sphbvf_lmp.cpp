@@ -4,6 +4,7 @@
    and stay there.
 ------------------------------------------------------------------------- */
 
+#include <stdlib.h>
 #include <string.h>
 #include "sphbvf_lmp.h"
 #include "atom.h"
@@ -133,6 +134,14 @@ void SphbvfLmp::start()
     // FixSsaTsdpdBvf*Cuda::setup_pre_force has just set vest = v and rhoI = rho on the host
     check(sphbvf_upload(ctx, SPHBVF_F_VEST, &atom->vest[0][0]));
     check(sphbvf_upload(ctx, SPHBVF_F_RHOI, atom->rhoI));
+  }
+  // stochastic stress (active only if some ssa_tsdpd/e != 0): kB of the unit system and a seed; upstream
+  // seeds from clock() (pair_ssa_tsdpd_bvf_transport_velocity.cpp:957-959), here runs are reproducible
+  // unless SPHBVF_SEED is changed
+  {
+    const char *env = getenv("SPHBVF_SEED");
+    const unsigned long long seed = env ? strtoull(env, NULL, 10) : 20261018ULL;
+    check(sphbvf_set_random(ctx, force->boltz, seed));
   }
   check(sphbvf_set_timestep(ctx, (long)update->ntimestep));
   check(sphbvf_set_run_length(ctx, (long)update->nsteps));

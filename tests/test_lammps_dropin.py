@@ -319,3 +319,80 @@ def test_deck_unchanged_with_sf_cuda(name):
             worst[c] = max(worst.get(c, 0.0), err)
     bad = {c: e for c, e in worst.items() if e > TOL}
     assert not bad, "%s: columns beyond %g: %s (all: %s)" % (name, TOL, bad, worst)
+
+
+# ---------------------------------------------------------------------------------------------
+# short-horizon field statistics (BASELINE.json north_star: "cavity centreline velocity, Nusselt
+# number matching within 1e-6"), computed by the same post-processing on both outputs
+# ---------------------------------------------------------------------------------------------
+def _final_dump(deck, exe, extra, nsteps):
+    deck = deck.replace("run 28", "run %d" % nsteps).replace("run 20\nrun 20", "run %d" % nsteps)
+    deck = deck.replace("custom 7 ", "custom %d " % nsteps).replace("custom 10 ", "custom %d " % nsteps)
+    wd, _ = run_deck(exe, deck, extra)
+    d = read_dumps(wd)
+    cols, data = d[max(d)]
+    return {c: data[:, k] for k, c in enumerate(cols)}
+
+
+def test_cavity_centreline_velocity_statistic():
+    if not (os.path.exists(REF) and os.path.exists(CUDA)):
+        pytest.skip("lmp_serial / lmp_cuda not built")
+    nsteps = 400
+    prof = []
+    for exe, extra in ((REF, []), (CUDA, ["-sf", "cuda"])):
+        f = _final_dump(CAVITY2D, exe, extra, nsteps)
+        d = 1.0 / 20
+        fluid = f["type"] == 1
+        strip = fluid & (np.abs(f["x"] - 0.5) < d)
+        bins = np.clip((f["y"][strip] / d).astype(int), 0, 19)
+        # u(y) on the vertical centreline and v(x) on the horizontal one (Ghia-style profiles)
+        u = np.bincount(bins, weights=f["vx"][strip], minlength=20) / np.maximum(np.bincount(bins, minlength=20), 1)
+        strip = fluid & (np.abs(f["y"] - 0.5) < d)
+        bins = np.clip((f["x"][strip] / d).astype(int), 0, 19)
+        v = np.bincount(bins, weights=f["vy"][strip], minlength=20) / np.maximum(np.bincount(bins, minlength=20), 1)
+        prof.append(np.concatenate([u, v]))
+    scale = np.abs(prof[0]).max()
+    assert scale > 1e-3
+    assert np.abs(prof[0] - prof[1]).max() / scale < 1e-6
+
+
+def test_heated_cavity_nusselt_statistic():
+    if not (os.path.exists(REF) and os.path.exists(CUDA)):
+        pytest.skip("lmp_serial / lmp_cuda not built")
+    nsteps = 400
+    nu = []
+    for exe, extra in ((REF, []), (CUDA, ["-sf", "cuda"])):
+        f = _final_dump(NATCONV2D, exe, extra, nsteps)
+        d = 1.0 / 24
+        fluid = f["type"] == 1
+        # wall heat flux of the hot (left) wall: -dC/dx from the first two fluid columns, averaged in y,
+        # over the conductive flux (C_hot - C_cold) / L = 1
+        c1 = f["c_cc"][fluid & (f["x"] < d)].mean()
+        c2 = f["c_cc"][fluid & (f["x"] > d) & (f["x"] < 2 * d)].mean()
+        nu.append(-(c2 - c1) / d)
+    assert abs(nu[0]) > 1e-3
+    assert abs(nu[0] - nu[1]) / abs(nu[0]) < 1e-6, nu
+
+
+def test_heated_cavity_with_stochastic_term_as_shipped():
+    """The reference's natural-convection decks set ssa_tsdpd/e = 1e-6 (SI units): the random stress is
+    then ~1e-8 of the deterministic force and unreproducible upstream (clock() seed).  The /cuda
+    styles apply their counter-based version of the term; fields must agree to that noise level."""
+    if not (os.path.exists(REF) and os.path.exists(CUDA)):
+        pytest.skip("lmp_serial / lmp_cuda not built")
+    deck = NATCONV2D.replace("set group all ssa_tsdpd/e 0.", "set group all ssa_tsdpd/e 1e-6")
+    assert deck != NATCONV2D
+    wd_ref, _ = run_deck(REF, deck, [])
+    wd_cuda, _ = run_deck(CUDA, deck, ["-sf", "cuda"])
+    ref, got = read_dumps(wd_ref), read_dumps(wd_cuda)
+    assert sorted(ref) == sorted(got)
+    cols = ref[min(ref)][0]
+    for s in sorted(ref):
+        a, b = ref[s][1], got[s][1]
+        fluid = a[:, 1] == 1
+        for k, c in enumerate(cols[2:], start=2):
+            x, y = a[:, k], b[:, k]
+            if c in ("fx", "fy"):
+                x, y = x[fluid], y[fluid]
+            scale = max(np.abs(ref[q][1][:, k]).max() for q in ref)
+            assert np.abs(x - y).max() <= 1e-5 * max(scale, 1e-300), (s, c)
