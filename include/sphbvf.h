@@ -145,6 +145,9 @@ int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt);
 /* Verlet::force_clear + Pair*::compute (+ reverse_comm, which the gather formulation makes a
  * no-op) (verlet.cpp:300-335, pair_ssa_tsdpd_bvf_*.cpp compute) */
 int sphbvf_pair_compute(sphbvf_ctx *ctx);
+/* Pair::virial_fdotr_compute (pair.cpp:1511-1560) for the forces just computed: virial[6] in LAMMPS
+ * order xx yy zz xy xz yz (this rank's share); call between pair_compute and post_force */
+int sphbvf_virial(sphbvf_ctx *ctx, double *virial6);
 int sphbvf_post_force(sphbvf_ctx *ctx);        /* buoyancy / setforce post_force */
 int sphbvf_final_integrate(sphbvf_ctx *ctx);   /* Fix*::final_integrate (:244) */
 int sphbvf_end_of_step(sphbvf_ctx *ctx);       /* buffer(density) end_of_step */

@@ -36,7 +36,7 @@ SYMBOLS = ["sphbvf_version", "sphbvf_device_count", "sphbvf_create", "sphbvf_des
            "sphbvf_add_forcing", "sphbvf_add_buffer", "sphbvf_add_setforce", "sphbvf_setup", "sphbvf_run",
            "sphbvf_setup_neighbors",
            "sphbvf_initial_integrate", "sphbvf_post_integrate", "sphbvf_neighbor", "sphbvf_pair_compute",
-           "sphbvf_post_force", "sphbvf_final_integrate", "sphbvf_end_of_step", "sphbvf_build_neighbors",
+           "sphbvf_virial", "sphbvf_post_force", "sphbvf_final_integrate", "sphbvf_end_of_step", "sphbvf_build_neighbors",
            "sphbvf_nlocal", "sphbvf_nghost", "sphbvf_ntimestep", "sphbvf_nbuilds", "sphbvf_ndanger",
            "sphbvf_get_pairs", "sphbvf_sync", "sphbvf_launch_count", "sphbvf_set_profiling", "sphbvf_kernel_ms",
            "sphbvf_stream", "sphbvf_comm_unique_id", "sphbvf_comm_init", "sphbvf_brick_bounds", "sphbvf_proc_grid",
@@ -77,6 +77,7 @@ def lib():
               "end_of_step", "build_neighbors", "nlocal", "nghost", "nbuilds", "ndanger", "sync"):
         getattr(L, "sphbvf_" + f).argtypes = [vp]
     L.sphbvf_run.argtypes = [vp, ci]
+    L.sphbvf_virial.argtypes = [vp, vp]
     L.sphbvf_neighbor.argtypes = [vp, C.POINTER(ci)]
     L.sphbvf_ntimestep.argtypes = [vp]
     L.sphbvf_ntimestep.restype = cl
@@ -184,6 +185,11 @@ class Engine:
     def pair_compute(self):
         self._ck(lib().sphbvf_pair_compute(self.h))
         self.sync()
+
+    def virial(self):
+        out = np.zeros(6)
+        self._ck(lib().sphbvf_virial(self.h, _p(out)))
+        return out
 
     def step_pieces(self):
         """One timestep through the fine-grained entry points the /cuda host classes use."""

@@ -416,6 +416,7 @@ void sphbvf_destroy(sphbvf_ctx *ctx) {
   for (void *p : ptrs) if (p) cudaFree(p);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->d_virial) cudaFree(ctx->d_virial);
   cudaStreamDestroy(ctx->st);
   delete ctx;
 }
@@ -658,6 +659,25 @@ int sphbvf_pair_compute(sphbvf_ctx *ctx) {
   launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->st);
   ctx->toc();
   CKLAUNCH();
+  return 0;
+}
+
+// Pair::virial_fdotr_compute (pair.cpp:1511-1560) = sum over local AND ghost atoms of x (x) f as the
+// half-list pair style leaves them before reverse communication.  In the gather formulation ghosts
+// carry no force; writing a ghost as x_g = x_owner + s_g and folding its force into the owner gives
+//   V = sum_{owned i} x_i (x) f_i  -  1/2 sum_{owned i} sum_{ghost g in N(i)} s_g (x) F_{i<-g}
+// (each periodic pair is seen twice in the full lists with opposite shifts and opposite forces, the
+// half list holds it once); s_g = 0 for plain inter-brick ghosts.  Call right after
+// sphbvf_pair_compute, before post_force fixes touch f.  Multi-rank: each rank returns its share.
+int sphbvf_virial(sphbvf_ctx *ctx, double *virial6) {
+  if (!ctx->setup_done) return ctx->fail(SPHBVF_ESTATE, "virial before setup");
+  cudaSetDevice(ctx->cfg.device);
+  if (!ctx->d_virial) CK(cudaMalloc((void **)&ctx->d_virial, sizeof(double) * 6));
+  CK(cudaMemsetAsync(ctx->d_virial, 0, sizeof(double) * 6, ctx->st));
+  launch_virial(ctx->d, ctx->co, pair_flags(ctx), ctx->d_virial, ctx->st);
+  CKLAUNCH();
+  CK(cudaMemcpyAsync(virial6, ctx->d_virial, sizeof(double) * 6, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
   return 0;
 }
 

@@ -34,6 +34,7 @@ struct sphbvf_ctx {
   long scan_cap = 0;
   int *h_flags = nullptr;      // pinned, 16 ints
   void *h_stage = nullptr;     // pinned staging (halo counts)
+  double *d_virial = nullptr;  // [6]
   CommState *comm = nullptr;
   std::string err;
   // accounting

@@ -146,10 +146,15 @@ __device__ __forceinline__ void gauss2(unsigned a, unsigned b, double &g0, doubl
 
 // SOLIDS: 0 = no atom has solid_tag, 1 = solids whose deviatoric stress is identically zero
 // (rigid walls: G0 == 0, dev == 0), 2 = elastic solids (deviatoric tensors gathered)
-template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM>
+// VIRIAL = true turns the kernel into the ghost part of Pair::virial_fdotr_compute (pair.cpp:1511): no
+// per-atom output is written; for every neighbour that is a periodic image (shift s != 0) the force
+// F it exerts on atom i is obtained as the change of the force accumulator and -1/2 s (x) F is summed
+// into virial_out[6] (see sphbvf_virial in capi.cu for the derivation).
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL = false>
 __global__ void __launch_bounds__(128, PAIR_MINB)
 pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
-            const double damp, const double rand_pref, const unsigned long long seed, const long ntimestep) {
+            const double damp, const double rand_pref, const unsigned long long seed, const long ntimestep,
+            double *virial_out = nullptr) {
   __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
   __shared__ int ring[RING][128];
   if (!UNIFORM) {
@@ -422,6 +427,20 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     }
   };
 
+  double vir[6] = {0, 0, 0, 0, 0, 0};
+  auto visit = [&](const int ent, const Rec4 &Aj, const Rec4 &Bj, const Rec4 &Cj) {
+    if (!VIRIAL) { body(ent, Aj, Bj, Cj); return; }
+    const int g = (ent & NEIGH_JMASK) - d.nlocal;
+    if (g < 0) return;
+    const double sx = d.gshift[3 * (size_t)g], sy = d.gshift[3 * (size_t)g + 1], sz = d.gshift[3 * (size_t)g + 2];
+    if (sx == 0.0 && sy == 0.0 && sz == 0.0) return;
+    const double f0x = fx + spi * Bi.x, f0y = fy + spi * Bi.y, f0z = fz + spi * Bi.z;
+    body(ent, Aj, Bj, Cj);
+    const double Fx = (fx + spi * Bi.x) - f0x, Fy = (fy + spi * Bi.y) - f0y, Fz = (fz + spi * Bi.z) - f0z;
+    vir[0] -= 0.5 * sx * Fx; vir[1] -= 0.5 * sy * Fy; vir[2] -= 0.5 * sz * Fz;
+    vir[3] -= 0.5 * sx * Fy; vir[4] -= 0.5 * sx * Fz; vir[5] -= 0.5 * sy * Fz;
+  };
+
   // ------------------------------------------------------------------ pipelined traversal
   // List entries stream from DRAM (4 B per neighbour, read once): each thread copies its own
   // entries RING rows ahead into a shared-memory ring with cp.async (no registers, no barrier:
@@ -455,16 +474,23 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     asm volatile("cp.async.wait_group %0;" ::"n"(RING / 2 - 2) : "memory");   // entries <= kk+5 landed
     const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * 128] : 0;
     const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * 128] : 0;
-    body(e0, A0, B0, C0);
+    visit(e0, A0, B0, C0);
     {
       const Prec *p = d.prec + (e2 & NEIGH_JMASK);
       A0 = p->A; B0 = p->B; C0 = p->C;
     }
-    if (kk + 1 < nn) body(e1, A1, B1, C1);
+    if (kk + 1 < nn) visit(e1, A1, B1, C1);
     e0 = e2;
     e1 = e3;
   }
 
+  if (VIRIAL) {
+    // only atoms next to a periodic face have anything to add: plain atomics
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+      if (vir[q] != 0.0) atomicAdd(virial_out + q, vir[q]);
+    return;
+  }
   const double ddvc = 10.0 * 7.0 * co.B[ti];
   const size_t i3 = 3 * (size_t)i;
   d.f[i3] = fma(spi, Bi.x, fx); d.f[i3 + 1] = fma(spi, Bi.y, fy); d.f[i3 + 2] = fma(spi, Bi.z, fz);
@@ -519,6 +545,58 @@ static void launch_species(const DevState &d, const Coeffs &co, const PairTables
                            bool uniform, cudaStream_t st) {
   if (co.nspecies > 0) launch_solids<VARIANT, true>(d, co, tb, pf, uniform, st);
   else launch_solids<VARIANT, false>(d, co, tb, pf, uniform, st);
+}
+
+// sum_i x_i (x) f_i over the owned atoms, LAMMPS order xx yy zz xy xz yz with virial[ab] = x_a f_b
+__global__ void virial_fdotr_kernel(const DevState d, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  if (i < d.nlocal) {
+    const size_t i3 = 3 * (size_t)i;
+    const double x = d.x[i3], y = d.x[i3 + 1], z = d.x[i3 + 2], fx = d.f[i3], fy = d.f[i3 + 1], fz = d.f[i3 + 2];
+    v[0] = fx * x; v[1] = fy * y; v[2] = fz * z; v[3] = fy * x; v[4] = fz * x; v[5] = fz * y;
+  }
+  __shared__ double sh[6][8];
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    double t = v[q];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[threadIdx.x][w];
+    atomicAdd(out + threadIdx.x, t);
+  }
+}
+
+template <int VARIANT, bool SPECIES>
+static void launch_virial_solids(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf,
+                                 double *out, cudaStream_t st) {
+  const int blocks = (d.nlocal + 127) / 128;
+  const int solids = !pf.any_solid ? 0 : (pf.with_dev ? 2 : 1);
+#define VK(S) pair_kernel<VARIANT, SPECIES, S, false, false, false, true><<<blocks, 128, 0, st>>>(d, co, tb, pf.damp, 0.0, 0ULL, pf.ntimestep, out)
+  if (solids == 0) VK(0);
+  else if (solids == 1) VK(1);
+  else VK(2);
+#undef VK
+}
+
+// Pair::virial_fdotr_compute for the gather formulation; out[6] must be zeroed by the caller
+void launch_virial(const DevState &d, const Coeffs &co, const PairFlags &pf, double *out, cudaStream_t st) {
+  if (!d.nlocal) return;
+  virial_fdotr_kernel<<<(d.nlocal + 255) / 256, 256, 0, st>>>(d, out);
+  if (!d.nghost) return;
+  PairTables tb;
+  make_tables(co, tb);
+  const bool sp = co.nspecies > 0;
+  switch (co.variant) {
+    case SPHBVF_TV: sp ? launch_virial_solids<SPHBVF_TV, true>(d, co, tb, pf, out, st) : launch_virial_solids<SPHBVF_TV, false>(d, co, tb, pf, out, st); break;
+    case SPHBVF_MECHANICS: sp ? launch_virial_solids<SPHBVF_MECHANICS, true>(d, co, tb, pf, out, st) : launch_virial_solids<SPHBVF_MECHANICS, false>(d, co, tb, pf, out, st); break;
+    default: sp ? launch_virial_solids<SPHBVF_FSI, true>(d, co, tb, pf, out, st) : launch_virial_solids<SPHBVF_FSI, false>(d, co, tb, pf, out, st); break;
+  }
 }
 
 void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, cudaStream_t st) {

@@ -157,6 +157,7 @@ struct PairFlags {
   long ntimestep;
 };
 void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, cudaStream_t st);
+void launch_virial(const DevState &d, const Coeffs &co, const PairFlags &pf, double *out6, cudaStream_t st);
 
 // kernels_neigh.cu
 struct NeighWork {      // scratch owned by the context

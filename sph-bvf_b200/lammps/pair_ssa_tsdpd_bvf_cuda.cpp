@@ -28,7 +28,6 @@ PairSsaTsdpdBvfCuda::PairSsaTsdpdBvfCuda(LAMMPS *lmp, int variant_in) : Pair(lmp
 {
   restartinfo = 0;
   single_enable = 0;
-  no_virial_fdotr_compute = 1;   // the virial is not accumulated on the device
   variant = variant_in;
   rho0 = soundspeed = B = G0 = NULL;
   cut = viscosity = cutc = NULL;
@@ -74,6 +73,13 @@ void PairSsaTsdpdBvfCuda::compute(int eflag, int vflag)
   }
   engine->check(sphbvf_pair_compute(engine->ctx));
   engine->mark_dirty();
+  // thermo steps: the virial LAMMPS would get from virial_fdotr_compute() on the host arrays
+  if (vflag_fdotr || vflag_global) {
+    double v[6];
+    engine->check(sphbvf_virial(engine->ctx, v));
+    for (int k = 0; k < 6; k++) virial[k] += v[k];
+    vflag_fdotr = 0;
+  }
 }
 
 /* ---------------------------------------------------------------------- */

@@ -281,6 +281,25 @@ def read_dumps(wd):
     return out
 
 
+def read_thermo(stdout):
+    """rows of the thermo table(s): Step Temp E_pair E_mol TotEng Press"""
+    rows, on = [], False
+    for ln in stdout.splitlines():
+        w = ln.split()
+        if w[:2] == ["Step", "Temp"]:
+            on = True
+            continue
+        if on:
+            if ln.startswith("Loop time"):
+                on = False
+                continue
+            try:
+                rows.append([float(v) for v in w])
+            except ValueError:
+                pass
+    return np.array(rows)
+
+
 def run_deck(exe, deck, extra):
     wd = tempfile.mkdtemp(prefix="sphbvf_deck_")
     with open(os.path.join(wd, "in.lmp"), "w") as fh:
@@ -295,9 +314,31 @@ def run_deck(exe, deck, extra):
 def test_deck_unchanged_with_sf_cuda(name):
     if not (os.path.exists(REF) and os.path.exists(CUDA)):
         pytest.skip("lmp_serial / lmp_cuda not built (make -C oracle ref; make -C sph-bvf_b200/lammps)")
-    wd_ref, _ = run_deck(REF, DECKS[name], [])
-    wd_cuda, log = run_deck(CUDA, DECKS[name], ["-sf", "cuda"])
-    assert "/cuda" in open(os.path.join(wd_cuda, "log.lammps")).read() or True
+    wd_ref, out_ref = run_deck(REF, DECKS[name], [])
+    wd_cuda, out_cuda = run_deck(CUDA, DECKS[name], ["-sf", "cuda"])
+    # thermo output (temperature from the synced host velocities, pressure from the device virial,
+    # sphbvf_virial == Pair::virial_fdotr_compute): printed with 5-6 significant digits
+    ta, tb = read_thermo(out_ref), read_thermo(out_cuda)
+    assert ta.shape == tb.shape and ta.shape[0] >= 3 and ta.shape[1] == 6, (ta.shape, tb.shape)
+    assert np.array_equal(ta[:, 0], tb[:, 0])
+    for col, what in ((1, "Temp"), (5, "Press")):
+        scale = np.abs(ta[:, col]).max()
+        assert scale > 0, what
+        # Press = (kinetic term + sum over local AND ghost atoms of x.f) / volume (Pair::virial_fdotr_compute).
+        # Upstream's forces on SOLID partners are not the mirror image of the forces on their fluid
+        # neighbours (different viscosity model; in transportVelocity also the un-flipped pressure switch,
+        # SURVEY.md A.5), so which half of such a pair lands on which atom -- and with it sum x.f --
+        # depends on half-list orientation.  The device virial (sphbvf_virial) is the orientation-free
+        # value, checked exactly against the oracle in tests/test_gpu_parity.py; against upstream it can
+        # agree only where no fluid-solid pair matters: tight for the ring deck (solid away from the
+        # periodic faces), loose for the channel deck (walls cross a periodic face), not at all for the
+        # wall-bounded transportVelocity decks.
+        if what == "Press" and name.startswith(("cavity", "natconv")):
+            continue
+        tol = 2e-3 if (what == "Press" and name == "fsi2d") else 2e-5
+        if what == "Press" and name == "fsi2d":
+            ta, tb = ta[1:], tb[1:]        # step 0 of the first setup: stale ghost velocities upstream (D.9)
+        assert np.abs(ta[:, col] - tb[:, col]).max() <= tol * scale, (name, what, ta[:, col], tb[:, col])
     ref, got = read_dumps(wd_ref), read_dumps(wd_cuda)
     assert sorted(ref) == sorted(got) and len(ref) >= 3, (sorted(ref), sorted(got))
     cols = ref[min(ref)][0]
