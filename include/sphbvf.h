@@ -124,6 +124,10 @@ int sphbvf_add_forcing(sphbvf_ctx *ctx, int groupbit, int kind, long step, int i
  * (fix_ssa_tsdpd_buffer.cpp:36-240): kind 0 tsdpd, 1 velocity, 2 density; axis 0 x, 1 y */
 int sphbvf_add_buffer(sphbvf_ctx *ctx, int groupbit, int kind, int axis, long step, int idx,
                       double cx, double cy, double length, double width, double value);
+/* fix ssa_tsdpd/chem_rxn_mass_action k nreact r0.. nprod p0.. (fix_ssa_tsdpd_chem_rxn_mass_action.cpp:24-112):
+ * post_force source  flux = k * prod_r C[r];  Q[r] -= flux;  Q[p] += flux;  nreact <= 2, nprod <= 4 */
+int sphbvf_add_chem_rxn(sphbvf_ctx *ctx, int groupbit, double k_rate, int nreact, const int *reactants,
+                        int nprod, const int *products);
 /* fix setforce fx fy fz with constants (fix_setforce.cpp:222-290), used by the cavity decks */
 int sphbvf_add_setforce(sphbvf_ctx *ctx, int groupbit, double fx, double fy, double fz);
 
@@ -148,7 +152,10 @@ int sphbvf_pair_compute(sphbvf_ctx *ctx);
 /* Pair::virial_fdotr_compute (pair.cpp:1511-1560) for the forces just computed: virial[6] in LAMMPS
  * order xx yy zz xy xz yz (this rank's share); call between pair_compute and post_force */
 int sphbvf_virial(sphbvf_ctx *ctx, double *virial6);
-int sphbvf_post_force(sphbvf_ctx *ctx);        /* buoyancy / setforce post_force */
+int sphbvf_post_force(sphbvf_ctx *ctx);        /* buoyancy / setforce / chem_rxn post_force */
+/* Modify::setup -> Fix::setup at the start of a run: only the fixes whose setup() forwards to
+ * post_force (setforce, buoyancy) act; follows the first pair_compute */
+int sphbvf_setup_post_force(sphbvf_ctx *ctx);
 int sphbvf_final_integrate(sphbvf_ctx *ctx);   /* Fix*::final_integrate (:244) */
 int sphbvf_end_of_step(sphbvf_ctx *ctx);       /* buffer(density) end_of_step */
 /* force a neighbour rebuild now (pbc + ghosts + sort + list), as Neighbor::build on a rebuild step */
@@ -160,6 +167,9 @@ int sphbvf_nghost(const sphbvf_ctx *ctx);
 long sphbvf_ntimestep(const sphbvf_ctx *ctx);
 int sphbvf_nbuilds(const sphbvf_ctx *ctx);    /* Neighbor::ncalls */
 int sphbvf_ndanger(const sphbvf_ctx *ctx);    /* Neighbor::ndanger */
+/* max over the atoms of `groupbit` (all ranks) of |v|^2 with v the transport velocity (atom->v): the
+ * reduction FixDtAdaptive::end_of_step does before its MPI_Allreduce (fix_dt_adaptive.cpp:118-148) */
+int sphbvf_max_vsq(sphbvf_ctx *ctx, int groupbit, double *max_vsq);
 /* the neighbour structure as unordered (tag_i, tag_j) rows, each pair once -- what
  * `compute property/local patom1 patom2` dumps for the reference; out=NULL sizes */
 long sphbvf_get_pairs(sphbvf_ctx *ctx, int *out, long cap);

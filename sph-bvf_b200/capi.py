@@ -33,10 +33,10 @@ _lib = None
 SYMBOLS = ["sphbvf_version", "sphbvf_device_count", "sphbvf_create", "sphbvf_destroy", "sphbvf_last_error",
            "sphbvf_set_type", "sphbvf_set_pair", "sphbvf_set_dt", "sphbvf_set_random", "sphbvf_set_timestep", "sphbvf_set_run_length",
            "sphbvf_set_atoms", "sphbvf_upload", "sphbvf_download", "sphbvf_download_local", "sphbvf_upload_local", "sphbvf_add_buoyancy",
-           "sphbvf_add_forcing", "sphbvf_add_buffer", "sphbvf_add_setforce", "sphbvf_setup", "sphbvf_run",
+           "sphbvf_add_forcing", "sphbvf_add_buffer", "sphbvf_add_setforce", "sphbvf_add_chem_rxn", "sphbvf_max_vsq", "sphbvf_setup", "sphbvf_run",
            "sphbvf_setup_neighbors",
            "sphbvf_initial_integrate", "sphbvf_post_integrate", "sphbvf_neighbor", "sphbvf_pair_compute",
-           "sphbvf_virial", "sphbvf_post_force", "sphbvf_final_integrate", "sphbvf_end_of_step", "sphbvf_build_neighbors",
+           "sphbvf_virial", "sphbvf_post_force", "sphbvf_setup_post_force", "sphbvf_final_integrate", "sphbvf_end_of_step", "sphbvf_build_neighbors",
            "sphbvf_nlocal", "sphbvf_nghost", "sphbvf_ntimestep", "sphbvf_nbuilds", "sphbvf_ndanger",
            "sphbvf_get_pairs", "sphbvf_sync", "sphbvf_launch_count", "sphbvf_set_profiling", "sphbvf_kernel_ms",
            "sphbvf_stream", "sphbvf_comm_unique_id", "sphbvf_comm_init", "sphbvf_brick_bounds", "sphbvf_proc_grid",
@@ -73,7 +73,9 @@ def lib():
     L.sphbvf_add_forcing.argtypes = [vp, ci, ci, cl, ci, ci, cd, cd, cd, cd, cd]
     L.sphbvf_add_buffer.argtypes = [vp, ci, ci, ci, cl, ci, cd, cd, cd, cd, cd]
     L.sphbvf_add_setforce.argtypes = [vp, ci, cd, cd, cd]
-    for f in ("setup", "setup_neighbors", "initial_integrate", "post_integrate", "pair_compute", "post_force", "final_integrate",
+    L.sphbvf_add_chem_rxn.argtypes = [vp, ci, cd, ci, vp, ci, vp]
+    L.sphbvf_max_vsq.argtypes = [vp, ci, C.POINTER(cd)]
+    for f in ("setup", "setup_neighbors", "setup_post_force", "initial_integrate", "post_integrate", "pair_compute", "post_force", "final_integrate",
               "end_of_step", "build_neighbors", "nlocal", "nghost", "nbuilds", "ndanger", "sync"):
         getattr(L, "sphbvf_" + f).argtypes = [vp]
     L.sphbvf_run.argtypes = [vp, ci]

@@ -545,14 +545,34 @@ int sphbvf_add_buffer(sphbvf_ctx *ctx, int groupbit, int kind, int axis, long st
   FixDesc f = {FIX_BUFFER, groupbit, {kind, idx, axis, 0}, step, {cx, cy, length, width, value, 0}};
   return add_fix(ctx, f);
 }
+int sphbvf_add_chem_rxn(sphbvf_ctx *ctx, int groupbit, double k_rate, int nreact, const int *reactants, int nprod,
+                        const int *products) {
+  const int S = ctx->co.nspecies;
+  if (nreact < 0 || nreact > 2 || nprod < 0 || nprod > 4 || (nreact && !reactants) || (nprod && !products))
+    return ctx->fail(SPHBVF_EINVAL, "Illegal fix ssa_tsdpd_chem_rxn_mass_action command");
+  int r = 0, p = 0;
+  for (int j = 0; j < nreact; j++) {
+    if (reactants[j] < 0 || reactants[j] >= S) return ctx->fail(SPHBVF_EINVAL, "chem_rxn: reactant species out of range");
+    r |= reactants[j] << (8 * j);
+  }
+  for (int j = 0; j < nprod; j++) {
+    if (products[j] < 0 || products[j] >= S) return ctx->fail(SPHBVF_EINVAL, "chem_rxn: product species out of range");
+    p |= products[j] << (8 * j);
+  }
+  FixDesc f = {FIX_CHEMRXN, groupbit, {nreact | (nprod << 8), r, p, 0}, 0, {k_rate, 0, 0, 0, 0, 0}};
+  return add_fix(ctx, f);
+}
 int sphbvf_add_setforce(sphbvf_ctx *ctx, int groupbit, double fx, double fy, double fz) {
   FixDesc f = {FIX_SETFORCE, groupbit, {0, 0, 0, 0}, 0, {fx, fy, fz, 0, 0, 0}};
   return add_fix(ctx, f);
 }
 
-static int run_fixes(sphbvf_ctx *ctx, int hook) {
+// in_setup: Modify::setup calls Fix::setup, which only FixSetForce and FixSsaTsdpdBuoyancy forward to
+// post_force (fix_setforce.cpp, fix_ssa_tsdpd_buoyancy.cpp:93-96); the reaction fix has no setup()
+static int run_fixes(sphbvf_ctx *ctx, int hook, bool in_setup = false) {
   bool any = false;
   for (int q = 0; q < ctx->nfix; q++) {
+    if (in_setup && ctx->fixes[q].kind == FIX_CHEMRXN) continue;
     if (!any) { ctx->tic(K_FIX, 0); any = true; }
     ctx->launches_fam[K_FIX]++;
     launch_fix(ctx->d, ctx->co, ctx->fixes[q], hook, ctx->ntimestep, ctx->st);
@@ -592,7 +612,7 @@ int sphbvf_setup(sphbvf_ctx *ctx) {
   ctx->ndanger = 0;
   ctx->setup_done = 1;
   if ((rc = sphbvf_pair_compute(ctx))) return rc;
-  if ((rc = run_fixes(ctx, 1))) return rc;   // modify->setup(): FixSetForce::setup, FixSsaTsdpdBuoyancy::setup
+  if ((rc = run_fixes(ctx, 1, true))) return rc;   // modify->setup(): FixSetForce::setup, FixSsaTsdpdBuoyancy::setup
   CK(cudaStreamSynchronize(ctx->st));
   return 0;
 }
@@ -623,6 +643,7 @@ int sphbvf_initial_integrate(sphbvf_ctx *ctx) {
 
 int sphbvf_post_integrate(sphbvf_ctx *ctx) { return run_fixes(ctx, 0); }
 int sphbvf_post_force(sphbvf_ctx *ctx) { return run_fixes(ctx, 1); }
+int sphbvf_setup_post_force(sphbvf_ctx *ctx) { return run_fixes(ctx, 1, true); }
 int sphbvf_end_of_step(sphbvf_ctx *ctx) { return run_fixes(ctx, 2); }
 
 int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt) {
@@ -678,6 +699,25 @@ int sphbvf_virial(sphbvf_ctx *ctx, double *virial6) {
   CKLAUNCH();
   CK(cudaMemcpyAsync(virial6, ctx->d_virial, sizeof(double) * 6, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
+int sphbvf_max_vsq(sphbvf_ctx *ctx, int groupbit, double *max_vsq) {
+  if (!ctx->atoms_set) return ctx->fail(SPHBVF_ESTATE, "max_vsq before set_atoms");
+  cudaSetDevice(ctx->cfg.device);
+  if (!ctx->d_virial) CK(cudaMalloc((void **)&ctx->d_virial, sizeof(double) * 6));
+  unsigned long long *slot = (unsigned long long *)ctx->d_virial;
+  CK(cudaMemsetAsync(slot, 0, sizeof(unsigned long long), ctx->st));
+  launch_max_vsq(ctx->d, groupbit, slot, ctx->st);
+  CKLAUNCH();
+  double v = 0.0;
+  CK(cudaMemcpyAsync(&v, slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  if (ctx->cfg.nranks > 1) {   // MPI_Allreduce(MAX) of fix_dt_adaptive.cpp:148
+    int rc;
+    if ((rc = comm_allreduce_max_double(ctx, &v))) return rc;
+  }
+  *max_vsq = v;
   return 0;
 }
 

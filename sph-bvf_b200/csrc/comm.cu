@@ -89,6 +89,7 @@ int comm_rebuild(sphbvf_ctx *ctx) { return ctx->fail(SPHBVF_ECOMM, "library buil
 int comm_forward(sphbvf_ctx *ctx) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
 int comm_vote(sphbvf_ctx *ctx, int *) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
 int comm_allreduce_max(sphbvf_ctx *ctx, int *, int) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
+int comm_allreduce_max_double(sphbvf_ctx *ctx, double *) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
 void comm_destroy(sphbvf_ctx *) {}
 extern "C" int sphbvf_comm_unique_id(void *) { return SPHBVF_ECOMM; }
 extern "C" int sphbvf_comm_init(sphbvf_ctx *ctx, const void *) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }

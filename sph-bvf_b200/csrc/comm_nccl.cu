@@ -421,6 +421,20 @@ int comm_allreduce_max(sphbvf_ctx *ctx, int *vals, int n) {
 
 int comm_vote(sphbvf_ctx *ctx, int *flag) { return comm_allreduce_max(ctx, flag, 1); }
 
+int comm_allreduce_max_double(sphbvf_ctx *ctx, double *val) {
+  CommState *c = ctx->comm;
+  if (!c) return ctx->fail(SPHBVF_ECOMM, "sphbvf_comm_init has not been called");
+  double *v = (double *)(c->d_counts + ((2 * ND + ND * ctx->cfg.nranks + 9) & ~1));   // 8-byte aligned scratch
+  double *h = (double *)(c->h_counts + 2);
+  *h = *val;
+  CK(cudaMemcpyAsync(v, h, sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  NK(nccl_api()->AllReduce(v, v, 1, ncclDouble, ncclMax, c->comm, ctx->st));
+  CK(cudaMemcpyAsync(h, v, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  *val = *h;
+  return 0;
+}
+
 // the rebuild branch of verlet.cpp:268-296 on a brick: pbc, exchange, sort, borders, list
 int comm_rebuild(sphbvf_ctx *ctx) {
   CommState *c = ctx->comm;
@@ -549,7 +563,7 @@ extern "C" int sphbvf_comm_init(sphbvf_ctx *ctx, const void *id128) {
   ncclUniqueId id;
   memcpy(&id, id128, sizeof id);
   NK(nccl_api()->CommInitRank(&c->comm, P, id, ctx->cfg.rank));
-  CK(cudaMalloc((void **)&c->d_counts, sizeof(int) * (2 * ND + ND * P + 8)));
+  CK(cudaMalloc((void **)&c->d_counts, sizeof(int) * (2 * ND + ND * P + 16)));
   CK(cudaMallocHost((void **)&c->h_counts, sizeof(int) * (ND * P + 8)));
   double shift[ND * 3];
   int rc = sphbvf_comm_plan(&ctx->cfg, ctx->cfg.rank, c->send.peer, shift);

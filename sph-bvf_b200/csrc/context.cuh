@@ -62,4 +62,5 @@ int comm_rebuild(sphbvf_ctx *ctx);        // pbc + migration + sort + borders + 
 int comm_forward(sphbvf_ctx *ctx);        // per-step halo of the packed records
 int comm_vote(sphbvf_ctx *ctx, int *flag); // rebuild vote: max over ranks
 int comm_allreduce_max(sphbvf_ctx *ctx, int *vals, int n);   // n <= 8
+int comm_allreduce_max_double(sphbvf_ctx *ctx, double *val);
 void comm_destroy(sphbvf_ctx *ctx);

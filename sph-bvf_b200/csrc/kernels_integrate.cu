@@ -233,6 +233,15 @@ __global__ void fix_kernel(const DevState d, const __grid_constant__ Coeffs co, 
     else d.f[i3 + fx.ia[1]] += m * fx.a[0] * (d.C[(size_t)i * S + fx.ia[2]] - fx.a[1]);
   } else if (fx.kind == FIX_SETFORCE) {
     d.f[i3] = fx.a[0]; d.f[i3 + 1] = fx.a[1]; d.f[i3 + 2] = fx.a[2];
+  } else if (fx.kind == FIX_CHEMRXN) {
+    // ia[0] = nreact | nprod << 8; ia[1] = reactants, ia[2] = products, one byte each
+    const int nr = fx.ia[0] & 255, np = fx.ia[0] >> 8;
+    double *C = d.C + (size_t)i * S, *Q = d.Q + (size_t)i * S;
+    double flux = fx.a[0];
+    if (nr == 2) flux = fx.a[0] * C[fx.ia[1] & 255] * C[(fx.ia[1] >> 8) & 255];
+    else if (nr == 1) flux = fx.a[0] * C[fx.ia[1] & 255];
+    for (int j = 0; j < nr; j++) Q[(fx.ia[1] >> (8 * j)) & 255] -= flux;
+    for (int j = 0; j < np; j++) Q[(fx.ia[2] >> (8 * j)) & 255] += flux;
   } else if (fx.kind == FIX_FORCING) {
     const double drx = d.x[i3] - fx.a[0], dry = d.x[i3 + 1] - fx.a[1];
     bool inside;
@@ -252,12 +261,30 @@ __global__ void fix_kernel(const DevState d, const __grid_constant__ Coeffs co, 
   }
 }
 
+// |v|^2 >= 0, so the IEEE bit patterns order like unsigned integers: atomicMax on the raw bits
+__global__ void max_vsq_kernel(const DevState d, const int groupbit, unsigned long long *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double vsq = 0.0;
+  if (i < d.nlocal && (d.mask[i] & groupbit)) {
+    const size_t i3 = 3 * (size_t)i;
+    vsq = d.v[i3] * d.v[i3] + d.v[i3 + 1] * d.v[i3 + 1] + d.v[i3 + 2] * d.v[i3 + 2];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) vsq = fmax(vsq, __shfl_xor_sync(0xffffffffu, vsq, o));
+  if ((threadIdx.x & 31) == 0 && vsq > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(vsq));
+}
+
+void launch_max_vsq(const DevState &d, int groupbit, unsigned long long *out, cudaStream_t st) {
+  if (d.nlocal) max_vsq_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, groupbit, out);
+}
+
 // hook: 0 post_integrate, 1 post_force, 2 end_of_step
 void launch_fix(const DevState &d, const Coeffs &co, const FixDesc &fx, int hook, long ntimestep, cudaStream_t st) {
   if (!d.nlocal) return;
   bool run = false;
   switch (fx.kind) {
     case FIX_BUOYANCY:
+    case FIX_CHEMRXN:
     case FIX_SETFORCE: run = hook == 1; break;
     case FIX_FORCING: run = hook == 0 && ntimestep > fx.step; break;
     case FIX_BUFFER:

@@ -93,7 +93,7 @@ struct Box {
   int dim;
 };
 
-enum FixKind { FIX_BUOYANCY = 0, FIX_FORCING = 1, FIX_BUFFER = 2, FIX_SETFORCE = 3 };
+enum FixKind { FIX_BUOYANCY = 0, FIX_FORCING = 1, FIX_BUFFER = 2, FIX_SETFORCE = 3, FIX_CHEMRXN = 4 };
 struct FixDesc {
   int kind, groupbit;
   int ia[4];
@@ -138,6 +138,7 @@ void launch_initial_integrate(const DevState &d, const Coeffs &co, double dt, lo
                               int groupbit, cudaStream_t st);
 void launch_final_integrate(const DevState &d, const Coeffs &co, double dt, long ntimestep,
                             int groupbit, cudaStream_t st);
+void launch_max_vsq(const DevState &d, int groupbit, unsigned long long *out, cudaStream_t st);
 void launch_fix(const DevState &d, const Coeffs &co, const FixDesc &fx, int hook, long ntimestep,
                 cudaStream_t st);   // hook: 0 post_integrate, 1 post_force, 2 end_of_step
 // pack owned atoms into pA..pD (+pCs, pdev) and refresh self-image ghosts from their owners

@@ -2,6 +2,7 @@
    argument parsing of the auxiliary /cuda fixes; see fix_ssa_tsdpd_aux_cuda.h
 ------------------------------------------------------------------------- */
 
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include "fix_ssa_tsdpd_aux_cuda.h"
@@ -9,10 +10,13 @@
 #include "domain.h"
 #include "error.h"
 #include "force.h"
+#include "modify.h"
+#include "pair.h"
+#include "update.h"
 
 using namespace LAMMPS_NS;
 
-enum { K_BUOYANCY = 0, K_FORCING = 1, K_BUFFER = 2, K_SETFORCE = 3 };
+enum { K_BUOYANCY = 0, K_FORCING = 1, K_BUFFER = 2, K_SETFORCE = 3, K_CHEMRXN = 4 };
 
 void FixSphbvfRegistered::init()
 {
@@ -119,3 +123,91 @@ FixSetForceCuda::FixSetForceCuda(LAMMPS *lmp, int narg, char **arg) : FixSphbvfR
     desc.a[k] = force->numeric(FLERR, arg[3 + k]);
   }
 }
+
+/* fix ID group ssa_tsdpd/chem_rxn_mass_action k nreact r0.. nprod p0.. -------------------------- */
+
+FixSsaTsdpdChemRxnMassActionCuda::FixSsaTsdpdChemRxnMassActionCuda(LAMMPS *lmp, int narg, char **arg) :
+  FixSphbvfRegistered(lmp, narg, arg)
+{
+  if (narg < 6) error->all(FLERR, "Illegal fix ssa_tsdpd_chem_rxn_mass_action command, first error.");
+  desc.kind = K_CHEMRXN;
+  int iarg = 3;
+  desc.a[0] = atof(arg[iarg++]);
+  const int nr = atoi(arg[iarg++]);
+  if (nr > atom->num_sdpd_species)
+    error->all(FLERR, "Illegal fix ssa_tsdpd_chem_rxn_mass_action command -- number of reactant species greater than number of species.\n");
+  if (nr > 2 || nr < 0)
+    error->all(FLERR, "Illegal fix ssa_tsdpd_chem_rxn_mass_action command -- mass action reactions can have at most 2 reactants.\n");
+  if (narg < iarg + nr + 1) error->all(FLERR, "Illegal fix ssa_tsdpd_chem_rxn_mass_action command");
+  for (int i = 0; i < nr; i++) {
+    const int r = atoi(arg[iarg++]);
+    if (r < 0 || r >= atom->num_sdpd_species) error->all(FLERR, "Illegal fix ssa_tsdpd_chem_rxn_mass_action command -- species index");
+    desc.ia[1] |= r << (8 * i);
+  }
+  const int np = atoi(arg[iarg++]);
+  if (np > atom->num_sdpd_species)
+    error->all(FLERR, "Illegal fix ssa_tsdpd_chem_rxn_mass_action command -- number of product species greater than number of species.\n");
+  if (np > 4 || np < 0)
+    error->all(FLERR, "Illegal fix ssa_tsdpd_chem_rxn_mass_action command -- maximum number of product limited to 4 .\n");
+  if (narg < iarg + np) error->all(FLERR, "Illegal fix ssa_tsdpd_chem_rxn_mass_action command");
+  for (int i = 0; i < np; i++) {
+    const int q = atoi(arg[iarg++]);
+    if (q < 0 || q >= atom->num_sdpd_species) error->all(FLERR, "Illegal fix ssa_tsdpd_chem_rxn_mass_action command -- species index");
+    desc.ia[2] |= q << (8 * i);
+  }
+  desc.ia[0] = nr | (np << 8);
+}
+
+/* fix ID group dt/adaptive N tmin tmax CFLmax dxAve ------------------------------------------ */
+
+FixDtAdaptiveCuda::FixDtAdaptiveCuda(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg)
+{
+  if (narg < 8) error->all(FLERR, "Illegal fix dt/adaptive command");
+  time_depend = 1;
+  scalar_flag = 1;
+  global_freq = 1;
+  extscalar = 0;
+  dynamic_group_allow = 1;
+  nevery = force->inumeric(FLERR, arg[3]);
+  if (nevery <= 0) error->all(FLERR, "Illegal fix dt/adaptive command");
+  minbound = maxbound = 1;
+  tmin = tmax = 0.0;
+  if (strcmp(arg[4], "NULL") == 0) minbound = 0;
+  else tmin = force->numeric(FLERR, arg[4]);
+  if (strcmp(arg[5], "NULL") == 0) maxbound = 0;
+  else tmax = force->numeric(FLERR, arg[5]);
+  CFLmax = force->numeric(FLERR, arg[6]);
+  dxAve = force->numeric(FLERR, arg[7]);
+  if (minbound && tmin < 0.0) error->all(FLERR, "Illegal fix dt/adaptive command");
+  if (maxbound && tmax < 0.0) error->all(FLERR, "Illegal fix dt/adaptive command");
+  if (minbound && maxbound && tmin >= tmax) error->all(FLERR, "Illegal fix dt/adaptive command");
+  if (CFLmax <= 0.0) error->all(FLERR, "Illegal fix dt/adaptive command");
+  if (dxAve <= 0.0) error->all(FLERR, "Illegal fix dt/adaptive command");
+  laststep = update->ntimestep;
+  dt = update->dt;
+}
+
+int FixDtAdaptiveCuda::setmask() { return FixConst::END_OF_STEP; }
+
+void FixDtAdaptiveCuda::init() { dt = update->dt; }
+
+void FixDtAdaptiveCuda::setup(int) { end_of_step(); }
+
+void FixDtAdaptiveCuda::end_of_step()
+{
+  SphbvfLmp *engine = SphbvfLmp::get(lmp);
+  if (!engine->active()) error->all(FLERR, "fix dt/adaptive/cuda requires pair_style ssa_tsdpd/bvf/<style>/cuda");
+  double maxAllVsq = 0.0;
+  engine->check(sphbvf_max_vsq(engine->ctx, groupbit, &maxAllVsq));
+  dt = CFLmax * dxAve / sqrt(maxAllVsq);
+  if (minbound) dt = MAX(dt, tmin);
+  if (maxbound) dt = MIN(dt, tmax);
+  if (dt == update->dt) return;
+  laststep = update->ntimestep;
+  update->update_time();
+  update->dt = dt;
+  if (force->pair) force->pair->reset_dt();
+  for (int i = 0; i < modify->nfix; i++) modify->fix[i]->reset_dt();
+}
+
+double FixDtAdaptiveCuda::compute_scalar() { return (double)laststep; }

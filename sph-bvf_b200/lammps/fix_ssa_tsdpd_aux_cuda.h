@@ -14,6 +14,8 @@ FixStyle(ssa_tsdpd/buoyancy/cuda,FixSsaTsdpdBuoyancyCuda)
 FixStyle(ssa_tsdpd/forcing/cuda,FixSsaTsdpdForcingCuda)
 FixStyle(ssa_tsdpd/buffer/cuda,FixSsaTsdpdBufferCuda)
 FixStyle(setforce/cuda,FixSetForceCuda)
+FixStyle(ssa_tsdpd/chem_rxn_mass_action/cuda,FixSsaTsdpdChemRxnMassActionCuda)
+FixStyle(dt/adaptive/cuda,FixDtAdaptiveCuda)
 
 #else
 
@@ -52,6 +54,28 @@ class FixSsaTsdpdBufferCuda : public FixSphbvfRegistered {
 class FixSetForceCuda : public FixSphbvfRegistered {
  public:
   FixSetForceCuda(class LAMMPS *, int, char **);
+};
+
+// fix ID group ssa_tsdpd/chem_rxn_mass_action k nreact r.. nprod p..  (fix_ssa_tsdpd_chem_rxn_mass_action.cpp)
+class FixSsaTsdpdChemRxnMassActionCuda : public FixSphbvfRegistered {
+ public:
+  FixSsaTsdpdChemRxnMassActionCuda(class LAMMPS *, int, char **);
+};
+
+// fix ID group dt/adaptive N tmin tmax CFLmax dxAve (fix_dt_adaptive.cpp:39-170): the max |v|^2 comes from
+// the device (sphbvf_max_vsq), the CFL arithmetic and the reset_dt() fan-out stay on the host
+class FixDtAdaptiveCuda : public Fix {
+ public:
+  FixDtAdaptiveCuda(class LAMMPS *, int, char **);
+  int setmask();
+  void init();
+  void setup(int);
+  void end_of_step();
+  double compute_scalar();
+ private:
+  int minbound, maxbound;
+  double tmin, tmax, CFLmax, dxAve, dt;
+  bigint laststep;
 };
 
 }

@@ -85,9 +85,9 @@ void FixSsaTsdpdBvfCuda::setup_pre_force(int)
 
 /* modify->setup(): post_force of the registered fixes once (FixSetForce::setup, FixSsaTsdpdBuoyancy::setup) */
 
-void FixSsaTsdpdBvfCuda::setup(int vflag)
+void FixSsaTsdpdBvfCuda::setup(int)
 {
-  post_force(vflag);
+  engine->check(sphbvf_setup_post_force(engine->ctx));
   engine->to_host();   // thermo output of step 0 reads the host arrays
 }
 

@@ -123,6 +123,12 @@ void SphbvfLmp::start()
       case 1: check(sphbvf_add_forcing(ctx, f.groupbit, f.ia[0], (long)f.step, f.ia[1], f.ia[2], f.a[0], f.a[1], f.a[2], f.a[3], f.a[4])); break;
       case 2: check(sphbvf_add_buffer(ctx, f.groupbit, f.ia[0], f.ia[2], (long)f.step, f.ia[1], f.a[0], f.a[1], f.a[2], f.a[3], f.a[4])); break;
       case 3: check(sphbvf_add_setforce(ctx, f.groupbit, f.a[0], f.a[1], f.a[2])); break;
+      case 4: {
+        int r[2] = {f.ia[1] & 255, (f.ia[1] >> 8) & 255};
+        int p[4] = {f.ia[2] & 255, (f.ia[2] >> 8) & 255, (f.ia[2] >> 16) & 255, (f.ia[2] >> 24) & 255};
+        check(sphbvf_add_chem_rxn(ctx, f.groupbit, f.a[0], f.ia[0] & 255, r, f.ia[0] >> 8, p));
+        break;
+      }
     }
   }
 

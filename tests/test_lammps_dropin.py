@@ -266,7 +266,60 @@ thermo 6
 run 24
 """
 
-DECKS = {"cavity2d": CAVITY2D, "cavity3d": CAVITY3D, "natconv2d": NATCONV2D, "fsi2d": FSI2D, "ring2d": RING2D}
+# three species with mass-action reactions A + B -> C, C -> A and a constant source of B, and a CFL-
+# controlled timestep: fix ssa_tsdpd/chem_rxn_mass_action and fix dt/adaptive (no shipped deck uses
+# them; SURVEY.md 8f-3)
+REACT2D = """
+dimension 2
+units si
+atom_style ssa_tsdpd/atomic 3 0 0
+boundary f f p
+variable n equal 26
+variable d equal 1.0/(v_n-6)
+variable lo equal -3*v_d
+variable hi equal 1.0+3*v_d
+region box block ${lo} ${hi} ${lo} ${hi} 0 ${d} units box
+create_box 2 box
+lattice sq ${d} origin 0.5 0.5 0.0
+create_atoms 2 box
+region inner block 0 1 0 1 0 ${d} units box
+group fluid region inner
+set group fluid type 1
+group solid subtract all fluid
+mass * $(v_d*v_d)
+set group all ssa_tsdpd/rho 1.0
+set group all ssa_tsdpd/e 0.
+variable ca atom 0.5+0.5*sin(PI*x)
+variable cb atom 0.5+0.5*cos(PI*y)
+set group all ssa_tsdpd/C 0 v_ca
+set group all ssa_tsdpd/C 1 v_cb
+set group all ssa_tsdpd/C 2 0.1
+set group solid ssa_tsdpd/solid_tag 1 fixed
+variable h equal 2.5*v_d
+pair_style ssa_tsdpd/bvf/transportVelocity
+pair_coeff * * 1.0 5.0 1e-2 ${h} ${h} 0.0 0.02 0.01 0.005
+variable ux atom 0.6*sin(PI*x)*cos(PI*y)
+variable uy atom -0.6*cos(PI*x)*sin(PI*y)
+velocity fluid set v_ux v_uy 0.0 units box
+fix integ all ssa_tsdpd/bvf/transportVelocity
+fix rxn1 fluid ssa_tsdpd/chem_rxn_mass_action 0.5 2 0 1 1 2
+fix rxn2 fluid ssa_tsdpd/chem_rxn_mass_action 0.7 1 2 1 0
+fix src fluid ssa_tsdpd/chem_rxn_mass_action 0.05 0 1 1
+fix cfl fluid dt/adaptive 1 1e-5 1e-3 0.005 ${d}
+neighbor $(0.3*v_h) bin
+timestep 2e-4
+compute crho all ssa_tsdpd/rho/atom
+compute c0 all ssa_tsdpd/C/atom 0
+compute c1 all ssa_tsdpd/C/atom 1
+compute c2 all ssa_tsdpd/C/atom 2
+dump d all custom 8 dump.*.txt id type x y vx vy fx fy c_crho c_c0 c_c1 c_c2
+dump_modify d sort id format float %.17g
+thermo_style custom step temp epair emol etotal press dt
+thermo 8
+run 32
+"""
+
+DECKS = {"react2d": REACT2D, "cavity2d": CAVITY2D, "cavity3d": CAVITY3D, "natconv2d": NATCONV2D, "fsi2d": FSI2D, "ring2d": RING2D}
 
 
 def read_dumps(wd):
@@ -319,7 +372,10 @@ def test_deck_unchanged_with_sf_cuda(name):
     # thermo output (temperature from the synced host velocities, pressure from the device virial,
     # sphbvf_virial == Pair::virial_fdotr_compute): printed with 5-6 significant digits
     ta, tb = read_thermo(out_ref), read_thermo(out_cuda)
-    assert ta.shape == tb.shape and ta.shape[0] >= 3 and ta.shape[1] == 6, (ta.shape, tb.shape)
+    assert ta.shape == tb.shape and ta.shape[0] >= 3 and ta.shape[1] >= 6, (ta.shape, tb.shape)
+    if ta.shape[1] == 7:     # the deck prints the (adaptive) timestep as a 7th column
+        assert len(set(ta[:, 6])) > 1, "dt/adaptive did not change the timestep"
+        assert np.abs(ta[:, 6] - tb[:, 6]).max() <= 2e-5 * ta[:, 6].max(), (ta[:, 6], tb[:, 6])
     assert np.array_equal(ta[:, 0], tb[:, 0])
     for col, what in ((1, "Temp"), (5, "Press")):
         scale = np.abs(ta[:, col]).max()
@@ -333,7 +389,7 @@ def test_deck_unchanged_with_sf_cuda(name):
         # agree only where no fluid-solid pair matters: tight for the ring deck (solid away from the
         # periodic faces), loose for the channel deck (walls cross a periodic face), not at all for the
         # wall-bounded transportVelocity decks.
-        if what == "Press" and name.startswith(("cavity", "natconv")):
+        if what == "Press" and name.startswith(("cavity", "natconv", "react")):
             continue
         tol = 2e-3 if (what == "Press" and name == "fsi2d") else 2e-5
         if what == "Press" and name == "fsi2d":
@@ -349,7 +405,7 @@ def test_deck_unchanged_with_sf_cuda(name):
         assert a.shape == b.shape, (name, s, a.shape, b.shape)
         assert np.array_equal(a[:, 0], b[:, 0]) and np.array_equal(a[:, 1], b[:, 1])
         # forces on FIXED solids are never consumed and orientation dependent in the reference
-        fixed = np.isin(a[:, 1], [2]) if name.startswith(("cavity", "natconv")) else np.isin(a[:, 1], [3]) if name == "fsi2d" else np.zeros(len(a), bool)
+        fixed = np.isin(a[:, 1], [2]) if name.startswith(("cavity", "natconv", "react")) else np.isin(a[:, 1], [3]) if name == "fsi2d" else np.zeros(len(a), bool)
         for k, c in enumerate(cols[2:], start=2):
             x, y = a[:, k], b[:, k]
             if c in ("fx", "fy", "fz"):
