@@ -308,7 +308,8 @@ def main():
     eng.profiling(True)
     eng.run(K)
     fam = {}
-    for idx, nm in enumerate(["pair", "initial_integrate", "final_integrate", "neighbor_rebuild", "pack_halo", "fixes"]):
+    for idx, nm in enumerate(["pair", "initial_integrate", "final_integrate", "neighbor_rebuild", "pack_halo", "fixes",
+                              "final_initial_pack_fused"]):
         t, c = eng.kernel_ms(idx)
         fam[nm] = {"ms": t, "launches": c}
     eng.profiling(False)

@@ -156,7 +156,12 @@ int sphbvf_post_force(sphbvf_ctx *ctx);        /* buoyancy / setforce / chem_rxn
 /* Modify::setup -> Fix::setup at the start of a run: only the fixes whose setup() forwards to
  * post_force (setforce, buoyancy) act; follows the first pair_compute */
 int sphbvf_setup_post_force(sphbvf_ctx *ctx);
-int sphbvf_final_integrate(sphbvf_ctx *ctx);   /* Fix*::final_integrate (:244) */
+/* Fix*::final_integrate (:244).  The launch is deferred: if the next call on this context is
+ * sphbvf_initial_integrate (nothing scheduled between two steps, as in Verlet::run without output or
+ * end_of_step fixes) ONE kernel runs final_integrate(n) + initial_integrate(n+1) and writes the pair-input
+ * records, bit-identical to the separate kernels; any other entry point first runs the plain
+ * final_integrate, so results are never observed out of order.  SPHBVF_NO_FUSE=1 disables the deferral. */
+int sphbvf_final_integrate(sphbvf_ctx *ctx);
 int sphbvf_end_of_step(sphbvf_ctx *ctx);       /* buffer(density) end_of_step */
 /* force a neighbour rebuild now (pbc + ghosts + sort + list), as Neighbor::build on a rebuild step */
 int sphbvf_build_neighbors(sphbvf_ctx *ctx);
@@ -178,7 +183,8 @@ int sphbvf_sync(sphbvf_ctx *ctx);
  * family in ms (CUDA events on the context's stream; enable with sphbvf_set_profiling) */
 long sphbvf_launch_count(const sphbvf_ctx *ctx);
 int sphbvf_set_profiling(sphbvf_ctx *ctx, int on);
-/* which: 0 pair, 1 initial_integrate, 2 final_integrate, 3 neighbor rebuild, 4 pack/halo, 5 fixes */
+/* which: 0 pair, 1 initial_integrate, 2 final_integrate, 3 neighbor rebuild, 4 pack/halo, 5 fixes,
+ * 6 fused final_integrate(n) + initial_integrate(n+1) + pack (see sphbvf_final_integrate) */
 double sphbvf_kernel_ms(const sphbvf_ctx *ctx, int which, long *launches);
 void *sphbvf_stream(sphbvf_ctx *ctx);         /* the cudaStream_t all work is queued on */
 

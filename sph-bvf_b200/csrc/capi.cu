@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -85,6 +86,22 @@ void sphbvf_ctx::drain_events() {
   }
   ev_list.clear();
 }
+
+// see context.cuh: a deferred final_integrate runs here unless sphbvf_initial_integrate absorbed it
+int flush_final(sphbvf_ctx *ctx) {
+  if (!ctx->final_pending) return 0;
+  ctx->final_pending = 0;
+  ctx->tic(K_FINAL);
+  launch_final_integrate(ctx->d, ctx->co, ctx->pend_dt, ctx->pend_step, ctx->cfg.integrate_groupbit, ctx->with_dev, ctx->st);
+  ctx->toc();
+  CKLAUNCH();
+  return 0;
+}
+#define FLUSH()                                  \
+  do {                                           \
+    int rcf_ = flush_final(ctx);                 \
+    if (rcf_) return rcf_;                       \
+  } while (0)
 
 static int ensure_scan(sphbvf_ctx *ctx, long n) {
   const long need = n / 1024 + 8192;
@@ -396,6 +413,7 @@ int sphbvf_create(const sphbvf_config *cfg, sphbvf_ctx **out) {
   }
   cudaMemset(ctx->w.flags, 0, sizeof(int) * 8);
   ctx->run_nsteps_user = -1;
+  { const char *e = getenv("SPHBVF_NO_FUSE"); ctx->fuse = !(e && atoi(e)); }
   *out = ctx;
   return 0;
 }
@@ -517,6 +535,8 @@ int sphbvf_set_atoms(sphbvf_ctx *ctx, int n, const int *tag, const int *type, co
   ctx->atoms_set = 1;
   ctx->setup_done = 0;
   ctx->migrated = 0;
+  ctx->final_pending = 0;
+  ctx->pack_valid = 0;
   return 0;
 }
 
@@ -573,7 +593,13 @@ static int run_fixes(sphbvf_ctx *ctx, int hook, bool in_setup = false) {
   bool any = false;
   for (int q = 0; q < ctx->nfix; q++) {
     if (in_setup && ctx->fixes[q].kind == FIX_CHEMRXN) continue;
-    if (!any) { ctx->tic(K_FIX, 0); any = true; }
+    if (!fix_runs(ctx->fixes[q], hook, ctx->ntimestep)) continue;
+    if (!any) {
+      FLUSH();
+      ctx->tic(K_FIX, 0);
+      any = true;
+      if (hook == 0) ctx->pack_valid = 0;   // post_integrate fixes edit vest / C after the records were written
+    }
     ctx->launches_fam[K_FIX]++;
     launch_fix(ctx->d, ctx->co, ctx->fixes[q], hook, ctx->ntimestep, ctx->st);
   }
@@ -585,6 +611,8 @@ int sphbvf_build_neighbors(sphbvf_ctx *ctx) {
   if (!ctx->atoms_set) return ctx->fail(SPHBVF_ESTATE, "build_neighbors before set_atoms");
   cudaSetDevice(ctx->cfg.device);
   int rc;
+  FLUSH();
+  ctx->pack_valid = 0;
   if ((rc = init_neighbor(ctx))) return rc;
   if (ctx->cfg.nranks > 1) return comm_rebuild(ctx);
   return rebuild(ctx);
@@ -594,6 +622,7 @@ int sphbvf_setup(sphbvf_ctx *ctx) {
   if (!ctx->atoms_set) return ctx->fail(SPHBVF_ESTATE, "setup before set_atoms");
   cudaSetDevice(ctx->cfg.device);
   int rc;
+  FLUSH();
   // Deliberate deviation: Verlet::setup creates ghosts BEFORE setup_pre_force sets
   // vest = v, rhoI = rho (verlet.cpp:118-132), so the reference's ghosts hold stale vest/rhoI at
   // step 0 -- and with its half list + Newton mirror the step-0 result is then not even
@@ -621,6 +650,7 @@ int sphbvf_setup_neighbors(sphbvf_ctx *ctx) {
   if (!ctx->atoms_set) return ctx->fail(SPHBVF_ESTATE, "setup before set_atoms");
   cudaSetDevice(ctx->cfg.device);
   int rc;
+  FLUSH();
   if (ctx->cfg.nranks > 1) {
     int v[3] = {ctx->any_solid, ctx->with_dev, ctx->e_nonzero};
     if ((rc = comm_allreduce_max(ctx, v, 3))) return rc;
@@ -634,8 +664,24 @@ int sphbvf_setup_neighbors(sphbvf_ctx *ctx) {
 }
 
 int sphbvf_initial_integrate(sphbvf_ctx *ctx) {
+  if (ctx->final_pending) {
+    // nothing touched the state since the deferred final_integrate: one pass does both halves and, unless a
+    // post_integrate fix may still edit vest / C, writes the pair-input records as well
+    int do_pack = 1;
+    for (int q = 0; q < ctx->nfix; q++)
+      if (ctx->fixes[q].kind == FIX_FORCING || (ctx->fixes[q].kind == FIX_BUFFER && ctx->fixes[q].ia[0] != 2)) do_pack = 0;
+    ctx->final_pending = 0;
+    ctx->tic(K_FUSED);
+    launch_final_initial(ctx->d, ctx->co, ctx->pend_dt, ctx->pend_step, ctx->cfg.dt, ctx->ntimestep,
+                         ctx->cfg.integrate_groupbit, do_pack, ctx->with_dev, ctx->st);
+    ctx->toc();
+    CKLAUNCH();
+    ctx->pack_valid = do_pack;
+    return 0;
+  }
+  ctx->pack_valid = 0;
   ctx->tic(K_INITIAL);
-  launch_initial_integrate(ctx->d, ctx->co, ctx->cfg.dt, ctx->ntimestep, ctx->cfg.integrate_groupbit, ctx->st);
+  launch_initial_integrate(ctx->d, ctx->co, ctx->cfg.dt, ctx->ntimestep, ctx->cfg.integrate_groupbit, ctx->with_dev, ctx->st);
   ctx->toc();
   CKLAUNCH();
   return 0;
@@ -649,6 +695,9 @@ int sphbvf_end_of_step(sphbvf_ctx *ctx) { return run_fixes(ctx, 2); }
 int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt) {
   if (!ctx->setup_done) return ctx->fail(SPHBVF_ESTATE, "neighbor before setup");
   int rc, flag = 0;
+  FLUSH();
+  const int pack_valid = ctx->pack_valid;
+  ctx->pack_valid = 0;
   // Neighbor::decide (neighbor.cpp:1922-1937)
   ctx->ago++;
   if (ctx->ago >= ctx->cfg.neigh_delay && ctx->ago % ctx->cfg.neigh_every == 0) {
@@ -665,8 +714,9 @@ int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt) {
   if (rebuilt) *rebuilt = flag;
   if (flag) return ctx->cfg.nranks > 1 ? comm_rebuild(ctx) : rebuild(ctx);
   // Comm::forward_comm (comm_brick.cpp:460-520): refresh the packed records of owned atoms and ghosts
-  ctx->tic(K_PACK);
-  launch_pack(ctx->d, ctx->co, ctx->with_dev, ctx->st);
+  if (pack_valid && ctx->cfg.nranks == 1 && !ctx->d.nghost) return 0;   // records are current, nothing to refresh
+  ctx->tic(K_PACK, pack_valid ? 0 : 1);
+  if (!pack_valid) launch_pack(ctx->d, ctx->co, ctx->with_dev, ctx->st);
   if (ctx->cfg.nranks > 1) { if ((rc = comm_forward(ctx))) return rc; }
   else launch_ghost_refresh(ctx->d, ctx->co, ctx->with_dev, ctx->st);
   ctx->toc();
@@ -676,6 +726,7 @@ int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt) {
 
 int sphbvf_pair_compute(sphbvf_ctx *ctx) {
   if (!ctx->setup_done) return ctx->fail(SPHBVF_ESTATE, "pair_compute before setup");
+  FLUSH();
   ctx->tic(K_PAIR);
   launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->st);
   ctx->toc();
@@ -693,6 +744,7 @@ int sphbvf_pair_compute(sphbvf_ctx *ctx) {
 int sphbvf_virial(sphbvf_ctx *ctx, double *virial6) {
   if (!ctx->setup_done) return ctx->fail(SPHBVF_ESTATE, "virial before setup");
   cudaSetDevice(ctx->cfg.device);
+  FLUSH();
   if (!ctx->d_virial) CK(cudaMalloc((void **)&ctx->d_virial, sizeof(double) * 6));
   CK(cudaMemsetAsync(ctx->d_virial, 0, sizeof(double) * 6, ctx->st));
   launch_virial(ctx->d, ctx->co, pair_flags(ctx), ctx->d_virial, ctx->st);
@@ -705,6 +757,7 @@ int sphbvf_virial(sphbvf_ctx *ctx, double *virial6) {
 int sphbvf_max_vsq(sphbvf_ctx *ctx, int groupbit, double *max_vsq) {
   if (!ctx->atoms_set) return ctx->fail(SPHBVF_ESTATE, "max_vsq before set_atoms");
   cudaSetDevice(ctx->cfg.device);
+  FLUSH();
   if (!ctx->d_virial) CK(cudaMalloc((void **)&ctx->d_virial, sizeof(double) * 6));
   unsigned long long *slot = (unsigned long long *)ctx->d_virial;
   CK(cudaMemsetAsync(slot, 0, sizeof(unsigned long long), ctx->st));
@@ -722,8 +775,15 @@ int sphbvf_max_vsq(sphbvf_ctx *ctx, int groupbit, double *max_vsq) {
 }
 
 int sphbvf_final_integrate(sphbvf_ctx *ctx) {
+  FLUSH();
+  if (ctx->fuse) {   // deferred: see flush_final / sphbvf_initial_integrate
+    ctx->final_pending = 1;
+    ctx->pend_dt = ctx->cfg.dt;
+    ctx->pend_step = ctx->ntimestep;
+    return 0;
+  }
   ctx->tic(K_FINAL);
-  launch_final_integrate(ctx->d, ctx->co, ctx->cfg.dt, ctx->ntimestep, ctx->cfg.integrate_groupbit, ctx->st);
+  launch_final_integrate(ctx->d, ctx->co, ctx->cfg.dt, ctx->ntimestep, ctx->cfg.integrate_groupbit, ctx->with_dev, ctx->st);
   ctx->toc();
   CKLAUNCH();
   return 0;
@@ -744,6 +804,7 @@ int sphbvf_run(sphbvf_ctx *ctx, int nsteps) {
     if ((rc = sphbvf_final_integrate(ctx))) return rc;
     if ((rc = sphbvf_end_of_step(ctx))) return rc;
   }
+  FLUSH();
   CK(cudaStreamSynchronize(ctx->st));
   return 0;
 }
@@ -756,6 +817,7 @@ int sphbvf_ndanger(const sphbvf_ctx *ctx) { return ctx->ndanger; }
 void *sphbvf_stream(sphbvf_ctx *ctx) { return (void *)ctx->st; }
 
 int sphbvf_sync(sphbvf_ctx *ctx) {
+  FLUSH();
   CK(cudaStreamSynchronize(ctx->st));
   return 0;
 }
@@ -767,6 +829,7 @@ long sphbvf_launch_count(const sphbvf_ctx *ctx) {
 }
 
 int sphbvf_set_profiling(sphbvf_ctx *ctx, int on) {
+  FLUSH();
   cudaStreamSynchronize(ctx->st);
   ctx->drain_events();
   ctx->profiling = on;
@@ -777,6 +840,7 @@ int sphbvf_set_profiling(sphbvf_ctx *ctx, int on) {
 double sphbvf_kernel_ms(const sphbvf_ctx *cctx, int which, long *launches) {
   sphbvf_ctx *ctx = const_cast<sphbvf_ctx *>(cctx);
   if (which < 0 || which >= K_NFAM) return -1.0;
+  if (flush_final(ctx)) return -1.0;
   cudaStreamSynchronize(ctx->st);
   ctx->drain_events();
   if (launches) *launches = ctx->launches_fam[which];
@@ -834,6 +898,7 @@ int sphbvf_download(sphbvf_ctx *ctx, int field, void *host) {
   int nc, is_int, rc;
   if (!field_info(ctx, field, &p, &nc, &is_int)) return ctx->fail(SPHBVF_EINVAL, "unknown field %d", field);
   if (ctx->migrated) return ctx->fail(SPHBVF_ESTATE, "atoms migrated between ranks: use sphbvf_download_local");
+  FLUSH();
   const int n = ctx->d.nlocal;
   if (!n || !nc) return 0;
   cudaSetDevice(ctx->cfg.device);
@@ -856,6 +921,7 @@ int sphbvf_download_local(sphbvf_ctx *ctx, int field, void *host, int cap_rows) 
   if (cap_rows < n) return ctx->fail(SPHBVF_EINVAL, "download_local: buffer too small (%d < %d)", cap_rows, n);
   if (!n || !nc) return 0;
   cudaSetDevice(ctx->cfg.device);
+  FLUSH();
   CK(cudaMemcpyAsync(host, p, (is_int ? 4 : 8) * (size_t)n * nc, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   return 0;
@@ -869,6 +935,8 @@ int sphbvf_upload_local(sphbvf_ctx *ctx, int field, const void *host, int nrows)
   if (nrows != n) return ctx->fail(SPHBVF_EINVAL, "upload_local: %d rows given, %d atoms owned", nrows, n);
   if (!n || !nc) return 0;
   cudaSetDevice(ctx->cfg.device);
+  FLUSH();
+  ctx->pack_valid = 0;
   CK(cudaMemcpyAsync(p, host, (is_int ? 4 : 8) * (size_t)n * nc, cudaMemcpyHostToDevice, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   return 0;
@@ -879,6 +947,8 @@ int sphbvf_upload(sphbvf_ctx *ctx, int field, const void *host) {
   int nc, is_int, rc;
   if (!field_info(ctx, field, &p, &nc, &is_int)) return ctx->fail(SPHBVF_EINVAL, "unknown field %d", field);
   if (ctx->migrated) return ctx->fail(SPHBVF_ESTATE, "atoms migrated between ranks: upload by slot is undefined");
+  FLUSH();
+  ctx->pack_valid = 0;
   const int n = ctx->d.nlocal;
   if (!n || !nc) return 0;
   cudaSetDevice(ctx->cfg.device);

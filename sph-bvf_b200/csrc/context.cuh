@@ -28,6 +28,12 @@ struct sphbvf_ctx {
   int ago = 0, nbuilds = 0, ndanger = 0, maxneigh_seen = 0;
   int atoms_set = 0, setup_done = 0, with_dev = 0, any_solid = 0, e_nonzero = 0, migrated = 0;
   double cutneighmax = 0.0, triggersq = 0.0;
+  // lazy fusion of the integrators: sphbvf_final_integrate only records its arguments; if the next call that
+  // touches the state is sphbvf_initial_integrate, ONE kernel does final(n) + initial(n+1) + pack, otherwise
+  // flush_final() launches the plain final_integrate first (any other entry point calls it)
+  int fuse = 1, final_pending = 0, pack_valid = 0;
+  double pend_dt = 0.0;
+  long pend_step = 0;
   int random_set = 0;
   double kboltz = 0.0;
   unsigned long long seed = 0;
@@ -56,6 +62,7 @@ int rebuild_sort(sphbvf_ctx *ctx);       // pbc + cell sort + permutation of the
 int rebuild_finish(sphbvf_ctx *ctx);     // ghost binning + Verlet list + xhold
 int ctx_ensure_capacity(sphbvf_ctx *ctx, int nmax, int nallmax);
 int ctx_fetch_flags(sphbvf_ctx *ctx);    // w.flags -> h_flags[0..8), synchronises the stream
+int flush_final(sphbvf_ctx *ctx);        // launch a final_integrate that sphbvf_final_integrate deferred
 
 // comm.cu / comm_nccl.cu: brick decomposition over NCCL (one rank per GPU)
 int comm_rebuild(sphbvf_ctx *ctx);        // pbc + migration + sort + borders + list

@@ -32,177 +32,262 @@ __device__ __forceinline__ void damp_factors(int variant, long ntimestep, double
   else dampSolid = tnow <= 1.0 ? 0.0 : 1.0;                              // ..._fsi.cpp:150-152
 }
 
-// Both integrators are pure streaming (HBM bound).  Every array an atom may need is loaded
-// UNCONDITIONALLY at the top of the kernel, before any branch on solid_tag / fixed_tag: with the
-// loads inside the branches the kernels ran at 23-30 % of HBM peak, all warps waiting on one
-// dependent round trip after another (ncu long_scoreboard 90 %, profiles/); the deviatoric tensors
-// (solids only) stay behind their branch.
-template <int VARIANT>
+__device__ __forceinline__ double ldv(const double *p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ldi(const int *p) {
+  int v;
+  asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// pack: primary state -> pair input records.  Holds every per-particle division of the pair pass:
+// V = m/rho, P/rho^2 with P = 7 B (rho/rho0 - 1) (pair_...transport_velocity.cpp:298-299), and the
+// scalar artificial stress of a stress-free solid (:454-461 with dev = 0).  Shared by pack_kernel and
+// the fused integrator so both produce the same bits.
+__device__ __forceinline__ void pack_atom(const DevState &d, const Coeffs &co, const int i, const int t, const int solid,
+                                          const int fixed, const double *x, const double *v, const double *vest,
+                                          const double rho, const double rhoI, const double e, const int with_dev) {
+  const double irho = 1.0 / rho;
+  const double P = 7.0 * co.B[t] * (rho / co.rho0[t] - 1.0);
+  const double Prr = P * irho * irho;
+  Prec r;
+  r.A = make_rec4(x[0], x[1], x[2], rho);
+  r.B = make_rec4(vest[0], vest[1], vest[2], co.mass[t] * irho);
+  r.C = make_rec4(vest[0] - v[0], vest[1] - v[1], vest[2] - v[2], Prr);
+  d.prec[i] = r;
+  double art = 0.0;
+  if (solid) {
+    const double c_art = co.variant == SPHBVF_FSI ? 0.1 : 0.35;
+    const double Ps = co.variant == SPHBVF_MECHANICS ? fabs(P) : P;
+    const double ts = -Ps;
+    art = ts > 0.0 ? -c_art * ts * irho * irho : 0.0;
+  }
+  const double C0 = co.nspecies ? d.C[(size_t)i * co.nspecies] : 0.0;
+  d.pD[i] = make_rec4(rhoI, art, C0, e);
+  d.pflags[i] = t | (solid << 4) | (fixed << 5);
+  for (int k = 0; k < co.nspecies; k++) d.pCs[(size_t)i * co.nspecies + k] = d.C[(size_t)i * co.nspecies + k];
+  if (with_dev)
+    for (int k = 0; k < 9; k++) d.pdev[9 * (size_t)i + k] = d.dev[9 * (size_t)i + k];
+}
+
+// The integrators are pure streaming (HBM bound): ONE kernel template holds both halves so that the
+// three ways of running them execute the same arithmetic on the same values, bit for bit:
+//   MODE 0  initial_integrate(step)                                  (fix_...:99-240)
+//   MODE 1  final_integrate(step)                                    (fix_...:244-461)
+//   MODE 2  final_integrate(step - 1) followed by initial_integrate(step) and, if asked, the pack of the
+//           pair-input records: what Verlet::run executes back to back when nothing is scheduled
+//           between two steps.  v, x, rho, rhoI stay in registers between the halves, f / drho / masks
+//           are read once and the intermediate state is never written: 444 B per atom instead of 664.
+// Every array an atom may need is loaded UNCONDITIONALLY at the top, before any branch on solid_tag /
+// fixed_tag: with the loads inside the branches the kernels ran at 23-30 % of HBM peak, all warps
+// waiting on one dependent round trip after another (ncu long_scoreboard 90 %, profiles/); the
+// deviatoric tensors (solids only) stay behind their branch.
+struct IntegArgs {
+  double dt_final, dt_init;
+  long step_final, step_init;
+  int groupbit, do_pack, with_dev;
+};
+
+template <int VARIANT, int MODE>
 __global__ void __launch_bounds__(256)
-initial_integrate_kernel(const DevState d, const __grid_constant__ Coeffs co, const double dtv, const long ntimestep,
-                         const int groupbit) {
+integrate_kernel(const DevState d, const __grid_constant__ Coeffs co, const IntegArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.nlocal) return;
   const size_t i3 = 3 * (size_t)i;
-  const int mask = d.mask[i], type = d.type[i], solid = d.solid[i], fixed = d.fixed[i];
-  const double rho = d.rho[i], drho = d.drho[i];
-  double v[3], f[3], ddv[3], x[3], ddx[3] = {0, 0, 0};
+  constexpr bool FIN = MODE != 0, INI = MODE != 1;
+  // freqFilter 20 (TV :287, mechanics :311); fsi: 1e16 -> INT_MAX, never fires (..._fsi.cpp:304)
+  const bool filter = FIN && (VARIANT == SPHBVF_FSI ? (a.step_final % 2147483647L) == 0 : (a.step_final % 20) == 0);
+  // one batch of loads, none of them behind a branch on loaded data (ldv/ldi are volatile: the compiler may
+  // neither sink them into the branches that use them nor split the batch)
+  const int mask = ldi(d.mask + i), type = ldi(d.type + i), solid = ldi(d.solid + i), fixed = ldi(d.fixed + i);
+  const double drho = ldv(d.drho + i);
+  double rho = 0.0, rhoI = 0.0, nd = 1.0, phi0 = 0.0, shep = 0.0, e_i = 0.0;
+  double v[3], f[3], x[3] = {0, 0, 0}, vest[3] = {0, 0, 0}, ddv[3] = {0, 0, 0}, ddx[3] = {0, 0, 0}, nw[3] = {0, 0, 0};
 #pragma unroll
-  for (int k = 0; k < 3; k++) { v[k] = d.v[i3 + k]; f[k] = d.f[i3 + k]; ddv[k] = d.ddv[i3 + k]; x[k] = d.x[i3 + k]; }
-  double ndi = 1.0;
+  for (int k = 0; k < 3; k++) { v[k] = ldv(d.v + i3 + k); f[k] = ldv(d.f + i3 + k); }
+  if (FIN) {
+    nd = ldv(d.nd + i); phi0 = ldv(d.phi + i); rhoI = ldv(d.rhoI + i);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { nw[k] = ldv(d.nw + i3 + k); vest[k] = ldv(d.vest + i3 + k); }
+  }
+  if (INI) {
+    if (!FIN) rho = ldv(d.rho + i);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { ddv[k] = ldv(d.ddv + i3 + k); x[k] = ldv(d.x + i3 + k); }
+    if (VARIANT != SPHBVF_TV && !FIN) nd = ldv(d.nd + i);
+  }
   if (VARIANT != SPHBVF_TV) {
-    ndi = d.nd[i];
 #pragma unroll
-    for (int k = 0; k < 3; k++) ddx[k] = d.ddx[i3 + k];
+    for (int k = 0; k < 3; k++) ddx[k] = ldv(d.ddx + i3 + k);
   }
-  if (!(mask & groupbit)) return;
-  const double dtf = 0.5 * dtv;
-  const double dtfm = dtf / co.mass[type];
-  double damp, dampSolid;
-  damp_factors(VARIANT, ntimestep, damp, dampSolid);
-  if (fixed == 0) {
-    if (solid == 0) {
+  if (MODE == 2 && a.do_pack) e_i = ldv(d.e + i);
+  if (filter) shep = ldv(d.rhoAux1 + i) / ldv(d.rhoAux2 + i);
+  const bool ingroup = (mask & a.groupbit) != 0;
+  if (MODE == 2 && !ingroup) { rho = d.rho[i]; rhoI = d.rhoI[i]; }
+  // deviatoric tensors exist only when some solid can carry stress (with_dev); otherwise dev == ddev == 0 and
+  // the reference's dev += c * ddev is the identity
+  const bool devs = a.with_dev != 0;
+
+  // ---------------------------------------------------------------- final_integrate(step_final)
+  if (FIN && ingroup) {
+    const double dtv = a.dt_final, dtf = 0.5 * dtv;
+    const double dtfm = dtf / co.mass[type];
+    double damp, dampSolid;
+    damp_factors(VARIANT, a.step_final, damp, dampSolid);
+    const double phi = phi0 / nd;
+    d.phi[i] = phi;
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        double vest;
-        if (VARIANT == SPHBVF_TV) vest = v[k] + dtfm * f[k];
-        else vest = v[k] + dtfm * f[k] * damp + 0.001 * ddx[k] / ndi;
-        const double vn = vest - dtfm * ddv[k];
-        d.vest[i3 + k] = vest;
-        d.v[i3 + k] = vn;
-        d.x[i3 + k] = x[k] + dtv * vn;
+    for (int k = 0; k < 3; k++) { nw[k] = nw[k] / nd; d.nw[i3 + k] = nw[k]; }
+    if (fixed == 0) {
+      if (solid == 0) {
+        if (phi > 0.5) {   // BVF wall reflection (fix_...transport_velocity.cpp:310-342)
+          double xr[3], vr[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++) { vr[k] = v[k]; xr[k] = (INI ? x[k] : d.x[i3 + k]) - dtv * vr[k]; }
+          const double norm = sqrt(nw[0] * nw[0] + nw[1] * nw[1] + nw[2] * nw[2]);
+          const double en[3] = {-nw[0] / norm, -nw[1] / norm, -nw[2] / norm};
+          const double vdot = vr[0] * en[0] + vr[1] * en[1] + vr[2] * en[2];
+          const double mx = vdot > 0.0 ? vdot : 0.0;   // std::max(0.0, v_dot_en)
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            vr[k] = -vr[k] + 2.0 * mx * en[k];
+            x[k] = xr[k] + dtv * vr[k];
+            if (!INI) d.x[i3 + k] = x[k];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          if (VARIANT == SPHBVF_TV) v[k] = vest[k] + dtfm * f[k];
+          else v[k] = vest[k] + dtfm * f[k] * damp + 0.001 * ddx[k] / nd;
+        }
+        if (VARIANT == SPHBVF_TV) rho = filter ? shep + dtf * drho : rhoI + dtf * drho;
+        else rho = filter ? shep + dtf * drho : rhoI + dtv * drho;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          double vn = v[k];
+          if (VARIANT == SPHBVF_TV) vn += dtfm * f[k];
+          else { vn += dtfm * f[k] + 0.001 * ddx[k] / nd; vn *= dampSolid; }
+          v[k] = vn;
+        }
+        const double cdev = VARIANT == SPHBVF_TV ? 0.5 * dtv : dtf;
+        if (devs) for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] += cdev * d.ddev[9 * (size_t)i + k];
+        if (VARIANT == SPHBVF_TV) rho = filter ? shep + dtf * drho : rhoI + dtf * drho;
+        else rho = rhoI + dtv * drho;
       }
     } else {
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        double vest, vn = v[k];
-        if (VARIANT == SPHBVF_TV) vest = vn + 2.0 * dtfm * f[k];
-        else vest = vn + 2.0 * dtfm * f[k] + 0.001 * ddx[k] / ndi;
-        vn += dtfm * f[k];
-        if (VARIANT != SPHBVF_TV) { vest *= dampSolid; vn *= dampSolid; }
-        d.vest[i3 + k] = vest;
-        d.v[i3 + k] = vn;
-        d.x[i3 + k] = x[k] + dtf * vn;     // sic: dtf (fix_...transport_velocity.cpp:183-185)
+      if (solid == 0) {
+        rho = filter ? shep + dtv * drho : rhoI + dtv * drho;
+      } else {
+        if (devs) for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] += dtf * d.ddev[9 * (size_t)i + k];
+        rho = filter ? shep : rhoI;
       }
-      const double cdev = VARIANT == SPHBVF_TV ? 0.5 * dtv : dtf;
-      for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] += cdev * d.ddev[9 * (size_t)i + k];
     }
-    d.rhoI[i] = rho;
-    d.rho[i] = rho + dtf * drho;
-  } else {
-    if (solid == 0) {
-      d.rhoI[i] = rho;
-      d.rho[i] = rho + dtf * drho;
+    for (int k = 0; k < co.nspecies; k++) {
+      const size_t q = (size_t)i * co.nspecies + k;
+      const double c = d.C[q] + d.Q[q] * dtf;
+      d.C[q] = c > 0 ? c : 0.0;
+    }
+    if (!INI) {
+      if (fixed == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) d.v[i3 + k] = v[k];
+      }
+      d.rho[i] = rho;
+    }
+  }
+
+  // ---------------------------------------------------------------- initial_integrate(step_init)
+  if (INI && ingroup) {
+    const double dtv = a.dt_init, dtf = 0.5 * dtv;
+    const double dtfm = dtf / co.mass[type];
+    double damp, dampSolid;
+    damp_factors(VARIANT, a.step_init, damp, dampSolid);
+    const double ndi = VARIANT != SPHBVF_TV ? nd : 1.0;
+    if (fixed == 0) {
+      if (solid == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          double ve;
+          if (VARIANT == SPHBVF_TV) ve = v[k] + dtfm * f[k];
+          else ve = v[k] + dtfm * f[k] * damp + 0.001 * ddx[k] / ndi;
+          const double vn = ve - dtfm * ddv[k];
+          vest[k] = ve;
+          v[k] = vn;
+          x[k] = x[k] + dtv * vn;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          double ve, vn = v[k];
+          if (VARIANT == SPHBVF_TV) ve = vn + 2.0 * dtfm * f[k];
+          else ve = vn + 2.0 * dtfm * f[k] + 0.001 * ddx[k] / ndi;
+          vn += dtfm * f[k];
+          if (VARIANT != SPHBVF_TV) { ve *= dampSolid; vn *= dampSolid; }
+          vest[k] = ve;
+          v[k] = vn;
+          x[k] = x[k] + dtf * vn;     // sic: dtf (fix_...transport_velocity.cpp:183-185)
+        }
+        const double cdev = VARIANT == SPHBVF_TV ? 0.5 * dtv : dtf;
+        if (devs) for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] += cdev * d.ddev[9 * (size_t)i + k];
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) { d.vest[i3 + k] = vest[k]; d.v[i3 + k] = v[k]; d.x[i3 + k] = x[k]; }
+      rhoI = rho;
+      rho = rho + dtf * drho;
+      d.rhoI[i] = rhoI;
+      d.rho[i] = rho;
     } else {
-      for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] += dtf * d.ddev[9 * (size_t)i + k];
-      d.rhoI[i] = rho;
+      // a fixed atom keeps x, v and vest; final_integrate only changed its rho
+      if (solid == 0) {
+        rhoI = rho;
+        rho = rho + dtf * drho;
+        d.rhoI[i] = rhoI;
+        d.rho[i] = rho;
+      } else {
+        if (devs) for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] += dtf * d.ddev[9 * (size_t)i + k];
+        rhoI = rho;
+        d.rhoI[i] = rhoI;
+        if (FIN) d.rho[i] = rho;
+      }
+    }
+    for (int k = 0; k < co.nspecies; k++) {
+      const size_t q = (size_t)i * co.nspecies + k;
+      const double c = d.C[q] + d.Q[q] * dtf;
+      d.C[q] = c > 0 ? c : 0.0;
     }
   }
-  for (int k = 0; k < co.nspecies; k++) {
-    const size_t q = (size_t)i * co.nspecies + k;
-    const double c = d.C[q] + d.Q[q] * dtf;
-    d.C[q] = c > 0 ? c : 0.0;
-  }
+  if (MODE == 2 && a.do_pack) pack_atom(d, co, i, type, solid, fixed, x, v, vest, rho, rhoI, e_i, a.with_dev);
+}
+
+template <int MODE>
+static void launch_integrate(const DevState &d, const Coeffs &co, const IntegArgs &a, cudaStream_t st) {
+  if (!d.nlocal) return;
+  const int b = nblocks(d.nlocal, 256);
+  if (co.variant == SPHBVF_TV) integrate_kernel<SPHBVF_TV, MODE><<<b, 256, 0, st>>>(d, co, a);
+  else if (co.variant == SPHBVF_MECHANICS) integrate_kernel<SPHBVF_MECHANICS, MODE><<<b, 256, 0, st>>>(d, co, a);
+  else integrate_kernel<SPHBVF_FSI, MODE><<<b, 256, 0, st>>>(d, co, a);
 }
 
 void launch_initial_integrate(const DevState &d, const Coeffs &co, double dt, long ntimestep, int groupbit,
-                              cudaStream_t st) {
-  if (!d.nlocal) return;
-  const int b = nblocks(d.nlocal, 256);
-  if (co.variant == SPHBVF_TV) initial_integrate_kernel<SPHBVF_TV><<<b, 256, 0, st>>>(d, co, dt, ntimestep, groupbit);
-  else if (co.variant == SPHBVF_MECHANICS) initial_integrate_kernel<SPHBVF_MECHANICS><<<b, 256, 0, st>>>(d, co, dt, ntimestep, groupbit);
-  else initial_integrate_kernel<SPHBVF_FSI><<<b, 256, 0, st>>>(d, co, dt, ntimestep, groupbit);
-}
-
-template <int VARIANT>
-__global__ void __launch_bounds__(256)
-final_integrate_kernel(const DevState d, const __grid_constant__ Coeffs co, const double dtv, const long ntimestep,
-                       const int groupbit) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.nlocal) return;
-  const size_t i3 = 3 * (size_t)i;
-  // freqFilter 20 (TV :287, mechanics :311); fsi: 1e16 -> INT_MAX, never fires (..._fsi.cpp:304)
-  const bool filter = VARIANT == SPHBVF_FSI ? (ntimestep % 2147483647L) == 0 : (ntimestep % 20) == 0;
-  const int mask = d.mask[i], type = d.type[i], solid = d.solid[i], fixed = d.fixed[i];
-  const double nd = d.nd[i], phi0 = d.phi[i], drho = d.drho[i], rhoI = d.rhoI[i];
-  double nw[3], v[3], vest[3], f[3], ddx[3] = {0, 0, 0};
-#pragma unroll
-  for (int k = 0; k < 3; k++) { nw[k] = d.nw[i3 + k]; v[k] = d.v[i3 + k]; vest[k] = d.vest[i3 + k]; f[k] = d.f[i3 + k]; }
-  if (VARIANT != SPHBVF_TV) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) ddx[k] = d.ddx[i3 + k];
-  }
-  double shep = 0.0;
-  if (filter) shep = d.rhoAux1[i] / d.rhoAux2[i];
-  if (!(mask & groupbit)) return;
-  const double dtf = 0.5 * dtv;
-  const double dtfm = dtf / co.mass[type];
-  double damp, dampSolid;
-  damp_factors(VARIANT, ntimestep, damp, dampSolid);
-  const double phi = phi0 / nd;
-  d.phi[i] = phi;
-#pragma unroll
-  for (int k = 0; k < 3; k++) { nw[k] = nw[k] / nd; d.nw[i3 + k] = nw[k]; }
-  double rho;
-  if (fixed == 0) {
-    if (solid == 0) {
-      if (phi > 0.5) {   // BVF wall reflection (fix_...transport_velocity.cpp:310-342)
-        double x[3], vr[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) { vr[k] = v[k]; x[k] = d.x[i3 + k] - dtv * vr[k]; }
-        const double norm = sqrt(nw[0] * nw[0] + nw[1] * nw[1] + nw[2] * nw[2]);
-        const double en[3] = {-nw[0] / norm, -nw[1] / norm, -nw[2] / norm};
-        const double vdot = vr[0] * en[0] + vr[1] * en[1] + vr[2] * en[2];
-        const double mx = vdot > 0.0 ? vdot : 0.0;   // std::max(0.0, v_dot_en)
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          vr[k] = -vr[k] + 2.0 * mx * en[k];
-          d.x[i3 + k] = x[k] + dtv * vr[k];
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        if (VARIANT == SPHBVF_TV) d.v[i3 + k] = vest[k] + dtfm * f[k];
-        else d.v[i3 + k] = vest[k] + dtfm * f[k] * damp + 0.001 * ddx[k] / nd;
-      }
-      if (VARIANT == SPHBVF_TV) rho = filter ? shep + dtf * drho : rhoI + dtf * drho;
-      else rho = filter ? shep + dtf * drho : rhoI + dtv * drho;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        double vn = v[k];
-        if (VARIANT == SPHBVF_TV) vn += dtfm * f[k];
-        else { vn += dtfm * f[k] + 0.001 * ddx[k] / nd; vn *= dampSolid; }
-        d.v[i3 + k] = vn;
-      }
-      const double cdev = VARIANT == SPHBVF_TV ? 0.5 * dtv : dtf;
-      for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] += cdev * d.ddev[9 * (size_t)i + k];
-      if (VARIANT == SPHBVF_TV) rho = filter ? shep + dtf * drho : rhoI + dtf * drho;
-      else rho = rhoI + dtv * drho;
-    }
-  } else {
-    if (solid == 0) {
-      rho = filter ? shep + dtv * drho : rhoI + dtv * drho;
-    } else {
-      for (int k = 0; k < 9; k++) d.dev[9 * (size_t)i + k] += dtf * d.ddev[9 * (size_t)i + k];
-      rho = filter ? shep : rhoI;
-    }
-  }
-  d.rho[i] = rho;
-  for (int k = 0; k < co.nspecies; k++) {
-    const size_t q = (size_t)i * co.nspecies + k;
-    const double c = d.C[q] + d.Q[q] * dtf;
-    d.C[q] = c > 0 ? c : 0.0;
-  }
+                              int with_dev, cudaStream_t st) {
+  IntegArgs a = {0.0, dt, 0, ntimestep, groupbit, 0, with_dev};
+  launch_integrate<0>(d, co, a, st);
 }
 
 void launch_final_integrate(const DevState &d, const Coeffs &co, double dt, long ntimestep, int groupbit,
-                            cudaStream_t st) {
-  if (!d.nlocal) return;
-  const int b = nblocks(d.nlocal, 256);
-  if (co.variant == SPHBVF_TV) final_integrate_kernel<SPHBVF_TV><<<b, 256, 0, st>>>(d, co, dt, ntimestep, groupbit);
-  else if (co.variant == SPHBVF_MECHANICS) final_integrate_kernel<SPHBVF_MECHANICS><<<b, 256, 0, st>>>(d, co, dt, ntimestep, groupbit);
-  else final_integrate_kernel<SPHBVF_FSI><<<b, 256, 0, st>>>(d, co, dt, ntimestep, groupbit);
+                            int with_dev, cudaStream_t st) {
+  IntegArgs a = {dt, 0.0, ntimestep, 0, groupbit, 0, with_dev};
+  launch_integrate<1>(d, co, a, st);
+}
+
+void launch_final_initial(const DevState &d, const Coeffs &co, double dt_final, long step_final, double dt_init,
+                          long step_init, int groupbit, int do_pack, int with_dev, cudaStream_t st) {
+  IntegArgs a = {dt_final, dt_init, step_final, step_init, groupbit, do_pack, with_dev};
+  launch_integrate<2>(d, co, a, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -279,57 +364,37 @@ void launch_max_vsq(const DevState &d, int groupbit, unsigned long long *out, cu
 }
 
 // hook: 0 post_integrate, 1 post_force, 2 end_of_step
-void launch_fix(const DevState &d, const Coeffs &co, const FixDesc &fx, int hook, long ntimestep, cudaStream_t st) {
-  if (!d.nlocal) return;
-  bool run = false;
+bool fix_runs(const FixDesc &fx, int hook, long ntimestep) {
   switch (fx.kind) {
     case FIX_BUOYANCY:
     case FIX_CHEMRXN:
-    case FIX_SETFORCE: run = hook == 1; break;
-    case FIX_FORCING: run = hook == 0 && ntimestep > fx.step; break;
+    case FIX_SETFORCE: return hook == 1;
+    case FIX_FORCING: return hook == 0 && ntimestep > fx.step;
     case FIX_BUFFER:
-      if (fx.ia[0] == 2) run = hook == 2 && ntimestep > fx.step;
-      else run = hook == 0 && ntimestep > fx.step;
-      break;
+      if (fx.ia[0] == 2) return hook == 2 && ntimestep > fx.step;
+      return hook == 0 && ntimestep > fx.step;
   }
-  if (run) fix_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, co, fx, hook);
+  return false;
+}
+
+void launch_fix(const DevState &d, const Coeffs &co, const FixDesc &fx, int hook, long ntimestep, cudaStream_t st) {
+  if (!d.nlocal) return;
+  if (fix_runs(fx, hook, ntimestep)) fix_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, co, fx, hook);
 }
 
 // ------------------------------------------------------------------------------------------
-// pack: primary state -> pair input records.  Holds every per-particle division of the pair
-// pass: V = m/rho, P/rho^2 with P = 7 B (rho/rho0 - 1) (pair_...transport_velocity.cpp:298-299),
-// and the scalar artificial stress of a stress-free solid (:454-461 with dev = 0).
+// pack kernel (steps where the fused integrator could not write the records: rebuilds, fixes in
+// post_integrate, host uploads)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pack_kernel(const DevState d, const __grid_constant__ Coeffs co, const int with_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.nlocal) return;
   const size_t i3 = 3 * (size_t)i;
-  const int t = d.type[i];
-  const double rho = d.rho[i];
-  const double vx = d.vest[i3], vy = d.vest[i3 + 1], vz = d.vest[i3 + 2];
-  const double irho = 1.0 / rho;
-  const double P = 7.0 * co.B[t] * (rho / co.rho0[t] - 1.0);
-  const double Prr = P * irho * irho;
-  Prec r;
-  r.A = make_rec4(d.x[i3], d.x[i3 + 1], d.x[i3 + 2], rho);
-  r.B = make_rec4(vx, vy, vz, co.mass[t] * irho);
-  r.C = make_rec4(vx - d.v[i3], vy - d.v[i3 + 1], vz - d.v[i3 + 2], Prr);
-  d.prec[i] = r;
-  const int solid = d.solid[i];
-  double art = 0.0;
-  if (solid) {
-    const double c_art = co.variant == SPHBVF_FSI ? 0.1 : 0.35;
-    const double Ps = co.variant == SPHBVF_MECHANICS ? fabs(P) : P;
-    const double ts = -Ps;
-    art = ts > 0.0 ? -c_art * ts * irho * irho : 0.0;
-  }
-  const double C0 = co.nspecies ? d.C[(size_t)i * co.nspecies] : 0.0;
-  d.pD[i] = make_rec4(d.rhoI[i], art, C0, d.e[i]);
-  d.pflags[i] = t | (solid << 4) | (d.fixed[i] << 5);
-  for (int k = 0; k < co.nspecies; k++) d.pCs[(size_t)i * co.nspecies + k] = d.C[(size_t)i * co.nspecies + k];
-  if (with_dev)
-    for (int k = 0; k < 9; k++) d.pdev[9 * (size_t)i + k] = d.dev[9 * (size_t)i + k];
+  const double x[3] = {d.x[i3], d.x[i3 + 1], d.x[i3 + 2]};
+  const double v[3] = {d.v[i3], d.v[i3 + 1], d.v[i3 + 2]};
+  const double vest[3] = {d.vest[i3], d.vest[i3 + 1], d.vest[i3 + 2]};
+  pack_atom(d, co, i, d.type[i], d.solid[i], d.fixed[i], x, v, vest, d.rho[i], d.rhoI[i], d.e[i], with_dev);
 }
 
 void launch_pack(const DevState &d, const Coeffs &co, int with_dev, cudaStream_t st) {

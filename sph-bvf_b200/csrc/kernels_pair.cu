@@ -116,9 +116,49 @@ __device__ __forceinline__ double fast_rcp(double x) {
 
 constexpr int RING = 16;  // list-entry prefetch depth (rows); power of two
 
-__device__ __forceinline__ void cp_async4(int *smem_dst, const int *gsrc) {
+// L2 residency (tuning switches):
+//   PAIR_L2HINT >= 1: the streams that are touched once per launch (list entries in, per-atom outputs out) are
+//                     marked evict-first so they do not push the gathered records out of L2;
+//   PAIR_L2HINT >= 2: the record gathers are marked evict-last on top of that;
+//   PAIR_PFL2 = D > 0: the records of the entries 2*D ahead of the register pipeline are prefetched into L2.
+#ifndef PAIR_L2HINT
+#define PAIR_L2HINT 0
+#endif
+#ifndef PAIR_PFL2
+#define PAIR_PFL2 0
+#endif
+
+__device__ __forceinline__ void cp_async4(int *smem_dst, const int *gsrc, unsigned long long pol) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+#if PAIR_L2HINT >= 1
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(sa), "l"(gsrc), "l"(pol) : "memory");
+#else
+  (void)pol;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+#endif
+}
+
+__device__ __forceinline__ Rec4 ld_rec(const Rec4 *p) {
+#if PAIR_L2HINT >= 2
+  Rec4 r;
+  asm("ld.global.L2::evict_last.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+#else
+  return *p;
+#endif
+}
+
+__device__ __forceinline__ void st_out(double *p, double v) {
+#if PAIR_L2HINT >= 1
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+
+__device__ __forceinline__ void prefetch_rec_l2(const Prec *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)p + 64));
 }
 
 // ---- counter-based randomness for the stochastic stress term: Philox-4x32-10 (Salmon et al. 2011)
@@ -450,34 +490,50 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   const int *np = d.neigh + i;
   const size_t stride = d.stride;
   int *myring = &ring[0][threadIdx.x];
+  unsigned long long pol = 0;
+#if PAIR_L2HINT >= 1
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
   auto fetch2 = [&](int k) {   // entries k, k+1 -> ring slots k % RING, (k+1) % RING; one group
-    if (k < nn) cp_async4(myring + (k % RING) * 128, np + (size_t)k * stride);
-    if (k + 1 < nn) cp_async4(myring + ((k + 1) % RING) * 128, np + (size_t)(k + 1) * stride);
+    if (k < nn) cp_async4(myring + (k % RING) * 128, np + (size_t)k * stride, pol);
+    if (k + 1 < nn) cp_async4(myring + ((k + 1) % RING) * 128, np + (size_t)(k + 1) * stride, pol);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  // groups allowed in flight after a wait: entries <= kk + 17 - 2 * PEND have landed
+  constexpr int PEND = RING / 2 - 2 - PAIR_PFL2;
+  static_assert(PEND >= 2, "prefetch distance too large for the ring");
 #pragma unroll
   for (int k = 0; k < RING; k += 2) fetch2(k);
-  asm volatile("cp.async.wait_group %0;" ::"n"(RING / 2 - 2) : "memory");   // entries 0..3 landed
+  asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries 0..3 (+ 2 PFL2) landed
   int e0 = nn > 0 ? myring[0] : 0;
   int e1 = nn > 1 ? myring[128] : 0;
+#if PAIR_PFL2 > 0
+#pragma unroll
+  for (int q = 2; q < 4 + 2 * PAIR_PFL2; q++)
+    if (q < nn) prefetch_rec_l2(d.prec + (myring[(q % RING) * 128] & NEIGH_JMASK));
+#endif
   Rec4 A0, B0, C0, A1, B1, C1;
   {
     const Prec *p = d.prec + (e0 & NEIGH_JMASK);
-    A0 = p->A; B0 = p->B; C0 = p->C;
+    A0 = ld_rec(&p->A); B0 = ld_rec(&p->B); C0 = ld_rec(&p->C);
   }
   for (int kk = 0; kk < nn; kk += 2) {
     {
       const Prec *p = d.prec + (e1 & NEIGH_JMASK);
-      A1 = p->A; B1 = p->B; C1 = p->C;
+      A1 = ld_rec(&p->A); B1 = ld_rec(&p->B); C1 = ld_rec(&p->C);
     }
     fetch2(kk + RING);   // slots of entries kk, kk+1: already in e0, e1
-    asm volatile("cp.async.wait_group %0;" ::"n"(RING / 2 - 2) : "memory");   // entries <= kk+5 landed
+    asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries <= kk+5 (+ 2 PFL2) landed
     const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * 128] : 0;
     const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * 128] : 0;
+#if PAIR_PFL2 > 0
+    if (kk + 4 + 2 * PAIR_PFL2 < nn) prefetch_rec_l2(d.prec + (myring[((kk + 4 + 2 * PAIR_PFL2) % RING) * 128] & NEIGH_JMASK));
+    if (kk + 5 + 2 * PAIR_PFL2 < nn) prefetch_rec_l2(d.prec + (myring[((kk + 5 + 2 * PAIR_PFL2) % RING) * 128] & NEIGH_JMASK));
+#endif
     visit(e0, A0, B0, C0);
     {
       const Prec *p = d.prec + (e2 & NEIGH_JMASK);
-      A0 = p->A; B0 = p->B; C0 = p->C;
+      A0 = ld_rec(&p->A); B0 = ld_rec(&p->B); C0 = ld_rec(&p->C);
     }
     if (kk + 1 < nn) visit(e1, A1, B1, C1);
     e0 = e2;
@@ -493,14 +549,14 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   }
   const double ddvc = 10.0 * 7.0 * co.B[ti];
   const size_t i3 = 3 * (size_t)i;
-  d.f[i3] = fma(spi, Bi.x, fx); d.f[i3 + 1] = fma(spi, Bi.y, fy); d.f[i3 + 2] = fma(spi, Bi.z, fz);
-  d.drho[i] = drho;
-  d.nd[i] = nd;
-  d.rhoAux1[i] = rA1;
-  d.rhoAux2[i] = rA2;
-  d.phi[i] = phi;
-  d.nw[i3] = nwx; d.nw[i3 + 1] = nwy; d.nw[i3 + 2] = nwz;
-  d.ddv[i3] = ddvc * ddvx; d.ddv[i3 + 1] = ddvc * ddvy; d.ddv[i3 + 2] = ddvc * ddvz;
+  st_out(d.f + i3, fma(spi, Bi.x, fx)); st_out(d.f + i3 + 1, fma(spi, Bi.y, fy)); st_out(d.f + i3 + 2, fma(spi, Bi.z, fz));
+  st_out(d.drho + i, drho);
+  st_out(d.nd + i, nd);
+  st_out(d.rhoAux1 + i, rA1);
+  st_out(d.rhoAux2 + i, rA2);
+  st_out(d.phi + i, phi);
+  st_out(d.nw + i3, nwx); st_out(d.nw + i3 + 1, nwy); st_out(d.nw + i3 + 2, nwz);
+  st_out(d.ddv + i3, ddvc * ddvx); st_out(d.ddv + i3 + 1, ddvc * ddvy); st_out(d.ddv + i3 + 2, ddvc * ddvz);
   if (VARIANT != SPHBVF_TV) {
     d.ddx[i3] = ddxx; d.ddx[i3 + 1] = ddxy; d.ddx[i3 + 2] = ddxz;
     d.Pnew[i] = Pi;   // pair_ssa_tsdpd_bvf_mechanics.cpp:188

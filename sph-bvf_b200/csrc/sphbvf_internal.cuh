@@ -125,7 +125,7 @@ struct DevState {
   int stride, maxneigh;
 };
 
-enum KernelFamily { K_PAIR = 0, K_INITIAL = 1, K_FINAL = 2, K_NEIGH = 3, K_PACK = 4, K_FIX = 5, K_NFAM = 6 };
+enum KernelFamily { K_PAIR = 0, K_INITIAL = 1, K_FINAL = 2, K_NEIGH = 3, K_PACK = 4, K_FIX = 5, K_FUSED = 6, K_NFAM = 7 };
 
 }  // namespace sphbvf
 
@@ -135,12 +135,16 @@ namespace sphbvf {
 // kernels_integrate.cu
 void launch_setup_pre_force(const DevState &d, int groupbit, cudaStream_t st);
 void launch_initial_integrate(const DevState &d, const Coeffs &co, double dt, long ntimestep,
-                              int groupbit, cudaStream_t st);
+                              int groupbit, int with_dev, cudaStream_t st);
 void launch_final_integrate(const DevState &d, const Coeffs &co, double dt, long ntimestep,
-                            int groupbit, cudaStream_t st);
+                            int groupbit, int with_dev, cudaStream_t st);
+// final_integrate(step_final) + initial_integrate(step_init) [+ pack] in one pass (bit-identical to the two calls)
+void launch_final_initial(const DevState &d, const Coeffs &co, double dt_final, long step_final, double dt_init,
+                          long step_init, int groupbit, int do_pack, int with_dev, cudaStream_t st);
 void launch_max_vsq(const DevState &d, int groupbit, unsigned long long *out, cudaStream_t st);
 void launch_fix(const DevState &d, const Coeffs &co, const FixDesc &fx, int hook, long ntimestep,
                 cudaStream_t st);   // hook: 0 post_integrate, 1 post_force, 2 end_of_step
+bool fix_runs(const FixDesc &fx, int hook, long ntimestep);   // would launch_fix launch anything?
 // pack owned atoms into pA..pD (+pCs, pdev) and refresh self-image ghosts from their owners
 void launch_pack(const DevState &d, const Coeffs &co, int with_dev, cudaStream_t st);
 void launch_ghost_refresh(const DevState &d, const Coeffs &co, int with_dev, cudaStream_t st);
