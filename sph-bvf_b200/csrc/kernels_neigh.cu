@@ -274,19 +274,203 @@ void launch_bin_ghosts(const DevState &d, const Grid &g, const NeighWork &w, cud
 }
 
 // ---------------------------------------------------------------- Verlet list
-// One thread per owned atom.  For every (dz, dy) row of the stencil the cells cx-s .. cx+s are
-// visited as at most two contiguous index ranges (cells are x-contiguous inside a tile), so the
-// cell_start table is read twice per segment instead of twice per cell.  Ghosts live in their own
-// cell table and only cells of the ghost shell are looked up there.
-// Entry order: the pair kernel gathers three 32-byte records per entry, and the 32 lanes of a
-// warp do so for 32 different atoms j at once.  A record sits at offset 32*(j mod 4) of its
-// 128-byte line, and the L1 data stage serialises lanes that hit the same 32-byte slice of
-// different lines.  The entries of each atom are therefore emitted so that entry k of lane l has
-// (j mod 4) == (l + k) mod 4 whenever the atom still has such a neighbour: every gather then
-// spreads its lanes evenly over the four slices (ncu: l1tex data-pipe wavefronts, profiles/).
-constexpr int LIST_CAP = 192;   // entries per atom ordered this way; any beyond keep traversal order
+// Two builders produce the same list (same entries, same order inside each atom's row is not required:
+// the pair SET is what is compared bit-exactly, and both orders are deterministic):
+//
+// (A) build_list_tile_kernel (default): one CTA per tile of the cell grid (4x4x4 cells in 3D, 8x8 in 2D: a
+//     contiguous range of ~145 atoms).  The candidates of the whole tile -- the atoms of the cells within the
+//     stencil reach of the tile, at most 8x8x8 cells, i.e. <= 3 contiguous index ranges per (y,z) row -- are
+//     staged ONCE in shared memory as {x, y, z, packed list entry} (32 B).  Every thread (one atom) then sweeps
+//     the staged candidates in lock step: no divergence, every shared-memory read is a broadcast, and the test
+//     is the reference's exact FP64 criterion (rsq evaluated without FMA in the reference's operation order);
+//     a warp only sweeps the z-layers of cells its own atoms can reach.  FP64-pipe bound (8 FP64 operations
+//     per candidate, ~800 candidates per atom) instead of divergence bound: the thread-per-atom walk (B) spent
+//     26 k warp instructions per 32 atoms at 12.6 of 32 active lanes (ncu, profiles/) in tiny per-cell loops
+//     whose trip counts differ in every lane.
+// (B) build_list_kernel (SPHBVF_LIST_BUILD=thread): one thread per owned atom walks its own stencil; for every
+//     (dz, dy) row the cells cx-s .. cx+s are visited as at most two contiguous index ranges, pruned by the
+//     atom's position.  Kept as the cross-check of (A) (tests/test_gpu_parity.py) and for A/B timing.
+// Ghosts live in their own cell table (gcell_start / gorder).
 
-template <bool UNIFORM, bool BALANCE>
+constexpr int TB_T = 224;                     // threads per CTA: a bulk 3D tile holds 125..216 atoms (one batch)
+constexpr int TB_CH = 1536;                   // staged candidates per chunk (48 KB, dynamic): a bulk halo is <= 11^3
+constexpr int TB_NH = 1;                      // 2: stage the halo as two y-halves (24 KB chunks, 8 CTAs/SM): measured slower
+constexpr int TB_MAXROW = 64;                 // (y,z) rows of the halo: 8 x 8 in 3D, 12 x 1 in 2D
+constexpr int TB_MAXSEG = TB_MAXROW * 3 * 2;  // x-parts per row (<= 3 tiles) x {owned, ghost}
+constexpr int TB_MAXLAY = 12;                 // z-layers of the halo (8 in 3D, 1 in 2D)
+
+struct __align__(16) Cand {   // two LDS.128 broadcasts per candidate: {x, y} and {z, entry}
+  double2 xy;
+  double2 ze;
+};
+
+// TB_NH == 2 stages the halo in two halves (low-y rows, then high-y rows): every warp has work in both halves (a
+// warp's atoms span the tile in y) and inside a half the rows stay z-major, so the z-layers a warp can reach are
+// still one contiguous range.  With TB_NH == 1 the second half is empty.
+template <bool UNIFORM>
+__global__ void __launch_bounds__(TB_T)
+build_list_tile_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_constant__ Coeffs co,
+                       const int *__restrict__ cell_start, const int *__restrict__ gcell_start,
+                       const int *__restrict__ gorder, const double cutmaxsq, int *flags) {
+  extern __shared__ __align__(16) unsigned char tb_smem[];
+  Cand *cand = reinterpret_cast<Cand *>(tb_smem);
+  __shared__ int seg_src[TB_MAXSEG];
+  __shared__ int seg_off[TB_MAXSEG + 1];
+  __shared__ int layer_off[2][TB_MAXLAY + 1];
+
+  const int tid = threadIdx.x;
+  const int bits = g.tb[0] + g.tb[1] + g.tb[2];
+  const int tile = blockIdx.x;
+  const int first = cell_start[(long)tile << bits], last = cell_start[((long)tile + 1) << bits];
+  if (first == last) return;   // empty tile (whole CTA)
+  const int tx = tile % g.nt[0], ty = (tile / g.nt[0]) % g.nt[1], tz = tile / (g.nt[0] * g.nt[1]);
+  const int x0 = tx << g.tb[0], y0 = ty << g.tb[1], z0 = tz << g.tb[2];
+  const int hx0 = max(x0 - g.s[0], 0), hx1 = min(x0 + (1 << g.tb[0]) - 1 + g.s[0], g.n[0] - 1);
+  const int hy0 = max(y0 - g.s[1], 0), hy1 = min(y0 + (1 << g.tb[1]) - 1 + g.s[1], g.n[1] - 1);
+  const int hz0 = max(z0 - g.s[2], 0), hz1 = min(z0 + (1 << g.tb[2]) - 1 + g.s[2], g.n[2] - 1);
+  const int ny = hy1 - hy0 + 1, nz = hz1 - hz0 + 1;
+  const int nya = TB_NH == 2 ? (ny + 1) >> 1 : ny;   // rows of the first half; the second has ny - nya
+  const int nseg_a = nz * nya * 6, nseg = nz * ny * 6;
+  const int tmask = (1 << g.tb[0]) - 1;
+  const bool have_ghosts = d.nghost > 0;
+
+  // ---- segment table: (half, z, y, x-part, owned|ghost) -> contiguous source range
+  for (int sid = tid; sid < nseg; sid += TB_T) {
+    const int half = sid >= nseg_a;
+    const int rs = half ? sid - nseg_a : sid, nyh = half ? ny - nya : nya;
+    const int pass = rs & 1, part = (rs >> 1) % 3, row = rs / 6;
+    const int y = hy0 + (half ? nya : 0) + row % nyh, z = hz0 + row / nyh;
+    int x = hx0, xe = min(hx1, x | tmask);
+    for (int q = 0; q < part && x <= hx1; q++) { x = xe + 1; xe = min(hx1, x | tmask); }
+    int a = 0, len = 0;
+    if (x <= hx1 && (pass == 0 || have_ghosts)) {
+      const int *start = pass ? gcell_start : cell_start;
+      const int c0 = cell_index(g, x, y, z), c1 = c0 + (xe - x);
+      a = start[c0];
+      len = start[c1 + 1] - a;
+    }
+    seg_src[sid] = a | (pass << 31);
+    seg_off[sid] = len;
+  }
+  __syncthreads();
+  if (tid < 32) {   // exclusive scan of <= 384 lengths: 12 per lane
+    constexpr int PER = TB_MAXSEG / 32;
+    int v[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const int sid = tid * PER + k;
+      v[k] = sid < nseg ? seg_off[sid] : 0;
+      sum += v[k];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += y;
+    }
+    int run = incl - sum;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const int sid = tid * PER + k;
+      if (sid <= nseg) seg_off[sid] = run;
+      run += v[k];
+    }
+    if (tid == 31) seg_off[nseg] = run;   // nseg == TB_MAXSEG: no lane owns that slot
+  }
+  __syncthreads();
+  if (tid <= nz) {
+    layer_off[0][tid] = seg_off[tid * nya * 6];
+    layer_off[1][tid] = seg_off[nseg_a + tid * (ny - nya) * 6];
+  }
+  __syncthreads();
+  const size_t stride = d.stride;
+#ifdef TB_DIAG_NOSTORE
+  const bool nostore = flags[7] != 0;
+#endif
+
+  for (int base = first; base < last; base += TB_T) {
+    const int i = base + tid;
+    const bool valid = i < last;
+    Rec4 Ai = make_rec4(0, 0, 0, 0);
+    int ti = 1;
+    if (valid) { Ai = d.prec[i].A; ti = d.pflags[i] & 7; }
+    double cut_i[MAXT];
+#pragma unroll
+    for (int t = 0; t < MAXT; t++) cut_i[t] = UNIFORM ? cutmaxsq : co.cutneighsq[ti][t];
+    // halo z-layers this WARP can reach
+    int llo = TB_MAXLAY, lhi = -1;
+    if (valid) {
+      int cz = g.dim == 2 ? 0 : (int)floor((Ai.z - g.lo[2]) * g.inv[2]);
+      cz = min(max(cz, hz0), hz1);
+      llo = max(cz - g.s[2], hz0) - hz0;
+      lhi = min(cz + g.s[2], hz1) - hz0;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      llo = min(llo, __shfl_xor_sync(0xffffffffu, llo, o));
+      lhi = max(lhi, __shfl_xor_sync(0xffffffffu, lhi, o));
+    }
+    int n = 0;
+    int *out = d.neigh + (valid ? i : first);
+    const int maxn = valid ? d.maxneigh : 0;
+
+    for (int half = 0; half < 2; half++) {
+      const int h0 = half ? seg_off[nseg_a] : 0, h1 = half ? seg_off[nseg] : seg_off[nseg_a];
+      const int wq0 = lhi >= 0 ? layer_off[half][llo] : 0, wq1 = lhi >= 0 ? layer_off[half][lhi + 1] : 0;
+      for (int clo = h0; clo < h1; clo += TB_CH) {
+        const int chi = min(h1, clo + TB_CH);
+        // ---- stage candidates clo .. chi
+        for (int q = clo + tid; q < chi; q += TB_T) {
+          int lo = 0, hi = nseg;   // largest sid with seg_off[sid] <= q
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (seg_off[mid] <= q) lo = mid; else hi = mid;
+          }
+          const int src = seg_src[lo];
+          const int p = (src & 0x7fffffff) + (q - seg_off[lo]);
+          const int j = src < 0 ? d.nlocal + gorder[p] : p;
+          const Rec4 A = d.prec[j].A;
+          const int fj = d.pflags[j];
+          Cand c;
+          c.xy = make_double2(A.x, A.y);
+          c.ze = make_double2(A.z, __hiloint2double(0, j | ((fj & 7) << NEIGH_JBITS) | (((fj >> 4) & 1) << 30)));
+          cand[q - clo] = c;
+        }
+        __syncthreads();
+        // ---- converged sweep with the exact criterion
+        const int qa = max(wq0, clo) - clo, qb = min(wq1, chi) - clo;
+#pragma unroll 4
+        for (int q = qa; q < qb; q++) {
+          const double2 cxy = cand[q].xy, cze = cand[q].ze;
+          const int ent = __double2loint(cze.y);
+          const double rsq = rsq_nofma(Ai.x - cxy.x, Ai.y - cxy.y, Ai.z - cze.x);
+          double cut = cut_i[0];
+          if (!UNIFORM) {
+            const int tj = (ent >> NEIGH_JBITS) & 7;
+#pragma unroll
+            for (int t = 1; t < MAXT; t++) cut = tj == t ? cut_i[t] : cut;
+          }
+          if (rsq <= cut && (ent & NEIGH_JMASK) != i) {
+#ifdef TB_DIAG_NOSTORE   // tools/: measure what the scattered emission costs (the list keeps its previous content)
+            if (n < maxn && !nostore) out[(size_t)n * stride] = ent;
+#else
+            if (n < maxn) out[(size_t)n * stride] = ent;
+#endif
+            n++;
+          }
+        }
+        // the staging area is reused only if another chunk, half or batch of atoms follows (CTA-uniform)
+        if (chi < h1 || (half == 0 && seg_off[nseg] > seg_off[nseg_a]) || base + TB_T < last) __syncthreads();
+      }
+    }
+    if (valid) {
+      d.numneigh[i] = n < d.maxneigh ? n : d.maxneigh;
+      atomicMax(&flags[2], n);
+    }
+  }
+}
+
+template <bool UNIFORM>
 __global__ void __launch_bounds__(128, 6)
 build_list_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_constant__ Coeffs co,
                   const int *__restrict__ cell_start, const int *__restrict__ gcell_start,
@@ -304,13 +488,8 @@ build_list_kernel(const DevState d, const __grid_constant__ Grid g, const __grid
   const bool have_ghosts = d.nghost > 0;
   int n = 0;
   int *out = d.neigh + i;
-  int loc[LIST_CAP];
-  int cnt[4] = {0, 0, 0, 0};
   auto emit = [&](int ent) {
-    if (BALANCE && n < LIST_CAP) {
-      loc[n] = ent;
-      cnt[ent & 3]++;
-    } else if (n < d.maxneigh) out[(size_t)n * d.stride] = ent;
+    if (n < d.maxneigh) out[(size_t)n * d.stride] = ent;
     n++;
   };
   const int xlo = max(cx - g.s[0], 0), xhi = min(cx + g.s[0], g.n[0] - 1);
@@ -366,34 +545,6 @@ build_list_kernel(const DevState d, const __grid_constant__ Grid g, const __grid
   }
   d.numneigh[i] = n < d.maxneigh ? n : d.maxneigh;
   atomicMax(&flags[2], n);
-  if (!BALANCE) return;
-  // counting sort of the staged entries by (j mod 4), then slice-balanced emission
-  const int m = n < LIST_CAP ? n : LIST_CAP;
-  const int mo = m < d.maxneigh ? m : d.maxneigh;
-  int srt[LIST_CAP];
-  int off[4] = {0, cnt[0], cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]};
-  int end[4] = {off[1], off[2], off[3], m};
-  {
-    int cur[4] = {off[0], off[1], off[2], off[3]};
-    for (int k = 0; k < m; k++) {
-      const int e = loc[k], c = e & 3;
-      const int pos = c == 0 ? cur[0]++ : (c == 1 ? cur[1]++ : (c == 2 ? cur[2]++ : cur[3]++));
-      srt[pos] = e;
-    }
-  }
-  const int lane = threadIdx.x & 3;
-  for (int k = 0; k < mo; k++) {
-    int e = 0;
-    bool got = false;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int c = (lane + k + q) & 3;
-#pragma unroll
-      for (int cc = 0; cc < 4; cc++)
-        if (!got && c == cc && off[cc] < end[cc]) { e = srt[off[cc]++]; got = true; }
-    }
-    out[(size_t)k * d.stride] = e;
-  }
 }
 
 void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const NeighWork &w, cudaStream_t st) {
@@ -405,12 +556,30 @@ void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const
       if (co.cutneighsq[i][j] != co.cutneighsq[1][1]) uniform = false;
     }
   if (!d.nlocal) return;
-  static const int balance = [] { const char *e = getenv("SPHBVF_SLICE_ORDER"); return e ? atoi(e) : 0; }();
+  const char *env = getenv("SPHBVF_LIST_BUILD");   // read per rebuild so that tests can compare both builders
+  const bool per_thread = env && env[0] == 't';
+  // the tile builder needs the halo of a tile to fit its tables: stencil half-width <= 2 cells (always true for
+  // cells of cutneigh/2, init_neighbor) and <= 64 (y,z) rows
+  const int ny = (1 << g.tb[1]) + 2 * g.s[1], nz = g.dim == 3 ? (1 << g.tb[2]) + 2 * g.s[2] : 1;
+  if (!per_thread && ny * nz <= TB_MAXROW && nz <= TB_MAXLAY) {
+    const long ntiles = (long)g.nt[0] * g.nt[1] * g.nt[2];
+    constexpr int smem = TB_CH * (int)sizeof(Cand);
+#ifdef TB_DIAG_NOSTORE
+    { const char *e = getenv("SPHBVF_TB_NOSTORE"); const int v = e && atoi(e); cudaMemcpyAsync(w.flags + 7, &v, sizeof(int), cudaMemcpyHostToDevice, st); cudaStreamSynchronize(st); }
+#endif
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(build_list_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(build_list_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr_set = true;
+    }
+    if (uniform) build_list_tile_kernel<true><<<(int)ntiles, TB_T, smem, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
+    else build_list_tile_kernel<false><<<(int)ntiles, TB_T, smem, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
+    return;
+  }
   const int nb = nblocks(d.nlocal, 128);
-#define BL(U, B) build_list_kernel<U, B><<<nb, 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags)
-  if (uniform) { if (balance) BL(true, true); else BL(true, false); }
-  else { if (balance) BL(false, true); else BL(false, false); }
-#undef BL
+  if (uniform) build_list_kernel<true><<<nb, 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
+  else build_list_kernel<false><<<nb, 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
 }
 
 void launch_copy_xhold(const DevState &d, cudaStream_t st) {

@@ -255,7 +255,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     for (int k = 0; k < MAXS; k++) Qs[k] = 0.0;
 
   // ------------------------------------------------------------------ one neighbour
-  auto body = [&](const int ent, const Rec4 &Aj, const Rec4 &Bj, const Rec4 &Cj) {
+  auto body = [&](const int ent, const Rec4 &Aj, const Rec4 &Bj, const Rec4 &Cj, const double rhoIj) {
     const int j = ent & NEIGH_JMASK;
     const int tj = (ent >> NEIGH_JBITS) & 7;
     const bool sj = SOLIDS && ((ent >> 30) & 1);
@@ -289,7 +289,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     // ---- sweep A (pair_...transport_velocity.cpp:243-254); ddv is scaled by 70 B_i at the end
     nd = fma(Vj2, wf, nd);
     rA2 += wf;
-    if (FILTER) rA1 = fma(d.pD[j].x, wf, rA1);
+    if (FILTER) rA1 = fma(rhoIj, wf, rA1);
     ddvx = fma(S2w, delx, ddvx); ddvy = fma(S2w, dely, ddvy); ddvz = fma(S2w, delz, ddvz);
     if (VARIANT != SPHBVF_TV) {   // ..._mechanics.cpp:250-252
       const double Vj2w = Vj2 * wf;
@@ -468,14 +468,14 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   };
 
   double vir[6] = {0, 0, 0, 0, 0, 0};
-  auto visit = [&](const int ent, const Rec4 &Aj, const Rec4 &Bj, const Rec4 &Cj) {
-    if (!VIRIAL) { body(ent, Aj, Bj, Cj); return; }
+  auto visit = [&](const int ent, const Rec4 &Aj, const Rec4 &Bj, const Rec4 &Cj, const double rhoIj) {
+    if (!VIRIAL) { body(ent, Aj, Bj, Cj, rhoIj); return; }
     const int g = (ent & NEIGH_JMASK) - d.nlocal;
     if (g < 0) return;
     const double sx = d.gshift[3 * (size_t)g], sy = d.gshift[3 * (size_t)g + 1], sz = d.gshift[3 * (size_t)g + 2];
     if (sx == 0.0 && sy == 0.0 && sz == 0.0) return;
     const double f0x = fx + spi * Bi.x, f0y = fy + spi * Bi.y, f0z = fz + spi * Bi.z;
-    body(ent, Aj, Bj, Cj);
+    body(ent, Aj, Bj, Cj, rhoIj);
     const double Fx = (fx + spi * Bi.x) - f0x, Fy = (fy + spi * Bi.y) - f0y, Fz = (fz + spi * Bi.z) - f0z;
     vir[0] -= 0.5 * sx * Fx; vir[1] -= 0.5 * sy * Fy; vir[2] -= 0.5 * sz * Fz;
     vir[3] -= 0.5 * sx * Fy; vir[4] -= 0.5 * sx * Fz; vir[5] -= 0.5 * sy * Fz;
@@ -513,14 +513,17 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     if (q < nn) prefetch_rec_l2(d.prec + (myring[(q % RING) * 128] & NEIGH_JMASK));
 #endif
   Rec4 A0, B0, C0, A1, B1, C1;
+  double D0 = 0.0, D1 = 0.0;   // rhoI_j of the Shepard numerator, part of the pipeline on filter steps
   {
     const Prec *p = d.prec + (e0 & NEIGH_JMASK);
     A0 = ld_rec(&p->A); B0 = ld_rec(&p->B); C0 = ld_rec(&p->C);
+    if (FILTER) D0 = d.pD[e0 & NEIGH_JMASK].x;
   }
   for (int kk = 0; kk < nn; kk += 2) {
     {
       const Prec *p = d.prec + (e1 & NEIGH_JMASK);
       A1 = ld_rec(&p->A); B1 = ld_rec(&p->B); C1 = ld_rec(&p->C);
+      if (FILTER) D1 = d.pD[e1 & NEIGH_JMASK].x;
     }
     fetch2(kk + RING);   // slots of entries kk, kk+1: already in e0, e1
     asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries <= kk+5 (+ 2 PFL2) landed
@@ -530,12 +533,13 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     if (kk + 4 + 2 * PAIR_PFL2 < nn) prefetch_rec_l2(d.prec + (myring[((kk + 4 + 2 * PAIR_PFL2) % RING) * 128] & NEIGH_JMASK));
     if (kk + 5 + 2 * PAIR_PFL2 < nn) prefetch_rec_l2(d.prec + (myring[((kk + 5 + 2 * PAIR_PFL2) % RING) * 128] & NEIGH_JMASK));
 #endif
-    visit(e0, A0, B0, C0);
+    visit(e0, A0, B0, C0, D0);
     {
       const Prec *p = d.prec + (e2 & NEIGH_JMASK);
       A0 = ld_rec(&p->A); B0 = ld_rec(&p->B); C0 = ld_rec(&p->C);
+      if (FILTER) D0 = d.pD[e2 & NEIGH_JMASK].x;
     }
-    if (kk + 1 < nn) visit(e1, A1, B1, C1);
+    if (kk + 1 < nn) visit(e1, A1, B1, C1, D1);
     e0 = e2;
     e1 = e3;
   }
