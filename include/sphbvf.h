@@ -175,6 +175,10 @@ int sphbvf_ndanger(const sphbvf_ctx *ctx);    /* Neighbor::ndanger */
 /* max over the atoms of `groupbit` (all ranks) of |v|^2 with v the transport velocity (atom->v): the
  * reduction FixDtAdaptive::end_of_step does before its MPI_Allreduce (fix_dt_adaptive.cpp:118-148) */
 int sphbvf_max_vsq(sphbvf_ctx *ctx, int groupbit, double *max_vsq);
+/* sum over the owned atoms of `groupbit` of m v_a v_b (v = atom->v, m = mass[type]), order xx yy zz xy xz yz: the
+ * accumulation of ComputeTemp::compute_scalar / compute_vector (compute_temp.cpp:78-135) before its MPI_Allreduce
+ * and unit factors; this rank's share; summed in a fixed order (reproducible) */
+int sphbvf_ke_tensor(sphbvf_ctx *ctx, int groupbit, double *ke6);
 /* the neighbour structure as unordered (tag_i, tag_j) rows, each pair once -- what
  * `compute property/local patom1 patom2` dumps for the reference; out=NULL sizes */
 long sphbvf_get_pairs(sphbvf_ctx *ctx, int *out, long cap);

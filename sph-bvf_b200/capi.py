@@ -33,7 +33,7 @@ _lib = None
 SYMBOLS = ["sphbvf_version", "sphbvf_device_count", "sphbvf_create", "sphbvf_destroy", "sphbvf_last_error",
            "sphbvf_set_type", "sphbvf_set_pair", "sphbvf_set_dt", "sphbvf_set_random", "sphbvf_set_timestep", "sphbvf_set_run_length",
            "sphbvf_set_atoms", "sphbvf_upload", "sphbvf_download", "sphbvf_download_local", "sphbvf_upload_local", "sphbvf_add_buoyancy",
-           "sphbvf_add_forcing", "sphbvf_add_buffer", "sphbvf_add_setforce", "sphbvf_add_chem_rxn", "sphbvf_max_vsq", "sphbvf_setup", "sphbvf_run",
+           "sphbvf_add_forcing", "sphbvf_add_buffer", "sphbvf_add_setforce", "sphbvf_add_chem_rxn", "sphbvf_max_vsq", "sphbvf_ke_tensor", "sphbvf_setup", "sphbvf_run",
            "sphbvf_setup_neighbors",
            "sphbvf_initial_integrate", "sphbvf_post_integrate", "sphbvf_neighbor", "sphbvf_pair_compute",
            "sphbvf_virial", "sphbvf_post_force", "sphbvf_setup_post_force", "sphbvf_final_integrate", "sphbvf_end_of_step", "sphbvf_build_neighbors",
@@ -75,6 +75,7 @@ def lib():
     L.sphbvf_add_setforce.argtypes = [vp, ci, cd, cd, cd]
     L.sphbvf_add_chem_rxn.argtypes = [vp, ci, cd, ci, vp, ci, vp]
     L.sphbvf_max_vsq.argtypes = [vp, ci, C.POINTER(cd)]
+    L.sphbvf_ke_tensor.argtypes = [vp, ci, vp]
     for f in ("setup", "setup_neighbors", "setup_post_force", "initial_integrate", "post_integrate", "pair_compute", "post_force", "final_integrate",
               "end_of_step", "build_neighbors", "nlocal", "nghost", "nbuilds", "ndanger", "sync"):
         getattr(L, "sphbvf_" + f).argtypes = [vp]
@@ -191,6 +192,11 @@ class Engine:
     def virial(self):
         out = np.zeros(6)
         self._ck(lib().sphbvf_virial(self.h, _p(out)))
+        return out
+
+    def ke_tensor(self, groupbit=1):
+        out = np.zeros(6)
+        self._ck(lib().sphbvf_ke_tensor(self.h, groupbit, _p(out)))
         return out
 
     def step_pieces(self):

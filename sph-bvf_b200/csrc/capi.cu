@@ -87,6 +87,16 @@ void sphbvf_ctx::drain_events() {
   ev_list.clear();
 }
 
+// staging buffer shared by the permutation of the rebuild, uploads / downloads and reductions
+static int stage(sphbvf_ctx *ctx, size_t bytes) {
+  if (bytes > ctx->w.tmp_perm_bytes) {
+    if (ctx->w.tmp_perm) cudaFree(ctx->w.tmp_perm);
+    ctx->w.tmp_perm_bytes = bytes;
+    CK(cudaMalloc(&ctx->w.tmp_perm, bytes));
+  }
+  return 0;
+}
+
 // see context.cuh: a deferred final_integrate runs here unless sphbvf_initial_integrate absorbed it
 int flush_final(sphbvf_ctx *ctx) {
   if (!ctx->final_pending) return 0;
@@ -774,6 +784,22 @@ int sphbvf_max_vsq(sphbvf_ctx *ctx, int groupbit, double *max_vsq) {
   return 0;
 }
 
+int sphbvf_ke_tensor(sphbvf_ctx *ctx, int groupbit, double *ke6) {
+  if (!ctx->atoms_set) return ctx->fail(SPHBVF_ESTATE, "ke_tensor before set_atoms");
+  if (!ke6) return ctx->fail(SPHBVF_EINVAL, "ke_tensor: null output");
+  cudaSetDevice(ctx->cfg.device);
+  FLUSH();
+  if (!ctx->d_virial) CK(cudaMalloc((void **)&ctx->d_virial, sizeof(double) * 6));
+  int rc;
+  const size_t need = sizeof(double) * 6 * (size_t)(ctx->d.nlocal / 256 + 2);
+  if ((rc = stage(ctx, need))) return rc;
+  launch_ke_tensor(ctx->d, ctx->co, groupbit, (double *)ctx->w.tmp_perm, ctx->d_virial, ctx->st);
+  CKLAUNCH();
+  CK(cudaMemcpyAsync(ke6, ctx->d_virial, sizeof(double) * 6, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
 int sphbvf_final_integrate(sphbvf_ctx *ctx) {
   FLUSH();
   if (ctx->fuse) {   // deferred: see flush_final / sphbvf_initial_integrate
@@ -884,14 +910,6 @@ static bool field_info(sphbvf_ctx *ctx, int field, void **ptr, int *ncols, int *
   return true;
 }
 
-static int stage(sphbvf_ctx *ctx, size_t bytes) {
-  if (bytes > ctx->w.tmp_perm_bytes) {
-    if (ctx->w.tmp_perm) cudaFree(ctx->w.tmp_perm);
-    ctx->w.tmp_perm_bytes = bytes;
-    CK(cudaMalloc(&ctx->w.tmp_perm, bytes));
-  }
-  return 0;
-}
 
 int sphbvf_download(sphbvf_ctx *ctx, int field, void *host) {
   void *p;

@@ -363,6 +363,61 @@ void launch_max_vsq(const DevState &d, int groupbit, unsigned long long *out, cu
   if (d.nlocal) max_vsq_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, groupbit, out);
 }
 
+// sum over the atoms of `groupbit` of m v_a v_b (v = atom->v), LAMMPS order xx yy zz xy xz yz: what
+// ComputeTemp::compute_scalar / compute_vector accumulate on the host (compute_temp.cpp:78-135).  Two stages with
+// a fixed summation order (per-block partials, then one block) so that thermo output is reproducible.
+__global__ void __launch_bounds__(256)
+ke_partial_kernel(const DevState d, const __grid_constant__ Coeffs co, const int groupbit, double *partial) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double t[6] = {0, 0, 0, 0, 0, 0};
+  if (i < d.nlocal && (d.mask[i] & groupbit)) {
+    const size_t i3 = 3 * (size_t)i;
+    const double m = co.mass[d.type[i]], vx = d.v[i3], vy = d.v[i3 + 1], vz = d.v[i3 + 2];
+    t[0] = m * vx * vx; t[1] = m * vy * vy; t[2] = m * vz * vz;
+    t[3] = m * vx * vy; t[4] = m * vx * vz; t[5] = m * vy * vz;
+  }
+  __shared__ double sh[6][8];
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    double x = t[q];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double x = 0.0;
+    for (int w = 0; w < 8; w++) x += sh[threadIdx.x][w];
+    partial[6 * (size_t)blockIdx.x + threadIdx.x] = x;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ke_final_kernel(const double *partial, const int nblk, double *out6) {
+  __shared__ double sh[6][256];
+  double t[6] = {0, 0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < nblk; b += 256)
+#pragma unroll
+    for (int q = 0; q < 6; q++) t[q] += partial[6 * (size_t)b + q];
+#pragma unroll
+  for (int q = 0; q < 6; q++) sh[q][threadIdx.x] = t[q];
+  __syncthreads();
+  for (int s = 128; s; s >>= 1) {
+    if (threadIdx.x < s)
+#pragma unroll
+      for (int q = 0; q < 6; q++) sh[q][threadIdx.x] += sh[q][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) out6[threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// scratch: >= 6 * ceil(nlocal / 256) doubles
+void launch_ke_tensor(const DevState &d, const Coeffs &co, int groupbit, double *scratch, double *out6, cudaStream_t st) {
+  const int nb = nblocks(d.nlocal > 0 ? d.nlocal : 1, 256);
+  ke_partial_kernel<<<nb, 256, 0, st>>>(d, co, groupbit, scratch);
+  ke_final_kernel<<<1, 256, 0, st>>>(scratch, nb, out6);
+}
+
 // hook: 0 post_integrate, 1 post_force, 2 end_of_step
 bool fix_runs(const FixDesc &fx, int hook, long ntimestep) {
   switch (fx.kind) {

@@ -142,6 +142,7 @@ void launch_final_integrate(const DevState &d, const Coeffs &co, double dt, long
 void launch_final_initial(const DevState &d, const Coeffs &co, double dt_final, long step_final, double dt_init,
                           long step_init, int groupbit, int do_pack, int with_dev, cudaStream_t st);
 void launch_max_vsq(const DevState &d, int groupbit, unsigned long long *out, cudaStream_t st);
+void launch_ke_tensor(const DevState &d, const Coeffs &co, int groupbit, double *scratch, double *out6, cudaStream_t st);
 void launch_fix(const DevState &d, const Coeffs &co, const FixDesc &fx, int hook, long ntimestep,
                 cudaStream_t st);   // hook: 0 post_integrate, 1 post_force, 2 end_of_step
 bool fix_runs(const FixDesc &fx, int hook, long ntimestep);   // would launch_fix launch anything?

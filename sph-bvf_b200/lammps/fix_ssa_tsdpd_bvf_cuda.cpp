@@ -88,7 +88,7 @@ void FixSsaTsdpdBvfCuda::setup_pre_force(int)
 void FixSsaTsdpdBvfCuda::setup(int)
 {
   engine->check(sphbvf_setup_post_force(engine->ctx));
-  engine->to_host();   // thermo output of step 0 reads the host arrays
+  if (engine->output_needs_host(true)) engine->to_host();   // output of step 0 (Verlet::setup -> output->setup)
 }
 
 /* ---------------------------------------------------------------------- */
@@ -109,7 +109,7 @@ void FixSsaTsdpdBvfCuda::final_integrate() { engine->check(sphbvf_final_integrat
 void FixSsaTsdpdBvfCuda::end_of_step()
 {
   engine->check(sphbvf_end_of_step(engine->ctx));
-  if (update->ntimestep == output->next) engine->to_host();
+  if (update->ntimestep == output->next && engine->output_needs_host()) engine->to_host();
 }
 
 void FixSsaTsdpdBvfCuda::post_run() { engine->stop(); }

@@ -14,8 +14,13 @@
 #include "force.h"
 #include "lammps.h"
 #include "memory.h"
+#include "compute.h"
+#include "fix.h"
+#include "modify.h"
 #include "neighbor.h"
+#include "output.h"
 #include "pair.h"
+#include "thermo.h"
 #include "update.h"
 
 using namespace LAMMPS_NS;
@@ -27,6 +32,8 @@ SphbvfLmp *SphbvfLmp::get(LAMMPS *lmp)
   if (!the_engine) the_engine = new SphbvfLmp(lmp);
   return the_engine;
 }
+
+SphbvfLmp *SphbvfLmp::peek() { return the_engine; }
 
 void SphbvfLmp::release(LAMMPS *)
 {
@@ -46,6 +53,7 @@ SphbvfLmp::SphbvfLmp(LAMMPS *lmp) : Pointers(lmp)
   ctx = NULL;
   host_current = 1;
   nlocal_uploaded = 0;
+  ndownloads = ndevice_thermo = nskipped = 0;
 }
 
 SphbvfLmp::~SphbvfLmp()
@@ -191,11 +199,56 @@ void SphbvfLmp::to_host()
     }
   }
   host_current = 1;
+  ndownloads++;
+}
+
+/* ----------------------------------------------------------------------
+   Does anything that fires on this output step read the host per-atom arrays?  Conservative: the download is
+   skipped only when (a) no dump and no restart is due now, (b) thermo has one of the fixed keyword sets
+   (style one / multi: step temp epair emol etotal press ..., all fed by temp, pe and pressure computes;
+   `custom` may reference variables and arbitrary computes, which cannot be inspected from here), (c) every
+   compute LAMMPS knows is temp/cuda, pressure or pe, or a per-atom / local compute (only dumps, fixes and
+   variables invoke those), and (d) every fix is one of the /cuda fixes (none of them reads host arrays).
+   SPHBVF_OUTPUT=full restores the unconditional download.
+------------------------------------------------------------------------- */
+
+bool SphbvfLmp::output_needs_host(bool at_setup)
+{
+  static const int force_full = [] { const char *e = getenv("SPHBVF_OUTPUT"); return e && strcmp(e, "full") == 0; }();
+  if (force_full) return true;
+  const bigint now = update->ntimestep;
+  // Fix::setup runs before Output::setup has scheduled this run's dumps: any dump may fire at the first step
+  if (at_setup && (output->ndump || output->restart_flag)) return true;
+  if (output->ndump && output->next_dump_any == now) return true;
+  if (output->restart_flag && output->next_restart == now) return true;
+  if (!output->thermo) return true;
+  const char *ts = output->thermo->style;
+  if (strcmp(ts, "one") != 0 && strcmp(ts, "multi") != 0) return true;
+  for (int i = 0; i < modify->ncompute; i++) {
+    Compute *c = modify->compute[i];
+    if (c->peratom_flag || c->local_flag) continue;
+    if (strcmp(c->style, "temp/cuda") == 0 || strcmp(c->style, "pressure") == 0 || strcmp(c->style, "pe") == 0) continue;
+    return true;
+  }
+  for (int i = 0; i < modify->nfix; i++) {
+    const char *fs = modify->fix[i]->style;
+    const size_t n = strlen(fs);
+    if (n < 5 || strcmp(fs + n - 5, "/cuda") != 0) return true;
+  }
+  nskipped++;
+  return false;
 }
 
 void SphbvfLmp::stop()
 {
   if (!ctx) return;
+  if (getenv("SPHBVF_VERBOSE") && comm->me == 0) {
+    char msg[256];
+    snprintf(msg, sizeof msg, "sphbvf: " BIGINT_FORMAT " full downloads, " BIGINT_FORMAT " output steps served from the device, "
+             BIGINT_FORMAT " device kinetic-energy reductions\n", ndownloads, nskipped, ndevice_thermo);
+    if (screen) fputs(msg, screen);
+    if (logfile) fputs(msg, logfile);
+  }
   to_host();
   sphbvf_destroy(ctx);
   ctx = NULL;

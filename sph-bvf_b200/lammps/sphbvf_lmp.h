@@ -19,6 +19,7 @@ namespace LAMMPS_NS {
 class SphbvfLmp : protected Pointers {
  public:
   static SphbvfLmp *get(class LAMMPS *);   // created on first use, destroyed with the pair style
+  static SphbvfLmp *peek();                // the engine if one exists (computes must not create it)
   static void release(class LAMMPS *);
 
   SphbvfLmp(class LAMMPS *);
@@ -44,11 +45,17 @@ class SphbvfLmp : protected Pointers {
   void check(int rc);           // rc != 0 -> error->one(FLERR, sphbvf_last_error())
   void to_host();               // device -> class Atom arrays (all fields the package owns)
   void mark_dirty() { host_current = 0; }
+  bool host_is_current() const { return host_current != 0; }
+  // output step: true if nothing scheduled now can read the host per-atom arrays (thermo of style one / multi
+  // fed by compute temp/cuda + the device virial, no dump, no restart, only /cuda fixes) -> no download
+  bool output_needs_host(bool at_setup = false);
+  void count_device_thermo() { ndevice_thermo++; }
   sphbvf_ctx *ctx;
 
  private:
   int host_current;
   int nlocal_uploaded;
+  bigint ndownloads, ndevice_thermo, nskipped;   // statistics printed at the end of a run (SPHBVF_VERBOSE)
 };
 
 }

@@ -493,3 +493,44 @@ def test_heated_cavity_with_stochastic_term_as_shipped():
                 x, y = x[fluid], y[fluid]
             scale = max(np.abs(ref[q][1][:, k]).max() for q in ref)
             assert np.abs(x - y).max() <= 1e-5 * max(scale, 1e-300), (s, c)
+
+
+# ---------------------------------------------------------------------------------------------
+# output path: thermo-only steps are served from the device (compute temp/cuda =
+# sphbvf_ke_tensor, pressure from sphbvf_virial) without downloading the per-atom arrays; dump steps
+# still see current host data
+# ---------------------------------------------------------------------------------------------
+def test_thermo_only_steps_need_no_download(monkeypatch):
+    if not (os.path.exists(REF) and os.path.exists(CUDA)):
+        pytest.skip("lmp_serial / lmp_cuda not built (make -C oracle ref; make -C sph-bvf_b200/lammps)")
+    deck = CAVITY2D.replace("dump d all custom 7 ", "dump d all custom 21 ").replace("thermo 7", "thermo 3").replace("run 28", "run 42")
+    wd_ref, out_ref = run_deck(REF, deck, [])
+    monkeypatch.setenv("SPHBVF_VERBOSE", "1")
+    wd_lazy, out_lazy = run_deck(CUDA, deck, ["-sf", "cuda"])
+    monkeypatch.setenv("SPHBVF_OUTPUT", "full")
+    wd_full, out_full = run_deck(CUDA, deck, ["-sf", "cuda"])
+    stats = {}
+    for tag, out in (("lazy", out_lazy), ("full", out_full)):
+        ln = [l for l in out.splitlines() if l.startswith("sphbvf:")]
+        assert ln, out[-2000:]
+        w = ln[-1].split()
+        stats[tag] = (int(w[1]), int(w[4]), int(w[-4]))   # full downloads, output steps from the device, KE reductions
+    # 15 output steps (0, 3, ..., 42); dumps at 0, 21, 42; the final download of Fix::post_run is not counted here
+    assert stats["lazy"][1] >= 11 and stats["lazy"][0] <= 3, stats
+    assert stats["full"][1] == 0 and stats["full"][0] >= 14, stats
+    assert stats["lazy"][2] >= 11, stats
+    ta, tl, tf = read_thermo(out_ref), read_thermo(out_lazy), read_thermo(out_full)
+    assert ta.shape == tl.shape == tf.shape and ta.shape[0] == 15
+    scale = np.abs(ta[:, 1]).max()
+    assert np.abs(ta[:, 1] - tl[:, 1]).max() <= 2e-5 * scale, (ta[:, 1], tl[:, 1])
+    # device reduction vs host loop over the downloaded velocities: same numbers at print precision
+    assert np.abs(tf[:, 1:] - tl[:, 1:]).max() <= 2e-5 * np.abs(tf[:, 1:]).max()
+    ref, got = read_dumps(wd_ref), read_dumps(wd_lazy)
+    assert sorted(ref) == sorted(got) == [0, 21, 42]
+    for s in ref:
+        a, b = ref[s][1], got[s][1]
+        for k, c in enumerate(ref[s][0]):
+            if c in ("fx", "fy"):
+                continue
+            sc = max(np.abs(a[:, k]).max(), 1e-300)
+            assert np.abs(a[:, k] - b[:, k]).max() <= TOL * sc, (s, c)
