@@ -577,7 +577,16 @@ static void launch_filter(const DevState &d, const Coeffs &co, const PairTables 
                           cudaStream_t st) {
   const int threads = 128;
   const int blocks = (d.nlocal + threads - 1) / threads;
+#ifdef PAIR_DIAG_SMEM   // tools/: occupancy probe -- extra dynamic shared memory limits the resident CTAs per SM
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_DIAG_SMEM);
+    once = true;
+  }
+#define PK(F, R) pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, F, R><<<blocks, threads, ((F) || (R)) ? 0 : PAIR_DIAG_SMEM, st>>>(d, co, tb, pf.damp, pf.rand_pref, pf.seed, pf.ntimestep)
+#else
 #define PK(F, R) pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, F, R><<<blocks, threads, 0, st>>>(d, co, tb, pf.damp, pf.rand_pref, pf.seed, pf.ntimestep)
+#endif
   // the stochastic variant always carries the Shepard numerator (one instantiation less per case)
   if (pf.random) PK(true, true);
   else if (pf.filter_step) PK(true, false);
