@@ -512,8 +512,16 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   for (int q = 2; q < 4 + 2 * PAIR_PFL2; q++)
     if (q < nn) prefetch_rec_l2(d.prec + (myring[(q % RING) * 128] & NEIGH_JMASK));
 #endif
+  // Register pipeline: while the record of one neighbour is evaluated, the record of the next one is in flight.
+  // ptxas puts all six record loads of the loop on ONE scoreboard, and a scoreboard is a counter: the first use of a
+  // record waits until EVERY load issued before it has returned.  Issued in source order (next record's loads, then
+  // the visit), the wait for record k therefore also waited for record k+1, requested five instructions earlier -- a
+  // full memory latency exposed on every second visit (ncu source page: one DADD held 33 % of all stall samples).
+  // The loads of record k+1 are therefore made DATA dependent on the first use of record k (`gate`: a NaN test the
+  // compiler cannot fold), so they are issued right after record k has arrived and have a whole visit to complete.
   Rec4 A0, B0, C0, A1, B1, C1;
   double D0 = 0.0, D1 = 0.0;   // rhoI_j of the Shepard numerator, part of the pipeline on filter steps
+  auto gate = [&](const Rec4 &A) { const double g = Ai.x - A.x; return g != g ? 1 : 0; };
   {
     const Prec *p = d.prec + (e0 & NEIGH_JMASK);
     A0 = ld_rec(&p->A); B0 = ld_rec(&p->B); C0 = ld_rec(&p->C);
@@ -521,9 +529,10 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   }
   for (int kk = 0; kk < nn; kk += 2) {
     {
-      const Prec *p = d.prec + (e1 & NEIGH_JMASK);
+      const int j1 = (e1 & NEIGH_JMASK) + gate(A0);
+      const Prec *p = d.prec + j1;
       A1 = ld_rec(&p->A); B1 = ld_rec(&p->B); C1 = ld_rec(&p->C);
-      if (FILTER) D1 = d.pD[e1 & NEIGH_JMASK].x;
+      if (FILTER) D1 = d.pD[j1].x;
     }
     fetch2(kk + RING);   // slots of entries kk, kk+1: already in e0, e1
     asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries <= kk+5 (+ 2 PFL2) landed
@@ -535,9 +544,10 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
 #endif
     visit(e0, A0, B0, C0, D0);
     {
-      const Prec *p = d.prec + (e2 & NEIGH_JMASK);
+      const int j2 = (e2 & NEIGH_JMASK) + gate(A1);
+      const Prec *p = d.prec + j2;
       A0 = ld_rec(&p->A); B0 = ld_rec(&p->B); C0 = ld_rec(&p->C);
-      if (FILTER) D0 = d.pD[e2 & NEIGH_JMASK].x;
+      if (FILTER) D0 = d.pD[j2].x;
     }
     if (kk + 1 < nn) visit(e1, A1, B1, C1, D1);
     e0 = e2;
