@@ -8,7 +8,8 @@ n^3 simple-cubic particles (3-layer fixed BVF walls, moving lid, fluid jittered 
 an analytic velocity/density perturbation so forces do not cancel), h = 2.6 delta, skin 0.01 h,
 dt = 0.05 h / c0, transportVelocity pair + fix.  A "step" is ONE full timestep of the hot path
 (initial_integrate -> neighbour decide/rebuild or halo -> fused density+force pair pass ->
-final_integrate) on device-resident state; rebuilds (every 10 steps with this skin) are inside
+final_integrate; final_integrate(n) and initial_integrate(n+1) run as one kernel when nothing is scheduled
+between two steps) on device-resident state; rebuilds (every 10 steps with this skin) are inside
 the timed region.  Weak scaling: n = 200 / 252 / 318 / 400 at 1 / 2 / 4 / 8 GPUs (8M atoms per GPU),
 brick decomposition, one process per GPU (torchrun), NCCL halo inside libsphbvf.so.
 
@@ -41,7 +42,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 B_ALG_PAIR = 240.0      # algorithmic bytes / atom-step of the pair pass
 B_ALG_STEP = 616.0      # whole step
 F_ALG_PAIR = 1.2e4      # FP64 flop / atom-step, 3D bulk (2.8e3 + 9.2e3)
-TRAFFIC_PAIR_B_PER_ATOM = 532.0   # measured DRAM bytes / atom of pair_kernel (profiles/r01c_*: 895 MB + 221 MB for 2.10 M atoms)
+TRAFFIC_PAIR_B_PER_ATOM = 605.0   # measured DRAM bytes / atom of pair_kernel (profiles/r01g_pair_and_integrate_n200.txt: 3.95 GB read + 0.88 GB written for 8.0 M atoms)
 WEAK_N = {1: 200, 2: 252, 4: 318, 8: 400}
 
 
@@ -321,13 +322,15 @@ def main():
     fp64_peak = float(os.environ.get("SPHBVF_FP64_PEAK_TFLOPS", "0") or 0) or 148 * 64 * 2 * 1.965e9 / 1e12
     roof = {"bound": "hbm", "kernel": "pair_kernel (fused density/BVF + force pass)", "achieved": achieved,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/): 532 B/atom
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/): 605 B/atom
             "traffic": TRAFFIC_PAIR_B_PER_ATOM * eng.nlocal,
             "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650 GB/s",
             "algorithmic_bytes_per_atom_step": B_ALG_PAIR, "pair_ms_per_step": pair_ms,
             "fp64_tflops_algorithmic": F_ALG_PAIR * eng.nlocal / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0,
             "note": "the pair pass is FP64-pipe / gather-latency bound (AI ~ 50 flop/B, SURVEY.md 8d); HBM fraction reported "
-                    "as the contract asks, fp64_frac is the meaningful roof"}
+                    "as the contract asks, fp64_frac is the meaningful roof",
+            "ncu": {"l1_data_pipe_busy": 0.81, "fp64_pipe_busy": 0.46, "issue_active": 0.42, "warps_per_sm": 11.2,
+                    "source": "profiles/r01g_pair_and_integrate_n200.txt (one --set full capture, not live)"}}
     if fp64_peak:
         roof["fp64_peak_tflops"] = fp64_peak
         roof["fp64_frac"] = roof["fp64_tflops_algorithmic"] / fp64_peak
