@@ -31,8 +31,14 @@
 namespace sphbvf {
 
 // resident CTAs per SM the pair kernel is compiled for: 3 -> 168 registers (no spills), 4 -> 128
+#ifndef PAIR_PIPE
+#define PAIR_PIPE 1   // records in flight per warp: 1 (two buffers, 3 CTAs/SM) or 2 (four buffers, 2 CTAs/SM)
+#endif
 #ifndef PAIR_MINB
-#define PAIR_MINB 3
+#define PAIR_MINB (PAIR_PIPE == 2 ? 2 : 3)
+#endif
+#ifndef PAIR_T
+#define PAIR_T (PAIR_PIPE == 2 ? 160 : 128)   // threads per CTA: MINB x PAIR_T x registers <= 64 K
 #endif
 
 // one row per (type_i, type_j); 8 doubles = 64 B so a row is two LDS.128 x2
@@ -191,12 +197,12 @@ __device__ __forceinline__ void gauss2(unsigned a, unsigned b, double &g0, doubl
 // F it exerts on atom i is obtained as the change of the force accumulator and -1/2 s (x) F is summed
 // into virial_out[6] (see sphbvf_virial in capi.cu for the derivation).
 template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL = false>
-__global__ void __launch_bounds__(128, PAIR_MINB)
+__global__ void __launch_bounds__(PAIR_T, PAIR_MINB)
 pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
             const double damp, const double rand_pref, const unsigned long long seed, const long ntimestep,
             double *virial_out = nullptr) {
   __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
-  __shared__ int ring[RING][128];
+  __shared__ int ring[RING][PAIR_T];
   if (!UNIFORM) {
     for (int q = threadIdx.x; q < MAXT * MAXT; q += blockDim.x) srow[q] = tb.row[q];
     __syncthreads();
@@ -495,8 +501,8 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
 #endif
   auto fetch2 = [&](int k) {   // entries k, k+1 -> ring slots k % RING, (k+1) % RING; one group
-    if (k < nn) cp_async4(myring + (k % RING) * 128, np + (size_t)k * stride, pol);
-    if (k + 1 < nn) cp_async4(myring + ((k + 1) % RING) * 128, np + (size_t)(k + 1) * stride, pol);
+    if (k < nn) cp_async4(myring + (k % RING) * PAIR_T, np + (size_t)k * stride, pol);
+    if (k + 1 < nn) cp_async4(myring + ((k + 1) % RING) * PAIR_T, np + (size_t)(k + 1) * stride, pol);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   // groups allowed in flight after a wait: entries <= kk + 17 - 2 * PEND have landed
@@ -506,11 +512,11 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   for (int k = 0; k < RING; k += 2) fetch2(k);
   asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries 0..3 (+ 2 PFL2) landed
   int e0 = nn > 0 ? myring[0] : 0;
-  int e1 = nn > 1 ? myring[128] : 0;
+  int e1 = nn > 1 ? myring[PAIR_T] : 0;
 #if PAIR_PFL2 > 0
 #pragma unroll
   for (int q = 2; q < 4 + 2 * PAIR_PFL2; q++)
-    if (q < nn) prefetch_rec_l2(d.prec + (myring[(q % RING) * 128] & NEIGH_JMASK));
+    if (q < nn) prefetch_rec_l2(d.prec + (myring[(q % RING) * PAIR_T] & NEIGH_JMASK));
 #endif
   // Register pipeline: while the record of one neighbour is evaluated, the record of the next one is in flight.
   // ptxas puts all six record loads of the loop on ONE scoreboard, and a scoreboard is a counter: the first use of a
@@ -519,6 +525,57 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   // full memory latency exposed on every second visit (ncu source page: one DADD held 33 % of all stall samples).
   // The loads of record k+1 are therefore made DATA dependent on the first use of record k (`gate`: a NaN test the
   // compiler cannot fold), so they are issued right after record k has arrived and have a whole visit to complete.
+#if PAIR_PIPE == 2
+  // Two records in flight per warp: the records of the NEXT TWO neighbours are requested (one batch of six loads, gated
+  // on the first use of the current pair so that the single scoreboard wait of the loop covers exactly one batch) while
+  // the current two are evaluated.  Four record buffers: ~210 registers, two CTAs per SM -- 8 warps x 2 records = 16
+  // records in flight per SM instead of 12 x 1.
+  Rec4 A0, B0, C0, A1, B1, C1, A2, B2, C2, A3, B3, C3;
+  double D0 = 0.0, D1 = 0.0, D2 = 0.0, D3 = 0.0;
+  auto gate = [&](const Rec4 &A) { const double g = Ai.x - A.x; return g != g ? 1 : 0; };
+  {
+    const Prec *p = d.prec + (e0 & NEIGH_JMASK);
+    A0 = ld_rec(&p->A); B0 = ld_rec(&p->B); C0 = ld_rec(&p->C);
+    if (FILTER) D0 = d.pD[e0 & NEIGH_JMASK].x;
+    const Prec *q = d.prec + (e1 & NEIGH_JMASK);
+    A1 = ld_rec(&q->A); B1 = ld_rec(&q->B); C1 = ld_rec(&q->C);
+    if (FILTER) D1 = d.pD[e1 & NEIGH_JMASK].x;
+  }
+  for (int kk = 0; kk < nn; kk += 4) {
+    // ---- half 1: evaluate e0, e1 (records 0, 1); request records 2, 3 for e2, e3
+    fetch2(kk + RING);
+    asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries <= kk+5 landed
+    const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * PAIR_T] : 0;
+    const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * PAIR_T] : 0;
+    {
+      const int g = gate(A0);
+      const int j2 = (e2 & NEIGH_JMASK) + g, j3 = (e3 & NEIGH_JMASK) + g;
+      const Prec *p = d.prec + j2, *q = d.prec + j3;
+      A2 = ld_rec(&p->A); B2 = ld_rec(&p->B); C2 = ld_rec(&p->C);
+      A3 = ld_rec(&q->A); B3 = ld_rec(&q->B); C3 = ld_rec(&q->C);
+      if (FILTER) { D2 = d.pD[j2].x; D3 = d.pD[j3].x; }
+    }
+    visit(e0, A0, B0, C0, D0);
+    if (kk + 1 < nn) visit(e1, A1, B1, C1, D1);
+    if (kk + 2 >= nn) break;
+    // ---- half 2: evaluate e2, e3 (records 2, 3); request records 0, 1 for e4, e5
+    fetch2(kk + 2 + RING);
+    asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries <= kk+7 landed
+    e0 = kk + 4 < nn ? myring[((kk + 4) % RING) * PAIR_T] : 0;
+    e1 = kk + 5 < nn ? myring[((kk + 5) % RING) * PAIR_T] : 0;
+    {
+      const int g = gate(A2);
+      const int j0 = (e0 & NEIGH_JMASK) + g, j1 = (e1 & NEIGH_JMASK) + g;
+      const Prec *p = d.prec + j0, *q = d.prec + j1;
+      A0 = ld_rec(&p->A); B0 = ld_rec(&p->B); C0 = ld_rec(&p->C);
+      A1 = ld_rec(&q->A); B1 = ld_rec(&q->B); C1 = ld_rec(&q->C);
+      if (FILTER) { D0 = d.pD[j0].x; D1 = d.pD[j1].x; }
+    }
+    visit(e2, A2, B2, C2, D2);
+    if (kk + 3 < nn) visit(e3, A3, B3, C3, D3);
+  }
+
+#else
   Rec4 A0, B0, C0, A1, B1, C1;
   double D0 = 0.0, D1 = 0.0;   // rhoI_j of the Shepard numerator, part of the pipeline on filter steps
   auto gate = [&](const Rec4 &A) { const double g = Ai.x - A.x; return g != g ? 1 : 0; };
@@ -536,11 +593,11 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     }
     fetch2(kk + RING);   // slots of entries kk, kk+1: already in e0, e1
     asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries <= kk+5 (+ 2 PFL2) landed
-    const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * 128] : 0;
-    const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * 128] : 0;
+    const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * PAIR_T] : 0;
+    const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * PAIR_T] : 0;
 #if PAIR_PFL2 > 0
-    if (kk + 4 + 2 * PAIR_PFL2 < nn) prefetch_rec_l2(d.prec + (myring[((kk + 4 + 2 * PAIR_PFL2) % RING) * 128] & NEIGH_JMASK));
-    if (kk + 5 + 2 * PAIR_PFL2 < nn) prefetch_rec_l2(d.prec + (myring[((kk + 5 + 2 * PAIR_PFL2) % RING) * 128] & NEIGH_JMASK));
+    if (kk + 4 + 2 * PAIR_PFL2 < nn) prefetch_rec_l2(d.prec + (myring[((kk + 4 + 2 * PAIR_PFL2) % RING) * PAIR_T] & NEIGH_JMASK));
+    if (kk + 5 + 2 * PAIR_PFL2 < nn) prefetch_rec_l2(d.prec + (myring[((kk + 5 + 2 * PAIR_PFL2) % RING) * PAIR_T] & NEIGH_JMASK));
 #endif
     visit(e0, A0, B0, C0, D0);
     {
@@ -554,6 +611,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     e1 = e3;
   }
 
+#endif
   if (VIRIAL) {
     // only atoms next to a periodic face have anything to add: plain atomics
 #pragma unroll
@@ -585,7 +643,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
 template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM>
 static void launch_filter(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf,
                           cudaStream_t st) {
-  const int threads = 128;
+  const int threads = PAIR_T;
   const int blocks = (d.nlocal + threads - 1) / threads;
 #ifdef PAIR_DIAG_SMEM   // tools/: occupancy probe -- extra dynamic shared memory limits the resident CTAs per SM
   static bool once = false;
@@ -654,9 +712,9 @@ __global__ void virial_fdotr_kernel(const DevState d, double *out) {
 template <int VARIANT, bool SPECIES>
 static void launch_virial_solids(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf,
                                  double *out, cudaStream_t st) {
-  const int blocks = (d.nlocal + 127) / 128;
+  const int blocks = (d.nlocal + PAIR_T - 1) / PAIR_T;
   const int solids = !pf.any_solid ? 0 : (pf.with_dev ? 2 : 1);
-#define VK(S) pair_kernel<VARIANT, SPECIES, S, false, false, false, true><<<blocks, 128, 0, st>>>(d, co, tb, pf.damp, 0.0, 0ULL, pf.ntimestep, out)
+#define VK(S) pair_kernel<VARIANT, SPECIES, S, false, false, false, true><<<blocks, PAIR_T, 0, st>>>(d, co, tb, pf.damp, 0.0, 0ULL, pf.ntimestep, out)
   if (solids == 0) VK(0);
   else if (solids == 1) VK(1);
   else VK(2);
