@@ -34,6 +34,9 @@ namespace sphbvf {
 #ifndef PAIR_PIPE
 #define PAIR_PIPE 1   // records in flight per warp: 1 (two buffers, 3 CTAs/SM) or 2 (four buffers, 2 CTAs/SM)
 #endif
+#ifndef PAIR_TMA
+#define PAIR_TMA 0    // D > 0: neighbour records travel global -> shared memory as per-lane bulk copies (TMA engine,
+#endif                // mbarrier completion), D records in flight per thread, no record buffers in registers
 #ifndef PAIR_MINB
 #define PAIR_MINB (PAIR_PIPE == 2 ? 2 : 3)
 #endif
@@ -121,6 +124,27 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 constexpr int RING = 16;  // list-entry prefetch depth (rows); power of two
+constexpr int TMA_RSTRIDE = 112;   // bytes per staged record: 96 + 16 pad, so that the 16-byte LDS of 8 lanes hit 32 banks
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// one bulk copy per calling lane: `bytes` (multiple of 16) from global to this CTA's shared memory, completion on `b`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
 
 // L2 residency (tuning switches):
 //   PAIR_L2HINT >= 1: the streams that are touched once per launch (list entries in, per-atom outputs out) are
@@ -207,8 +231,20 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     for (int q = threadIdx.x; q < MAXT * MAXT; q += blockDim.x) srow[q] = tb.row[q];
     __syncthreads();
   }
+#if PAIR_TMA
+  extern __shared__ __align__(128) unsigned char pair_dyn[];
+  unsigned long long *mbar_all = reinterpret_cast<unsigned long long *>(pair_dyn + (size_t)PAIR_TMA * PAIR_T * TMA_RSTRIDE);
+  if (threadIdx.x < (PAIR_T / 32) * PAIR_TMA) mbar_init(mbar_all + threadIdx.x, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  // every lane stays alive (warp-wide mbarrier protocol): lanes past the last atom shadow atom 0 with an empty list
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = gi < d.nlocal;
+  const int i = live ? gi : 0;
+#else
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.nlocal) return;
+#endif
 
   const int fl = d.pflags[i];
   const int ti = fl & 7;
@@ -492,7 +528,11 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   // entries RING rows ahead into a shared-memory ring with cp.async (no registers, no barrier:
   // a thread only ever reads the slots it wrote).  The records of neighbour k+1 are requested
   // before neighbour k is evaluated.
+#if PAIR_TMA
+  const int nn = live ? d.numneigh[i] : 0;
+#else
   const int nn = d.numneigh[i];
+#endif
   const int *np = d.neigh + i;
   const size_t stride = d.stride;
   int *myring = &ring[0][threadIdx.x];
@@ -500,6 +540,57 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
 #if PAIR_L2HINT >= 1
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
 #endif
+#if PAIR_TMA
+  // ------------------------------------------------------------------ TMA traversal
+  // Per lane, the 96-byte record of entry k + D is copied global -> shared memory by the bulk-copy engine while entry k
+  // is evaluated: D records in flight per thread without a single register, and the L1/LSU pipe only sees conflict-free
+  // LDS.128 reads (24 wavefronts per visit instead of 66 for three gathers).  One mbarrier per (warp, slot): lane 0
+  // posts the expected byte count of the warp's active lanes, each lane's copy completes its share, all lanes wait.
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int nnmax = nn;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nnmax = max(nnmax, __shfl_xor_sync(0xffffffffu, nnmax, o));
+    unsigned char *myrec = pair_dyn + (size_t)threadIdx.x * TMA_RSTRIDE;
+    unsigned long long *mbar = mbar_all + warp * PAIR_TMA;
+    auto fetch1 = [&](int k) {
+      if (k < nn) cp_async4(myring + (k % RING) * PAIR_T, np + (size_t)k * stride, pol);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto issue = [&](int k) {   // warp-uniform call, k < nnmax, entry k has landed in the ring
+      const int slot = k % PAIR_TMA;
+      const bool act = k < nn;
+      const unsigned m = __ballot_sync(0xffffffffu, act);
+      if (lane == 0) mbar_expect_tx(mbar + slot, 96u * (unsigned)__popc(m));
+      __syncwarp();
+      if (act) {
+        const int e = myring[(k % RING) * PAIR_T];
+        bulk_g2s(myrec + (size_t)slot * PAIR_T * TMA_RSTRIDE, d.prec + (e & NEIGH_JMASK), 96u, mbar + slot);
+      }
+    };
+#pragma unroll
+    for (int k = 0; k < RING; k++) fetch1(k);
+    asm volatile("cp.async.wait_group %0;" ::"n"(RING - PAIR_TMA) : "memory");   // entries < D landed
+    __syncwarp();
+    for (int k = 0; k < PAIR_TMA && k < nnmax; k++) issue(k);
+    for (int k = 0; k < nnmax; k++) {
+      const bool act = k < nn;
+      const int e = act ? myring[(k % RING) * PAIR_T] : 0;
+      fetch1(k + RING);
+      asm volatile("cp.async.wait_group %0;" ::"n"(RING - PAIR_TMA) : "memory");   // entries <= k + D landed
+      mbar_wait(mbar + (k % PAIR_TMA), (unsigned)((k / PAIR_TMA) & 1));
+      if (act) {
+        const double2 *r = reinterpret_cast<const double2 *>(myrec + (size_t)(k % PAIR_TMA) * PAIR_T * TMA_RSTRIDE);
+        const double2 a0 = r[0], a1 = r[1], b0 = r[2], b1 = r[3], c0 = r[4], c1 = r[5];
+        const Rec4 Aj = make_rec4(a0.x, a0.y, a1.x, a1.y), Bj = make_rec4(b0.x, b0.y, b1.x, b1.y),
+                   Cj = make_rec4(c0.x, c0.y, c1.x, c1.y);
+        visit(e, Aj, Bj, Cj, FILTER ? d.pD[e & NEIGH_JMASK].x : 0.0);
+      }
+      __syncwarp();
+      if (k + PAIR_TMA < nnmax) issue(k + PAIR_TMA);
+    }
+  }
+#else
   auto fetch2 = [&](int k) {   // entries k, k+1 -> ring slots k % RING, (k+1) % RING; one group
     if (k < nn) cp_async4(myring + (k % RING) * PAIR_T, np + (size_t)k * stride, pol);
     if (k + 1 < nn) cp_async4(myring + ((k + 1) % RING) * PAIR_T, np + (size_t)(k + 1) * stride, pol);
@@ -612,6 +703,8 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   }
 
 #endif
+#endif   // PAIR_TMA
+
   if (VIRIAL) {
     // only atoms next to a periodic face have anything to add: plain atomics
 #pragma unroll
@@ -619,6 +712,9 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
       if (vir[q] != 0.0) atomicAdd(virial_out + q, vir[q]);
     return;
   }
+#if PAIR_TMA
+  if (!live) return;
+#endif
   const double ddvc = 10.0 * 7.0 * co.B[ti];
   const size_t i3 = 3 * (size_t)i;
   st_out(d.f + i3, fma(spi, Bi.x, fx)); st_out(d.f + i3 + 1, fma(spi, Bi.y, fy)); st_out(d.f + i3 + 2, fma(spi, Bi.z, fz));
@@ -645,7 +741,17 @@ static void launch_filter(const DevState &d, const Coeffs &co, const PairTables 
                           cudaStream_t st) {
   const int threads = PAIR_T;
   const int blocks = (d.nlocal + threads - 1) / threads;
-#ifdef PAIR_DIAG_SMEM   // tools/: occupancy probe -- extra dynamic shared memory limits the resident CTAs per SM
+#if PAIR_TMA
+  constexpr int dyn = PAIR_TMA * PAIR_T * TMA_RSTRIDE + (PAIR_T / 32) * PAIR_TMA * 8;
+  static bool once_tma = false;
+  if (!once_tma) {
+    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    once_tma = true;
+  }
+#define PK(F, R) pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, F, R><<<blocks, threads, dyn, st>>>(d, co, tb, pf.damp, pf.rand_pref, pf.seed, pf.ntimestep)
+#elif defined(PAIR_DIAG_SMEM)   // tools/: occupancy probe -- extra dynamic shared memory limits the resident CTAs per SM
   static bool once = false;
   if (!once) {
     cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_DIAG_SMEM);
@@ -714,7 +820,19 @@ static void launch_virial_solids(const DevState &d, const Coeffs &co, const Pair
                                  double *out, cudaStream_t st) {
   const int blocks = (d.nlocal + PAIR_T - 1) / PAIR_T;
   const int solids = !pf.any_solid ? 0 : (pf.with_dev ? 2 : 1);
-#define VK(S) pair_kernel<VARIANT, SPECIES, S, false, false, false, true><<<blocks, PAIR_T, 0, st>>>(d, co, tb, pf.damp, 0.0, 0ULL, pf.ntimestep, out)
+#if PAIR_TMA
+  constexpr int vdyn = PAIR_TMA * PAIR_T * TMA_RSTRIDE + (PAIR_T / 32) * PAIR_TMA * 8;
+  static bool once_v = false;
+  if (!once_v) {
+    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, 0, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vdyn);
+    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, 1, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vdyn);
+    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, 2, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vdyn);
+    once_v = true;
+  }
+#else
+  constexpr int vdyn = 0;
+#endif
+#define VK(S) pair_kernel<VARIANT, SPECIES, S, false, false, false, true><<<blocks, PAIR_T, vdyn, st>>>(d, co, tb, pf.damp, 0.0, 0ULL, pf.ntimestep, out)
   if (solids == 0) VK(0);
   else if (solids == 1) VK(1);
   else VK(2);
