@@ -567,11 +567,15 @@ void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const
 #ifdef TB_DIAG_NOSTORE
     { const char *e = getenv("SPHBVF_TB_NOSTORE"); const int v = e && atoi(e); cudaMemcpyAsync(w.flags + 7, &v, sizeof(int), cudaMemcpyHostToDevice, st); cudaStreamSynchronize(st); }
 #endif
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in to > 48 KB of dynamic shared memory is per device (one process may drive several GPUs, each from
+    // its own thread): setting it again is harmless, missing it is a launch failure
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
       cudaFuncSetAttribute(build_list_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       cudaFuncSetAttribute(build_list_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      attr_set = true;
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     if (uniform) build_list_tile_kernel<true><<<(int)ntiles, TB_T, smem, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
     else build_list_tile_kernel<false><<<(int)ntiles, TB_T, smem, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);

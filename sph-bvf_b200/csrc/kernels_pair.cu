@@ -743,20 +743,14 @@ static void launch_filter(const DevState &d, const Coeffs &co, const PairTables 
   const int blocks = (d.nlocal + threads - 1) / threads;
 #if PAIR_TMA
   constexpr int dyn = PAIR_TMA * PAIR_T * TMA_RSTRIDE + (PAIR_T / 32) * PAIR_TMA * 8;
-  static bool once_tma = false;
-  if (!once_tma) {
+  {   // per device: cheap enough to repeat on every launch of this tuning path
     cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    once_tma = true;
   }
 #define PK(F, R) pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, F, R><<<blocks, threads, dyn, st>>>(d, co, tb, pf.damp, pf.rand_pref, pf.seed, pf.ntimestep)
 #elif defined(PAIR_DIAG_SMEM)   // tools/: occupancy probe -- extra dynamic shared memory limits the resident CTAs per SM
-  static bool once = false;
-  if (!once) {
-    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_DIAG_SMEM);
-    once = true;
-  }
+  cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_DIAG_SMEM);
 #define PK(F, R) pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, F, R><<<blocks, threads, ((F) || (R)) ? 0 : PAIR_DIAG_SMEM, st>>>(d, co, tb, pf.damp, pf.rand_pref, pf.seed, pf.ntimestep)
 #else
 #define PK(F, R) pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, F, R><<<blocks, threads, 0, st>>>(d, co, tb, pf.damp, pf.rand_pref, pf.seed, pf.ntimestep)
@@ -822,12 +816,10 @@ static void launch_virial_solids(const DevState &d, const Coeffs &co, const Pair
   const int solids = !pf.any_solid ? 0 : (pf.with_dev ? 2 : 1);
 #if PAIR_TMA
   constexpr int vdyn = PAIR_TMA * PAIR_T * TMA_RSTRIDE + (PAIR_T / 32) * PAIR_TMA * 8;
-  static bool once_v = false;
-  if (!once_v) {
+  {
     cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, 0, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vdyn);
     cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, 1, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vdyn);
     cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, 2, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vdyn);
-    once_v = true;
   }
 #else
   constexpr int vdyn = 0;

@@ -18,7 +18,7 @@ bool ComputeTempCuda::device_sums(double *ke6)
 {
   SphbvfLmp *engine = SphbvfLmp::peek();
   if (!engine || !engine->active() || engine->host_is_current()) return false;
-  engine->check(sphbvf_ke_tensor(engine->ctx, groupbit, ke6));
+  engine->ke_tensor(groupbit, ke6);
   engine->count_device_thermo();
   return true;
 }

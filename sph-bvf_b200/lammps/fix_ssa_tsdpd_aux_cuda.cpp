@@ -197,8 +197,7 @@ void FixDtAdaptiveCuda::end_of_step()
 {
   SphbvfLmp *engine = SphbvfLmp::get(lmp);
   if (!engine->active()) error->all(FLERR, "fix dt/adaptive/cuda requires pair_style ssa_tsdpd/bvf/<style>/cuda");
-  double maxAllVsq = 0.0;
-  engine->check(sphbvf_max_vsq(engine->ctx, groupbit, &maxAllVsq));
+  const double maxAllVsq = engine->max_vsq(groupbit);
   dt = CFLmax * dxAve / sqrt(maxAllVsq);
   if (minbound) dt = MAX(dt, tmin);
   if (maxbound) dt = MIN(dt, tmax);

@@ -87,7 +87,7 @@ void FixSsaTsdpdBvfCuda::setup_pre_force(int)
 
 void FixSsaTsdpdBvfCuda::setup(int)
 {
-  engine->check(sphbvf_setup_post_force(engine->ctx));
+  engine->call(sphbvf_setup_post_force);
   if (engine->output_needs_host(true)) engine->to_host();   // output of step 0 (Verlet::setup -> output->setup)
 }
 
@@ -95,20 +95,20 @@ void FixSsaTsdpdBvfCuda::setup(int)
 
 void FixSsaTsdpdBvfCuda::initial_integrate(int)
 {
-  engine->check(sphbvf_set_timestep(engine->ctx, (long)update->ntimestep));
-  engine->check(sphbvf_initial_integrate(engine->ctx));
+  engine->set_timestep(update->ntimestep);
+  engine->call(sphbvf_initial_integrate);
   engine->mark_dirty();
 }
 
-void FixSsaTsdpdBvfCuda::post_integrate() { engine->check(sphbvf_post_integrate(engine->ctx)); }
+void FixSsaTsdpdBvfCuda::post_integrate() { engine->call(sphbvf_post_integrate); }
 
-void FixSsaTsdpdBvfCuda::post_force(int) { engine->check(sphbvf_post_force(engine->ctx)); }
+void FixSsaTsdpdBvfCuda::post_force(int) { engine->call(sphbvf_post_force); }
 
-void FixSsaTsdpdBvfCuda::final_integrate() { engine->check(sphbvf_final_integrate(engine->ctx)); }
+void FixSsaTsdpdBvfCuda::final_integrate() { engine->call(sphbvf_final_integrate); }
 
 void FixSsaTsdpdBvfCuda::end_of_step()
 {
-  engine->check(sphbvf_end_of_step(engine->ctx));
+  engine->call(sphbvf_end_of_step);
   if (update->ntimestep == output->next && engine->output_needs_host()) engine->to_host();
 }
 
@@ -118,5 +118,5 @@ void FixSsaTsdpdBvfCuda::post_run() { engine->stop(); }
 
 void FixSsaTsdpdBvfCuda::reset_dt()
 {
-  if (engine->active()) engine->check(sphbvf_set_dt(engine->ctx, update->dt));
+  if (engine->active()) engine->set_dt(update->dt);
 }

@@ -69,14 +69,14 @@ void PairSsaTsdpdBvfCuda::compute(int eflag, int vflag)
   if (!engine->active()) engine->start();                       // setup: neighbour build included
   else {
     int rebuilt = 0;
-    engine->check(sphbvf_neighbor(engine->ctx, &rebuilt));      // decide + rebuild | forward halo
+    engine->neighbor_step(&rebuilt);                                        // decide + rebuild | forward halo
   }
-  engine->check(sphbvf_pair_compute(engine->ctx));
+  engine->call(sphbvf_pair_compute);
   engine->mark_dirty();
   // thermo steps: the virial LAMMPS would get from virial_fdotr_compute() on the host arrays
   if (vflag_fdotr || vflag_global) {
     double v[6];
-    engine->check(sphbvf_virial(engine->ctx, v));
+    engine->virial(v);
     for (int k = 0; k < 6; k++) virial[k] += v[k];
     vflag_fdotr = 0;
   }

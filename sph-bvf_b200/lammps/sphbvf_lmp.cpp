@@ -6,6 +6,9 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include "sphbvf_lmp.h"
 #include "atom.h"
 #include "comm.h"
@@ -26,6 +29,70 @@
 using namespace LAMMPS_NS;
 
 static SphbvfLmp *the_engine = NULL;   // one LAMMPS instance per process in this build
+
+namespace LAMMPS_NS {
+/* one persistent thread per GPU: run(f) executes f(rank) on every worker and returns the status codes.
+   The library's multi-rank entry points contain NCCL collectives and stream synchronisations, so the ranks
+   of one process must be inside the same call at the same time -- exactly what MPI ranks do upstream. */
+class SphbvfWorkers {
+ public:
+  explicit SphbvfWorkers(int n) : n_(n), gen_(0), pending_(0), quit_(false), rc_(n, 0)
+  {
+    for (int r = 0; r < n; r++) th_.emplace_back([this, r] { loop(r); });
+  }
+  ~SphbvfWorkers()
+  {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      quit_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (size_t r = 0; r < th_.size(); r++) th_[r].join();
+  }
+  const std::vector<int> &run(const std::function<int(int)> &f)
+  {
+    std::unique_lock<std::mutex> lk(m_);
+    task_ = &f;
+    pending_ = n_;
+    gen_++;
+    cv_.notify_all();
+    done_.wait(lk, [this] { return pending_ == 0; });
+    return rc_;
+  }
+
+ private:
+  void loop(int r)
+  {
+    unsigned long seen = 0;
+    for (;;) {
+      const std::function<int(int)> *f;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (quit_) return;
+        f = task_;
+      }
+      const int rc = (*f)(r);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        rc_[r] = rc;
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  int n_;
+  unsigned long gen_;
+  int pending_;
+  bool quit_;
+  std::vector<int> rc_;
+  const std::function<int(int)> *task_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> th_;
+};
+}
 
 SphbvfLmp *SphbvfLmp::get(LAMMPS *lmp)
 {
@@ -54,11 +121,66 @@ SphbvfLmp::SphbvfLmp(LAMMPS *lmp) : Pointers(lmp)
   host_current = 1;
   nlocal_uploaded = 0;
   ndownloads = ndevice_thermo = nskipped = 0;
+  nranks = 1;
+  workers = NULL;
 }
 
 SphbvfLmp::~SphbvfLmp()
 {
-  if (ctx) sphbvf_destroy(ctx);
+  if (ctxs.size() > 1 && workers) workers->run([&](int r) { sphbvf_destroy(ctxs[r]); return 0; });
+  else if (ctxs.size() == 1) sphbvf_destroy(ctxs[0]);
+  delete workers;
+}
+
+/* f(ctx_r, r) on every rank at the same time; the first failing rank's message becomes the LAMMPS error */
+
+void SphbvfLmp::all(const std::function<int(sphbvf_ctx *, int)> &f)
+{
+  if (nranks == 1) {
+    check(f(ctx, 0));
+    return;
+  }
+  const std::vector<int> &rc = workers->run([&](int r) { return f(ctxs[r], r); });
+  for (int r = 0; r < nranks; r++)
+    if (rc[r]) {
+      char msg[600];
+      snprintf(msg, sizeof msg, "sphbvf (%d) on GPU %d: %s", rc[r], r, sphbvf_last_error(ctxs[r]));
+      error->one(FLERR, msg);
+    }
+}
+
+void SphbvfLmp::neighbor_step(int *rebuilt)
+{
+  std::vector<int> rb(nranks, 0);
+  all([&](sphbvf_ctx *c, int r) { return sphbvf_neighbor(c, &rb[r]); });
+  if (rebuilt) *rebuilt = rb[0];   // the rebuild vote is global
+}
+
+void SphbvfLmp::virial(double *v6)
+{
+  std::vector<double> v(6 * (size_t)nranks, 0.0);
+  all([&](sphbvf_ctx *c, int r) { return sphbvf_virial(c, &v[6 * (size_t)r]); });
+  for (int k = 0; k < 6; k++) {
+    v6[k] = 0.0;
+    for (int r = 0; r < nranks; r++) v6[k] += v[6 * (size_t)r + k];
+  }
+}
+
+void SphbvfLmp::ke_tensor(int groupbit, double *t6)
+{
+  std::vector<double> v(6 * (size_t)nranks, 0.0);
+  all([&](sphbvf_ctx *c, int r) { return sphbvf_ke_tensor(c, groupbit, &v[6 * (size_t)r]); });
+  for (int k = 0; k < 6; k++) {
+    t6[k] = 0.0;
+    for (int r = 0; r < nranks; r++) t6[k] += v[6 * (size_t)r + k];
+  }
+}
+
+double SphbvfLmp::max_vsq(int groupbit)
+{
+  std::vector<double> v(nranks, 0.0);
+  all([&](sphbvf_ctx *c, int r) { return sphbvf_max_vsq(c, groupbit, &v[r]); });   // all-reduced inside the library
+  return v[0];
 }
 
 void SphbvfLmp::check(int rc)
@@ -110,44 +232,133 @@ void SphbvfLmp::start()
   cfg.neigh_check = neighbor->dist_check;
   cfg.dt = update->dt;
   cfg.integrate_groupbit = integrate_groupbit;
-  cfg.device = 0;
-  cfg.rank = 0;
-  cfg.nranks = 1;
-  int rc = sphbvf_create(&cfg, &ctx);
-  if (rc) {
-    ctx = NULL;
-    error->all(FLERR, "sphbvf_create failed (more than 4 atom types / species, or no usable GPU)");
+
+  // ---- how many GPUs: SPHBVF_NGPU, else every visible GPU once there are >= 10^6 atoms for each
+  const int n = atom->nlocal;
+  int want = sphbvf_device_count();
+  {
+    const char *env = getenv("SPHBVF_NGPU");
+    if (env) want = atoi(env);
+    else want = MIN(want, MAX(1, n / 1000000));
+  }
+  nranks = MAX(1, MIN(want, sphbvf_device_count()));
+  {
+    double prd[3] = {domain->xprd, domain->yprd, domain->zprd};
+    int grid[3] = {1, 1, 1};
+    check(sphbvf_proc_grid(nranks, cfg.dim, prd, grid));
+    for (int k = 0; k < 3; k++) cfg.procgrid[k] = grid[k];
+  }
+  cfg.nranks = nranks;
+  if (nranks > 1 && !workers) workers = new SphbvfWorkers(nranks);
+  if (workers && nranks == 1) { delete workers; workers = NULL; }
+
+  // ---- one context per GPU, created on the worker thread that will drive it (cudaSetDevice is per thread)
+  ctxs.assign(nranks, (sphbvf_ctx *)NULL);
+  std::vector<int> rc_create(nranks, 0);
+  {
+    auto create = [&](int r) {
+      sphbvf_config c = cfg;
+      c.device = r;
+      c.rank = r;
+      rc_create[r] = sphbvf_create(&c, &ctxs[r]);
+      return 0;
+    };
+    if (nranks == 1) create(0);
+    else workers->run(create);
+  }
+  for (int r = 0; r < nranks; r++)
+    if (rc_create[r]) {
+      for (int q = 0; q < nranks; q++) if (ctxs[q]) sphbvf_destroy(ctxs[q]);
+      ctxs.clear();
+      ctx = NULL;
+      error->all(FLERR, "sphbvf_create failed (more than 4 atom types / species, or no usable GPU)");
+    }
+  ctx = ctxs[0];
+  if (nranks > 1) {
+    char id[128];
+    check(sphbvf_comm_unique_id(id));
+    all([&](sphbvf_ctx *c, int) { return sphbvf_comm_init(c, id); });
   }
 
   // Pair::coeff / init_one already mirrored [i][j] -> [j][i] (pair_ssa_tsdpd_bvf_<style>.cpp init_one)
-  for (int i = 1; i <= ntypes; i++) check(sphbvf_set_type(ctx, i, atom->mass[i], rho0[i], soundspeed[i], G0[i]));
-  for (int i = 1; i <= ntypes; i++)
-    for (int j = i; j <= ntypes; j++)
-      check(sphbvf_set_pair(ctx, i, j, viscosity[i][j], cut[i][j], cutc[i][j], S ? kappa[i][j] : NULL));
-  for (int q = 0; q < nfixdesc; q++) {
-    const FixDesc &f = fixdesc[q];
-    switch (f.kind) {
-      case 0: check(sphbvf_add_buoyancy(ctx, f.groupbit, f.ia[0], f.a[0], f.ia[1], f.ia[2], f.a[1])); break;
-      case 1: check(sphbvf_add_forcing(ctx, f.groupbit, f.ia[0], (long)f.step, f.ia[1], f.ia[2], f.a[0], f.a[1], f.a[2], f.a[3], f.a[4])); break;
-      case 2: check(sphbvf_add_buffer(ctx, f.groupbit, f.ia[0], f.ia[2], (long)f.step, f.ia[1], f.a[0], f.a[1], f.a[2], f.a[3], f.a[4])); break;
-      case 3: check(sphbvf_add_setforce(ctx, f.groupbit, f.a[0], f.a[1], f.a[2])); break;
-      case 4: {
-        int r[2] = {f.ia[1] & 255, (f.ia[1] >> 8) & 255};
-        int p[4] = {f.ia[2] & 255, (f.ia[2] >> 8) & 255, (f.ia[2] >> 16) & 255, (f.ia[2] >> 24) & 255};
-        check(sphbvf_add_chem_rxn(ctx, f.groupbit, f.a[0], f.ia[0] & 255, r, f.ia[0] >> 8, p));
-        break;
+  all([&](sphbvf_ctx *c, int) {
+    int rc;
+    for (int i = 1; i <= ntypes; i++)
+      if ((rc = sphbvf_set_type(c, i, atom->mass[i], rho0[i], soundspeed[i], G0[i]))) return rc;
+    for (int i = 1; i <= ntypes; i++)
+      for (int j = i; j <= ntypes; j++)
+        if ((rc = sphbvf_set_pair(c, i, j, viscosity[i][j], cut[i][j], cutc[i][j], S ? kappa[i][j] : NULL))) return rc;
+    for (int q = 0; q < nfixdesc; q++) {
+      const FixDesc &f = fixdesc[q];
+      rc = 0;
+      switch (f.kind) {
+        case 0: rc = sphbvf_add_buoyancy(c, f.groupbit, f.ia[0], f.a[0], f.ia[1], f.ia[2], f.a[1]); break;
+        case 1: rc = sphbvf_add_forcing(c, f.groupbit, f.ia[0], (long)f.step, f.ia[1], f.ia[2], f.a[0], f.a[1], f.a[2], f.a[3], f.a[4]); break;
+        case 2: rc = sphbvf_add_buffer(c, f.groupbit, f.ia[0], f.ia[2], (long)f.step, f.ia[1], f.a[0], f.a[1], f.a[2], f.a[3], f.a[4]); break;
+        case 3: rc = sphbvf_add_setforce(c, f.groupbit, f.a[0], f.a[1], f.a[2]); break;
+        case 4: {
+          int r[2] = {f.ia[1] & 255, (f.ia[1] >> 8) & 255};
+          int p[4] = {f.ia[2] & 255, (f.ia[2] >> 8) & 255, (f.ia[2] >> 16) & 255, (f.ia[2] >> 24) & 255};
+          rc = sphbvf_add_chem_rxn(c, f.groupbit, f.a[0], f.ia[0] & 255, r, f.ia[0] >> 8, p);
+          break;
+        }
       }
+      if (rc) return rc;
     }
-  }
+    return 0;
+  });
 
-  const int n = atom->nlocal;
-  check(sphbvf_set_atoms(ctx, n, atom->tag, atom->type, atom->mask, atom->solid_tag, atom->fixed_tag,
-                         n ? &atom->x[0][0] : NULL, n ? &atom->v[0][0] : NULL, atom->rho, atom->e,
-                         (S && n) ? &atom->C[0][0] : NULL, n ? &atom->deviatoricTensor[0][0][0] : NULL));
-  if (n) {
-    // FixSsaTsdpdBvf*Cuda::setup_pre_force has just set vest = v and rhoI = rho on the host
-    check(sphbvf_upload(ctx, SPHBVF_F_VEST, &atom->vest[0][0]));
-    check(sphbvf_upload(ctx, SPHBVF_F_RHOI, atom->rhoI));
+  // FixSsaTsdpdBvf*Cuda::setup_pre_force has just set vest = v and rhoI = rho on the host
+  if (nranks == 1) {
+    check(sphbvf_set_atoms(ctx, n, atom->tag, atom->type, atom->mask, atom->solid_tag, atom->fixed_tag,
+                           n ? &atom->x[0][0] : NULL, n ? &atom->v[0][0] : NULL, atom->rho, atom->e,
+                           (S && n) ? &atom->C[0][0] : NULL, n ? &atom->deviatoricTensor[0][0][0] : NULL));
+    if (n) {
+      check(sphbvf_upload(ctx, SPHBVF_F_VEST, &atom->vest[0][0]));
+      check(sphbvf_upload(ctx, SPHBVF_F_RHOI, atom->rhoI));
+    }
+  } else {
+    // the atoms of each brick (domain.cpp:308-330 sub-box rule: lo <= x < hi, the last brick also takes x == boxhi)
+    std::vector<std::vector<int> > mine(nranks);
+    std::vector<double> lo(3 * (size_t)nranks), hi(3 * (size_t)nranks);
+    for (int r = 0; r < nranks; r++) check(sphbvf_brick_bounds(&cfg, r, &lo[3 * r], &hi[3 * r]));
+    const int P[3] = {cfg.procgrid[0], cfg.procgrid[1], cfg.procgrid[2]};
+    int maxtag = 0;
+    for (int i = 0; i < n; i++) {
+      int idx[3] = {0, 0, 0};
+      for (int k = 0; k < cfg.dim; k++) {
+        // bricks along dimension k: rank index stride follows sphbvf_brick_bounds (x fastest)
+        const int stride = k == 0 ? 1 : (k == 1 ? P[0] : P[0] * P[1]);
+        int q = 0;
+        while (q + 1 < P[k] && atom->x[i][k] >= hi[3 * (size_t)(q * stride) + k]) q++;
+        idx[k] = q;
+      }
+      mine[idx[0] + P[0] * (idx[1] + P[1] * idx[2])].push_back(i);
+      if (atom->tag[i] > maxtag) maxtag = atom->tag[i];
+    }
+    tag2idx.assign((size_t)maxtag + 1, -1);
+    for (int i = 0; i < n; i++) tag2idx[atom->tag[i]] = i;
+    all([&](sphbvf_ctx *c, int r) {
+      const std::vector<int> &ix = mine[r];
+      const int m = (int)ix.size();
+      std::vector<int> tag(m), type(m), mask(m), solid(m), fixed(m);
+      std::vector<double> x(3 * (size_t)m), v(3 * (size_t)m), vest(3 * (size_t)m), rho(m), rhoI(m), e(m),
+          C((size_t)(S ? S : 1) * m), dev(9 * (size_t)m);
+      for (int q = 0; q < m; q++) {
+        const int i = ix[q];
+        tag[q] = atom->tag[i]; type[q] = atom->type[i]; mask[q] = atom->mask[i];
+        solid[q] = atom->solid_tag[i]; fixed[q] = atom->fixed_tag[i];
+        for (int k = 0; k < 3; k++) { x[3 * (size_t)q + k] = atom->x[i][k]; v[3 * (size_t)q + k] = atom->v[i][k]; vest[3 * (size_t)q + k] = atom->vest[i][k]; }
+        rho[q] = atom->rho[i]; rhoI[q] = atom->rhoI[i]; e[q] = atom->e[i];
+        for (int k = 0; k < S; k++) C[(size_t)q * S + k] = atom->C[i][k];
+        for (int k = 0; k < 9; k++) dev[9 * (size_t)q + k] = (&atom->deviatoricTensor[i][0][0])[k];
+      }
+      int rc = sphbvf_set_atoms(c, m, tag.data(), type.data(), mask.data(), solid.data(), fixed.data(), x.data(), v.data(),
+                                rho.data(), e.data(), S ? C.data() : NULL, dev.data());
+      if (rc || !m) return rc;
+      if ((rc = sphbvf_upload(c, SPHBVF_F_VEST, vest.data()))) return rc;
+      return sphbvf_upload(c, SPHBVF_F_RHOI, rhoI.data());
+    });
   }
   // stochastic stress (active only if some ssa_tsdpd/e != 0): kB of the unit system and a seed; upstream
   // seeds from clock() (pair_ssa_tsdpd_bvf_transport_velocity.cpp:957-959), here runs are reproducible
@@ -155,15 +366,26 @@ void SphbvfLmp::start()
   {
     const char *env = getenv("SPHBVF_SEED");
     const unsigned long long seed = env ? strtoull(env, NULL, 10) : 20261018ULL;
-    check(sphbvf_set_random(ctx, force->boltz, seed));
+    const double kb = force->boltz;
+    const long step = (long)update->ntimestep, nsteps = (long)update->nsteps;
+    all([&](sphbvf_ctx *c, int) {
+      int rc;
+      if ((rc = sphbvf_set_random(c, kb, seed))) return rc;
+      if ((rc = sphbvf_set_timestep(c, step))) return rc;
+      if ((rc = sphbvf_set_run_length(c, nsteps))) return rc;
+      return sphbvf_setup_neighbors(c);
+    });
   }
-  check(sphbvf_set_timestep(ctx, (long)update->ntimestep));
-  check(sphbvf_set_run_length(ctx, (long)update->nsteps));
-  check(sphbvf_setup_neighbors(ctx));
   nlocal_uploaded = n;
   host_current = 0;
   // the host copy is stale from now on: LAMMPS must not reorder it behind the device's back
   atom->sortfreq = 0;
+  if (nranks > 1 && comm->me == 0) {
+    char msg[128];
+    snprintf(msg, sizeof msg, "sphbvf: %d GPUs, brick grid %d x %d x %d\n", nranks, cfg.procgrid[0], cfg.procgrid[1], cfg.procgrid[2]);
+    if (screen) fputs(msg, screen);
+    if (logfile) fputs(msg, logfile);
+  }
 }
 
 /* ---------------------------------------------------------------------- */
@@ -173,6 +395,12 @@ void SphbvfLmp::to_host()
   if (!ctx || host_current) return;
   const int n = atom->nlocal, S = atom->num_sdpd_species;
   if (n != nlocal_uploaded) error->one(FLERR, "Atom count changed during a /cuda run");
+  if (nranks > 1) {
+    to_host_multi();
+    host_current = 1;
+    ndownloads++;
+    return;
+  }
   if (n) {
     check(sphbvf_download(ctx, SPHBVF_F_X, &atom->x[0][0]));
     check(sphbvf_download(ctx, SPHBVF_F_V, &atom->v[0][0]));
@@ -200,6 +428,66 @@ void SphbvfLmp::to_host()
   }
   host_current = 1;
   ndownloads++;
+}
+
+/* ----------------------------------------------------------------------
+   several GPUs: atoms have migrated between bricks, so every rank hands back its rows in device order together
+   with their tags and the rows are scattered into the host arrays by tag
+------------------------------------------------------------------------- */
+
+void SphbvfLmp::to_host_multi()
+{
+  const int S = atom->num_sdpd_species;
+  struct Field { int id, ncols; double *host; };
+  std::vector<Field> fields;
+  fields.push_back({SPHBVF_F_X, 3, &atom->x[0][0]});
+  fields.push_back({SPHBVF_F_V, 3, &atom->v[0][0]});
+  fields.push_back({SPHBVF_F_VEST, 3, &atom->vest[0][0]});
+  fields.push_back({SPHBVF_F_F, 3, &atom->f[0][0]});
+  fields.push_back({SPHBVF_F_RHO, 1, atom->rho});
+  fields.push_back({SPHBVF_F_RHOI, 1, atom->rhoI});
+  fields.push_back({SPHBVF_F_DRHO, 1, atom->drho});
+  fields.push_back({SPHBVF_F_PHI, 1, atom->phi});
+  fields.push_back({SPHBVF_F_NUMBER_DENSITY, 1, atom->number_density});
+  fields.push_back({SPHBVF_F_NW, 3, &atom->nw[0][0]});
+  fields.push_back({SPHBVF_F_DDV, 3, &atom->ddv[0][0]});
+  fields.push_back({SPHBVF_F_RHOAUX1, 1, atom->rhoAux1});
+  fields.push_back({SPHBVF_F_RHOAUX2, 1, atom->rhoAux2});
+  fields.push_back({SPHBVF_F_DEV, 9, &atom->deviatoricTensor[0][0][0]});
+  fields.push_back({SPHBVF_F_DDEV, 9, &atom->ddeviatoricTensor[0][0][0]});
+  if (variant != SPHBVF_TV) {
+    fields.push_back({SPHBVF_F_DDX, 3, &atom->ddx[0][0]});
+    fields.push_back({SPHBVF_F_PNEW, 1, atom->Pnew});
+  }
+  if (S) {
+    fields.push_back({SPHBVF_F_C, S, &atom->C[0][0]});
+    fields.push_back({SPHBVF_F_Q, S, &atom->Q[0][0]});
+  }
+  std::vector<int> count(nranks, 0);
+  all([&](sphbvf_ctx *c, int r) {
+    // each rank scatters its own rows: distinct tags, so the writes of different ranks never overlap
+    const int m = sphbvf_nlocal(c);
+    count[r] = m;
+    if (!m) return 0;
+    std::vector<int> tag(m);
+    int rc = sphbvf_download_local(c, SPHBVF_F_TAG, tag.data(), m);
+    if (rc) return rc;
+    std::vector<double> buf(9 * (size_t)m);
+    for (size_t q = 0; q < fields.size(); q++) {
+      const int nc = fields[q].ncols;
+      if ((size_t)nc * m > buf.size()) buf.resize((size_t)nc * m);
+      if ((rc = sphbvf_download_local(c, fields[q].id, buf.data(), m))) return rc;
+      double *host = fields[q].host;
+      for (int a = 0; a < m; a++) {
+        const int i = tag2idx[tag[a]];
+        for (int k = 0; k < nc; k++) host[(size_t)i * nc + k] = buf[(size_t)a * nc + k];
+      }
+    }
+    return 0;
+  });
+  bigint tot = 0;
+  for (int r = 0; r < nranks; r++) tot += count[r];
+  if (tot != atom->nlocal) error->one(FLERR, "Atoms lost or duplicated between the GPUs of a /cuda run");
 }
 
 /* ----------------------------------------------------------------------
@@ -250,6 +538,8 @@ void SphbvfLmp::stop()
     if (logfile) fputs(msg, logfile);
   }
   to_host();
-  sphbvf_destroy(ctx);
+  if (nranks == 1) sphbvf_destroy(ctx);
+  else workers->run([&](int r) { sphbvf_destroy(ctxs[r]); return 0; });   // on the thread that owns the device
+  ctxs.clear();
   ctx = NULL;
 }

@@ -4,6 +4,12 @@
    uploads the atoms of class Atom when a run starts, and copies device state back into the
    host arrays only when LAMMPS is about to read them (thermo / dump steps, end of run).
 
+   One LAMMPS process (comm->nprocs == 1) drives ALL GPUs of the box: the engine owns
+   one sphbvf_ctx per GPU, each a rank of the library's brick decomposition (NCCL halo + migration
+   inside libsphbvf.so), and one worker thread per context; every hook fans out to the workers and
+   joins.  SPHBVF_NGPU sets the count (default: all visible GPUs if the system has at least 10^6
+   atoms per GPU, else 1).
+
    These files are meant to be dropped into the reference's src/ (see INTEGRATION.md): they use
    only LAMMPS' public class interfaces of the 22Aug2018 fork and the C ABI -- no CUDA headers.
 ------------------------------------------------------------------------- */
@@ -11,6 +17,8 @@
 #ifndef LMP_SPHBVF_LMP_H
 #define LMP_SPHBVF_LMP_H
 
+#include <functional>
+#include <vector>
 #include "pointers.h"
 #include "sphbvf.h"
 
@@ -43,6 +51,17 @@ class SphbvfLmp : protected Pointers {
   void stop();                  // end of run (Fix::post_run) or destruction: download, destroy ctx
   bool active() const { return ctx != NULL; }
   void check(int rc);           // rc != 0 -> error->one(FLERR, sphbvf_last_error())
+  // ---- fan-out over the GPUs: f(ctx_r, r) on every rank concurrently (worker threads), status codes checked
+  int nranks;
+  std::vector<sphbvf_ctx *> ctxs;
+  void all(const std::function<int(sphbvf_ctx *, int)> &f);
+  void call(int (*fn)(sphbvf_ctx *)) { all([fn](sphbvf_ctx *c, int) { return fn(c); }); }
+  void set_timestep(bigint n) { all([n](sphbvf_ctx *c, int) { return sphbvf_set_timestep(c, (long)n); }); }
+  void set_dt(double dt) { all([dt](sphbvf_ctx *c, int) { return sphbvf_set_dt(c, dt); }); }
+  void neighbor_step(int *rebuilt);
+  void virial(double *v6);                    // summed over the ranks
+  void ke_tensor(int groupbit, double *t6);   // summed over the ranks
+  double max_vsq(int groupbit);
   void to_host();               // device -> class Atom arrays (all fields the package owns)
   void mark_dirty() { host_current = 0; }
   bool host_is_current() const { return host_current != 0; }
@@ -55,6 +74,9 @@ class SphbvfLmp : protected Pointers {
  private:
   int host_current;
   int nlocal_uploaded;
+  class SphbvfWorkers *workers;
+  std::vector<int> tag2idx;   // atom tag -> row of the host arrays (multi-GPU: atoms migrate between ranks)
+  void to_host_multi();
   bigint ndownloads, ndevice_thermo, nskipped;   // statistics printed at the end of a run (SPHBVF_VERBOSE)
 };
 

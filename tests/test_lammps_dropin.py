@@ -365,6 +365,22 @@ def run_deck(exe, deck, extra):
 
 @pytest.mark.parametrize("name", sorted(DECKS))
 def test_deck_unchanged_with_sf_cuda(name):
+    _check_deck(name)
+
+
+@pytest.mark.parametrize("name", ["cavity3d", "cavity2d", "fsi2d", "ring2d", "natconv2d"])
+def test_deck_unchanged_on_two_gpus(name, monkeypatch):
+    """One LAMMPS process (one MPI rank) driving two GPUs: the engine splits the atoms into bricks, one context and
+    one worker thread per GPU, NCCL halo / migration inside the library; same decks, same bar."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("SPHBVF_NGPU", "2")
+    out = _check_deck(name)
+    assert "sphbvf: 2 GPUs" in out, out[-1500:]
+
+
+def _check_deck(name):
     if not (os.path.exists(REF) and os.path.exists(CUDA)):
         pytest.skip("lmp_serial / lmp_cuda not built (make -C oracle ref; make -C sph-bvf_b200/lammps)")
     wd_ref, out_ref = run_deck(REF, DECKS[name], [])
@@ -416,6 +432,7 @@ def test_deck_unchanged_with_sf_cuda(name):
             worst[c] = max(worst.get(c, 0.0), err)
     bad = {c: e for c, e in worst.items() if e > TOL}
     assert not bad, "%s: columns beyond %g: %s (all: %s)" % (name, TOL, bad, worst)
+    return out_cuda
 
 
 # ---------------------------------------------------------------------------------------------
