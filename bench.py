@@ -22,6 +22,9 @@ kernel): algorithmic bytes 240 B/atom-step (124 + 116) over its CU
 /root/reference) timed on one host core on a bounded sample (smaller n, same deck); if that binary
 did not travel, the plain-C oracle port is timed instead and says so.
 
+`lammps_dropin` (N=1 only, extra key) = the same deck at n=160 as an UNMODIFIED LAMMPS input through
+`lmp_cuda -sf cuda` (the /cuda style classes over the C ABI), LAMMPS' own Loop time.
+
 --impl reference runs only that CPU arm (rank 0) and prints the same line shape.
 """
 import argparse
@@ -179,6 +182,29 @@ def time_reference(n, steps, warm):
     return len(a["tag"]) * steps / dt, "port", len(a["tag"])
 
 
+def time_lmp_cuda(n, steps, warm, ngpu=1):
+    """atom-steps/s of REF_DECK run unmodified through lmp_cuda -sf cuda (Loop time of the 2nd run); None if not built"""
+    exe = os.path.join(ROOT, "sph-bvf_b200", "lammps", "_build", "lmp_cuda")
+    if not os.path.exists(exe):
+        return None
+    try:
+        with tempfile.TemporaryDirectory() as wd:
+            with open(os.path.join(wd, "in.lmp"), "w") as fh:
+                fh.write(REF_DECK.format(n=n, steps=steps, warm=warm))
+            env = dict(os.environ, SPHBVF_NGPU=str(ngpu))
+            out = subprocess.run([exe, "-in", "in.lmp", "-log", "none", "-echo", "none", "-sf", "cuda"], cwd=wd, env=env,
+                                 capture_output=True, text=True, timeout=1200)
+            loops = re.findall(r"Loop time of ([0-9.eE+-]+) on (\d+) procs for (\d+) steps with (\d+) atoms", out.stdout)
+            if out.returncode != 0 or not loops:
+                return {"value": None, "error": (out.stdout[-300:] + out.stderr[-300:])}
+            t, _, st, atoms = loops[-1]
+            return {"value": int(atoms) * int(st) / float(t), "unit": "atom-steps/s", "atoms": int(atoms), "steps": int(st),
+                    "n_gpus": ngpu, "how": "unmodified LAMMPS deck through lmp_cuda -sf cuda, one LAMMPS process; LAMMPS' own "
+                                           "Loop time (state device resident between the upload in setup and the download after the run)"}
+    except Exception as ex:  # noqa: BLE001
+        return {"value": None, "error": repr(ex)}
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, dev):
         super().__init__(daemon=True)
@@ -223,6 +249,8 @@ def main():
     ap.add_argument("--ref-n", type=int, default=40, help="lattice edge of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-lammps", action="store_true", help="skip the lmp_cuda drop-in leg")
+    ap.add_argument("--lammps-n", type=int, default=160, help="lattice edge of the lmp_cuda drop-in leg")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -383,6 +411,12 @@ def main():
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": "atom-steps/s", "cores": 1, "kind": "reference", "sample": "failed: %r" % (ex,)}
 
+    # drop-in leg: the same deck as an unmodified LAMMPS input through `lmp_cuda -sf cuda` (one LAMMPS process, the
+    # /cuda style classes of sph-bvf_b200/lammps over the C ABI): LAMMPS' own "Loop time" of the second `run`
+    dropin = None
+    if rank == 0 and world == 1 and not args.no_lammps:
+        dropin = time_lmp_cuda(args.lammps_n, 50, 10)
+
     if rank == 0:
         time.sleep(0.3)
         line = {"metric": "atom-steps/sec", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -392,7 +426,7 @@ def main():
                            "l2": "inputs larger than L2 (state >> 126 MB), no explicit flush",
                            "rebuild": "every 10 steps (delay 10, skin 0.01h), inside the timed region"},
                 "gpu_launches": int(launches), "kernels": fam, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
-                "clocks": sampler.summary(), "maxneigh": None}
+                "clocks": sampler.summary(), "lammps_dropin": dropin}
         print(json.dumps(line))
     eng.close()
     if world > 1:
