@@ -38,7 +38,7 @@ namespace sphbvf {
 #define PAIR_TMA 0    // D > 0: neighbour records travel global -> shared memory as per-lane bulk copies (TMA engine,
 #endif                // mbarrier completion), D records in flight per thread, no record buffers in registers
 #ifndef PAIR_MINB
-#define PAIR_MINB (PAIR_PIPE == 2 ? 2 : 3)
+#define PAIR_MINB (PAIR_PIPE == 2 ? 2 : (PAIR_PIPE == 0 ? 4 : 3))
 #endif
 #ifndef PAIR_T
 #define PAIR_T (PAIR_PIPE == 2 ? 160 : 128)   // threads per CTA: MINB x PAIR_T x registers <= 64 K
@@ -616,7 +616,29 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   // full memory latency exposed on every second visit (ncu source page: one DADD held 33 % of all stall samples).
   // The loads of record k+1 are therefore made DATA dependent on the first use of record k (`gate`: a NaN test the
   // compiler cannot fold), so they are issued right after record k has arrived and have a whole visit to complete.
-#if PAIR_PIPE == 2
+#if PAIR_PIPE == 0
+  // No register pipeline at all: one record buffer, the latency of every record is covered by other warps only
+  // (<= 128 registers -> four CTAs, 16 warps per SM).
+  for (int kk = 0; kk < nn; kk += 2) {
+    fetch2(kk + RING);
+    asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");
+    const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * PAIR_T] : 0;
+    const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * PAIR_T] : 0;
+    {
+      const Prec *p = d.prec + (e0 & NEIGH_JMASK);
+      const Rec4 A = ld_rec(&p->A), B = ld_rec(&p->B), C = ld_rec(&p->C);
+      visit(e0, A, B, C, FILTER ? d.pD[e0 & NEIGH_JMASK].x : 0.0);
+    }
+    if (kk + 1 < nn) {
+      const Prec *p = d.prec + (e1 & NEIGH_JMASK);
+      const Rec4 A = ld_rec(&p->A), B = ld_rec(&p->B), C = ld_rec(&p->C);
+      visit(e1, A, B, C, FILTER ? d.pD[e1 & NEIGH_JMASK].x : 0.0);
+    }
+    e0 = e2;
+    e1 = e3;
+  }
+
+#elif PAIR_PIPE == 2
   // Two records in flight per warp: the records of the NEXT TWO neighbours are requested (one batch of six loads, gated
   // on the first use of the current pair so that the single scoreboard wait of the loop covers exactly one batch) while
   // the current two are evaluated.  Four record buffers: ~210 registers, two CTAs per SM -- 8 warps x 2 records = 16
