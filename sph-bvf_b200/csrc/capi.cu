@@ -335,7 +335,7 @@ static int rebuild(sphbvf_ctx *ctx) {
   if (d.nlocal + nghost > d.nallmax)
     if ((rc = ensure_capacity(ctx, d.nmax, d.nlocal + nghost + nghost / 4 + 1024))) return rc;
   d.nghost = nghost;
-  launch_fill_images(d, ctx->box, ctx->cutneighmax, w, st);
+  if (nghost) launch_fill_images(d, ctx->box, ctx->cutneighmax, w, st);   // 27 shift tests per atom: skip without images
   CK(cudaMemcpyAsync(d.ptag, d.tag, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
   launch_pack(d, co, ctx->with_dev, st);
   launch_ghost_refresh(d, co, ctx->with_dev, st);

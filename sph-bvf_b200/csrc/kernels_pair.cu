@@ -30,18 +30,29 @@
 
 namespace sphbvf {
 
-// resident CTAs per SM the pair kernel is compiled for: 3 -> 168 registers (no spills), 4 -> 128
+// ---- compile-time tuning switches.  The defaults are what ships; every other setting is a measured and rejected
+// experiment kept buildable so that it can be re-measured (tools/build_variant.sh; pair kernel ms
+// at 8 M atoms on one B200, default 5.71):
+//   PAIR_PIPE      records in flight per warp in the register pipeline: 0 = none (one buffer, 128 registers, 16 warps
+//                  per SM: 7.01), 1 = default (two buffers, 160 registers, 12 warps), 2 = two (four buffers, 204
+//                  registers, 8 warps: 6.34)
+//   PAIR_TMA = D   records through the bulk-copy engine into a shared-memory ring D deep (16.3 with D = 4)
+//   PAIR_L2HINT    evict-first on the list / output streams (1) and evict-last on the record gathers (2): 5.84 / 5.90
+//   PAIR_PFL2 = D  prefetch.global.L2 of the records 2 D entries ahead: 7.33 with D = 2
+//   PAIR_DIAG_SMEM ballast dynamic shared memory (occupancy probe: 7.70 at 2 CTAs, 13.4 at 1 CTA per SM)
+//   PAIR_MINB / PAIR_T  resident CTAs per SM the kernel is compiled for / threads per CTA (MINB x T x registers <= 64 K,
+//                  split over four register files: only 8 / 12 / 16 warps at <= 255 / 168 / 128 registers exist)
 #ifndef PAIR_PIPE
-#define PAIR_PIPE 1   // records in flight per warp: 1 (two buffers, 3 CTAs/SM) or 2 (four buffers, 2 CTAs/SM)
+#define PAIR_PIPE 1
 #endif
 #ifndef PAIR_TMA
-#define PAIR_TMA 0    // D > 0: neighbour records travel global -> shared memory as per-lane bulk copies (TMA engine,
-#endif                // mbarrier completion), D records in flight per thread, no record buffers in registers
+#define PAIR_TMA 0
+#endif
 #ifndef PAIR_MINB
 #define PAIR_MINB (PAIR_PIPE == 2 ? 2 : (PAIR_PIPE == 0 ? 4 : 3))
 #endif
 #ifndef PAIR_T
-#define PAIR_T (PAIR_PIPE == 2 ? 160 : 128)   // threads per CTA: MINB x PAIR_T x registers <= 64 K
+#define PAIR_T 128
 #endif
 
 // one row per (type_i, type_j); 8 doubles = 64 B so a row is two LDS.128 x2
