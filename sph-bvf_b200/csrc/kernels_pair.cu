@@ -48,11 +48,11 @@ namespace sphbvf {
 #ifndef PAIR_TMA
 #define PAIR_TMA 0
 #endif
-#ifndef PAIR_MINB
-#define PAIR_MINB (PAIR_PIPE == 2 ? 2 : (PAIR_PIPE == 0 ? 4 : 3))
-#endif
 #ifndef PAIR_T
-#define PAIR_T 128
+#define PAIR_T (PAIR_PIPE == 1 ? 192 : 128)   // 12 warps as 2 x 192 threads: 5.63 (3 x 128: 5.71, 6 x 64: 5.73, 1 x 384: 5.66)
+#endif
+#ifndef PAIR_MINB
+#define PAIR_MINB (PAIR_PIPE == 2 ? 2 : (PAIR_PIPE == 0 ? 4 : (PAIR_T == 192 ? 2 : 3)))
 #endif
 
 // one row per (type_i, type_j); 8 doubles = 64 B so a row is two LDS.128 x2
