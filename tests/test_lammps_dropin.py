@@ -368,7 +368,7 @@ def test_deck_unchanged_with_sf_cuda(name):
     _check_deck(name)
 
 
-@pytest.mark.parametrize("name", ["cavity3d", "cavity2d", "fsi2d", "ring2d", "natconv2d"])
+@pytest.mark.parametrize("name", ["cavity3d", "cavity2d", "fsi2d", "ring2d", "natconv2d", "react2d"])
 def test_deck_unchanged_on_two_gpus(name, monkeypatch):
     """One LAMMPS process (one MPI rank) driving two GPUs: the engine splits the atoms into bricks, one context and
     one worker thread per GPU, NCCL halo / migration inside the library; same decks, same bar."""
