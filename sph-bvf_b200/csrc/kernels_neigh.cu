@@ -292,7 +292,14 @@ void launch_bin_ghosts(const DevState &d, const Grid &g, const NeighWork &w, cud
 //     atom's position.  Kept as the cross-check of (A) (tests/test_gpu_parity.py) and for A/B timing.
 // Ghosts live in their own cell table (gcell_start / gorder).
 
-constexpr int TB_T = 224;                     // threads per CTA: a bulk 3D tile holds 125..216 atoms (one batch)
+#ifndef TB_THREADS
+#define TB_THREADS 224
+#endif
+#ifndef TB_UNROLL
+#define TB_UNROLL 4
+#endif
+constexpr int TB_U = TB_UNROLL;               // unroll factor of the sweep
+constexpr int TB_T = TB_THREADS;              // threads per CTA: a bulk 3D tile holds 125..216 atoms (one batch)
 constexpr int TB_CH = 1536;                   // staged candidates per chunk (48 KB, dynamic): a bulk halo is <= 11^3
 constexpr int TB_NH = 1;                      // 2: stage the halo as two y-halves (24 KB chunks, 8 CTAs/SM): measured slower
 constexpr int TB_MAXROW = 64;                 // (y,z) rows of the halo: 8 x 8 in 3D, 12 x 1 in 2D
@@ -439,7 +446,7 @@ build_list_tile_kernel(const DevState d, const __grid_constant__ Grid g, const _
         __syncthreads();
         // ---- converged sweep with the exact criterion
         const int qa = max(wq0, clo) - clo, qb = min(wq1, chi) - clo;
-#pragma unroll 4
+#pragma unroll TB_U
         for (int q = qa; q < qb; q++) {
           const double2 cxy = cand[q].xy, cze = cand[q].ze;
           const int ent = __double2loint(cze.y);
