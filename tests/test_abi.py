@@ -112,3 +112,18 @@ def test_comm_plan_is_symmetric():
                 back_peer, back_shift = plans[peer[d]]
                 assert back_peer[26 - d] == r
                 assert np.array_equal(back_shift[26 - d], -shift[d])
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/sphbvf.h is the drop-in boundary: it must compile as C99 with nothing but the C library, declare
+    every function with C linkage only, and use no C++ or CUDA types."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "sphbvf.h"\nint main(void) { sphbvf_config c; (void)c; return sphbvf_version() < 0; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, "sphbvf.h")).read(), flags=re.S)   # code only
+    for bad in ("cuda", "torch", "std::", "class ", "template", "#include <c"):
+        assert bad not in text.replace("SPHBVF_ECUDA", ""), bad
