@@ -275,6 +275,12 @@ def main():
         print(json.dumps(line))
         return
 
+    # ONE JSON line on stdout: everything else that may write to file descriptor 1 (NCCL prints its version banner
+    # there from C) goes to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     pkg = load_package()
@@ -427,7 +433,8 @@ def main():
                            "rebuild": "every 10 steps (delay 10, skin 0.01h), inside the timed region"},
                 "gpu_launches": int(launches), "kernels": fam, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
                 "clocks": sampler.summary(), "lammps_dropin": dropin}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     eng.close()
     if world > 1:
         dist.destroy_process_group()
