@@ -50,6 +50,7 @@ class SphbvfWorkers {
     cv_.notify_all();
     for (size_t r = 0; r < th_.size(); r++) th_[r].join();
   }
+  int size() const { return n_; }
   const std::vector<int> &run(const std::function<int(int)> &f)
   {
     std::unique_lock<std::mutex> lk(m_);
@@ -249,8 +250,8 @@ void SphbvfLmp::start()
     for (int k = 0; k < 3; k++) cfg.procgrid[k] = grid[k];
   }
   cfg.nranks = nranks;
+  if (workers && workers->size() != nranks) { delete workers; workers = NULL; }   // GPU count changed between runs
   if (nranks > 1 && !workers) workers = new SphbvfWorkers(nranks);
-  if (workers && nranks == 1) { delete workers; workers = NULL; }
 
   // ---- one context per GPU, created on the worker thread that will drive it (cudaSetDevice is per thread)
   ctxs.assign(nranks, (sphbvf_ctx *)NULL);
