@@ -19,8 +19,10 @@ the library's stream), inputs resident in HBM.  `e2e` = same metric through the 
 device->host inside the timed region.  `roofline` is for the dominant kernel (the fused pair
 kernel): algorithmic bytes 240 B/atom-step (124 + 116) over its CUDA-event time.
 `cpu_baseline` = the UNMODIFIED reference (oracle/_ref/lmp_serial, built by oracle/Makefile from
-/root/reference) timed on one host core on a bounded sample (smaller n, same deck); if that binary
-did not travel, the plain-C oracle port is timed instead and says so.
+/root/reference) on ALL host cores on a bounded sample (smaller n, same deck): the reference is MPI-parallel
+only and the image has no MPI runtime, so one single-rank replica runs per core and the aggregate is reported
+(an upper bound for one MPI job); if that binary did not travel, the plain-C oracle port is timed instead
+(one core) and says so.
 
 `lammps_dropin` (N=1 only, extra key) = the same deck at n=160 as an UNMODIFIED LAMMPS input through
 `lmp_cuda -sf cuda` (the /cuda style classes over the C ABI), LAMMPS' own Loop time.
@@ -153,20 +155,38 @@ run {steps}
 """
 
 
-def time_reference(n, steps, warm):
-    """atom-steps/s of the unmodified reference CPU path on one host core (Loop time of the 2nd run)."""
+def host_cores():
+    try:
+        return max(1, min(128, len(os.sched_getaffinity(0))))
+    except AttributeError:
+        return max(1, min(128, os.cpu_count() or 1))
+
+
+def time_reference(n, steps, warm, procs=1):
+    """atom-steps/s of the unmodified reference CPU path (Loop time of the 2nd run).  The reference is MPI-parallel
+    only (no threaded variant of these styles) and the image has no MPI runtime, so "all host cores" is `procs`
+    independent single-rank replicas of the same deck running at the same time, one per core; the aggregate is an
+    upper bound for what one MPI job over the same cores could do (no halo exchange, no load imbalance)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "lmp_serial")
     if os.path.exists(exe):
         with tempfile.TemporaryDirectory() as wd:
-            with open(os.path.join(wd, "in.lmp"), "w") as fh:
-                fh.write(REF_DECK.format(n=n, steps=steps, warm=warm))
-            out = subprocess.run([exe, "-in", "in.lmp", "-log", "none", "-echo", "none"], cwd=wd,
-                                 capture_output=True, text=True, timeout=3000)
-            loops = re.findall(r"Loop time of ([0-9.eE+-]+) on (\d+) procs for (\d+) steps with (\d+) atoms", out.stdout)
-            if out.returncode != 0 or not loops:
-                raise RuntimeError("lmp_serial failed: " + out.stdout[-400:] + out.stderr[-400:])
-            t, _, st, atoms = loops[-1]
-            return int(atoms) * int(st) / float(t), "reference", int(atoms)
+            jobs = []
+            for p in range(procs):
+                sub = os.path.join(wd, "r%d" % p)
+                os.makedirs(sub)
+                with open(os.path.join(sub, "in.lmp"), "w") as fh:
+                    fh.write(REF_DECK.format(n=n, steps=steps, warm=warm))
+                jobs.append(subprocess.Popen([exe, "-in", "in.lmp", "-log", "none", "-echo", "none"], cwd=sub,
+                                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+            total, atoms = 0.0, 0
+            for j in jobs:
+                so, se = j.communicate(timeout=3000)
+                loops = re.findall(r"Loop time of ([0-9.eE+-]+) on (\d+) procs for (\d+) steps with (\d+) atoms", so)
+                if j.returncode != 0 or not loops:
+                    raise RuntimeError("lmp_serial failed: " + so[-400:] + se[-400:])
+                t, _, st, atoms = loops[-1]
+                total += int(atoms) * int(st) / float(t)
+            return total, "reference", int(atoms)
     # the reference binary did not travel: time the plain-C restatement instead
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_api import Oracle
@@ -263,14 +283,19 @@ def main():
         if rank != 0:
             return
         ref_steps = max(1, min(K, 5))
-        val, kind, atoms = time_reference(args.ref_n, ref_steps, 1)
+        cores = host_cores()
+        val, kind, atoms = time_reference(args.ref_n, ref_steps, 1, cores)
+        if kind != "reference":
+            cores = 1
         line = {"impl": "reference", "metric": "atom-steps/sec", "value": val, "unit": "atom-steps/s", "n_gpus": args.gpus,
-                "steps": K, "warmup": W, "ms_per_step": 1e3 * atoms / val, "higher_is_better": True, "scaling": "weak",
+                "steps": K, "warmup": W, "ms_per_step": 1e3 * atoms * cores / val, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "cpu_sample": "%d^3 = %d atoms, %d timed steps" % (args.ref_n, atoms, ref_steps)},
-                "cpu_baseline": {"value": val, "unit": "atom-steps/s", "cores": 1, "kind": kind,
-                                 "sample": "same deck at n=%d (%d atoms), %d steps, 1 rank x 1 thread (no MPI runtime / no "
-                                           "OpenMP variant of these styles exists)" % (args.ref_n, atoms, ref_steps)},
+                "config": {"workload": workload, "cpu_sample": "%d replicas x %d^3 = %d atoms, %d timed steps" % (cores, args.ref_n, atoms, ref_steps)},
+                "cpu_baseline": {"value": val, "unit": "atom-steps/s", "cores": cores, "kind": kind,
+                                 "sample": "%d independent single-rank replicas of the same deck at n=%d (%d atoms each), one per "
+                                           "host core, %d steps: aggregate throughput, an upper bound for one MPI job on these cores "
+                                           "(no MPI runtime in the image, no threaded variant of these styles)"
+                                           % (cores, args.ref_n, atoms, ref_steps)},
                 "e2e": {"value": val, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -411,9 +436,14 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu and world == 1:
         try:
-            val, kind, ca = time_reference(args.ref_n, 3, 1)
-            cpu = {"value": val, "unit": "atom-steps/s", "cores": 1, "kind": kind,
-                   "sample": "same deck at n=%d (%d atoms), 3 timed steps after 1, 1 rank x 1 thread" % (args.ref_n, ca)}
+            cores = host_cores()
+            val, kind, ca = time_reference(args.ref_n, 3, 1, cores)
+            if kind != "reference":
+                cores = 1
+            cpu = {"value": val, "unit": "atom-steps/s", "cores": cores, "kind": kind,
+                   "sample": "%d independent single-rank replicas of the same deck at n=%d (%d atoms each), one per host core, "
+                             "3 timed steps after 1: aggregate throughput (upper bound for one MPI job on these cores)"
+                             % (cores, args.ref_n, ca)}
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": "atom-steps/s", "cores": 1, "kind": "reference", "sample": "failed: %r" % (ex,)}
 
