@@ -29,7 +29,7 @@
 #define SMALL 1.0e-6          /* nbin_standard.cpp:29 */
 #define CUT2BIN_RATIO 100     /* nbin_standard.cpp:30 */
 
-enum { FIX_BUOYANCY, FIX_FORCING, FIX_BUFFER, FIX_SETFORCE };
+enum { FIX_BUOYANCY, FIX_FORCING, FIX_BUFFER, FIX_SETFORCE, FIX_CHEMRXN };
 
 typedef struct {
   int kind, groupbit;
@@ -218,6 +218,24 @@ int orc_add_buffer(orc_ctx *c, int groupbit, int kind, int axis, long step, int 
 }
 int orc_add_setforce(orc_ctx *c, int groupbit, double fx, double fy, double fz) {
   orc_fix f = {FIX_SETFORCE, groupbit, {0, 0, 0, 0}, 0, {fx, fy, fz, 0, 0, 0}};
+  return add_fix(c, &f);
+}
+
+/* fix ssa_tsdpd/chem_rxn_mass_action k nr r.. np p.. (fix_ssa_tsdpd_chem_rxn_mass_action.cpp:24-54):
+ * a_int = {nreact, nprod, reactants packed one byte each, products packed one byte each} */
+int orc_add_chem_rxn(orc_ctx *c, int groupbit, double k_rate, int nreact, const int *reactants, int nprod,
+                     const int *products) {
+  if (nreact < 0 || nreact > 2 || nprod < 0 || nprod > 4) return fail(c, "Illegal fix ssa_tsdpd_chem_rxn_mass_action command");
+  int r = 0, p = 0;
+  for (int j = 0; j < nreact; j++) {
+    if (reactants[j] < 0 || reactants[j] >= c->cfg.nspecies) return fail(c, "chem_rxn: reactant species out of range");
+    r |= reactants[j] << (8 * j);
+  }
+  for (int j = 0; j < nprod; j++) {
+    if (products[j] < 0 || products[j] >= c->cfg.nspecies) return fail(c, "chem_rxn: product species out of range");
+    p |= products[j] << (8 * j);
+  }
+  orc_fix f = {FIX_CHEMRXN, groupbit, {nreact, nprod, r, p}, 0, {k_rate, 0, 0, 0, 0, 0}};
   return add_fix(c, &f);
 }
 
@@ -991,12 +1009,27 @@ static void post_integrate(orc_ctx *c) {
   }
 }
 
-/* FixSsaTsdpdBuoyancy::post_force (fix_ssa_tsdpd_buoyancy.cpp:113-140), FixSetForce::post_force */
-static void post_force(orc_ctx *c) {
+/* FixSsaTsdpdBuoyancy::post_force (fix_ssa_tsdpd_buoyancy.cpp:113-140), FixSetForce::post_force,
+ * FixSsaTsdpdChemRxnMassAction::post_force (fix_ssa_tsdpd_chem_rxn_mass_action.cpp:76-112).  in_setup: Modify::setup
+ * calls Fix::setup, which only setforce and buoyancy forward to post_force; the reaction fix has no setup(). */
+static void post_force(orc_ctx *c, int in_setup) {
   int S = c->cfg.nspecies;
   for (int q = 0; q < c->nfix; q++) {
     orc_fix *fx = &c->fix[q];
-    if (fx->kind == FIX_BUOYANCY) {
+    if (fx->kind == FIX_CHEMRXN) {
+      if (in_setup) continue;
+      const int nr = fx->a_int[0], np = fx->a_int[1];
+      for (int i = 0; i < c->nlocal; i++) {
+        if (!(c->mask[i] & fx->groupbit)) continue;
+        double *C = c->C + (size_t)S * i, *Q = c->Q + (size_t)S * i;
+        double flux;
+        if (nr == 2) flux = fx->a[0] * C[fx->a_int[2] & 255] * C[(fx->a_int[2] >> 8) & 255];
+        else if (nr == 1) flux = fx->a[0] * C[fx->a_int[2] & 255];
+        else flux = fx->a[0];
+        for (int j = 0; j < nr; j++) Q[(fx->a_int[2] >> (8 * j)) & 255] -= flux;
+        for (int j = 0; j < np; j++) Q[(fx->a_int[3] >> (8 * j)) & 255] += flux;
+      }
+    } else if (fx->kind == FIX_BUOYANCY) {
       for (int i = 0; i < c->nlocal; i++) {
         if (!(c->mask[i] & fx->groupbit)) continue;
         double m = c->mass[c->type[i]];
@@ -1055,7 +1088,7 @@ int orc_setup(orc_ctx *c) {
   setup_pre_force(c);
   pair_compute(c);
   reverse_comm(c);
-  post_force(c);       /* modify->setup -> FixSetForce::setup / FixSsaTsdpdBuoyancy::setup */
+  post_force(c, 1);    /* modify->setup -> FixSetForce::setup / FixSsaTsdpdBuoyancy::setup */
   c->setup_done = 1;
   return 0;
 }
@@ -1078,7 +1111,7 @@ int orc_run(orc_ctx *c, int nsteps) {
     force_clear(c);
     pair_compute(c);
     reverse_comm(c);
-    post_force(c);
+    post_force(c, 0);
     final_integrate(c);
     end_of_step(c);
   }

@@ -62,6 +62,9 @@ int orc_add_buffer(orc_ctx *c, int groupbit, int kind, int axis, long step, int 
                    double cy, double length, double width, double value);
 /* LAMMPS core fix setforce with three constants (fix_setforce.cpp post_force) */
 int orc_add_setforce(orc_ctx *c, int groupbit, double fx, double fy, double fz);
+/* fix ssa_tsdpd/chem_rxn_mass_action (fix_ssa_tsdpd_chem_rxn_mass_action.cpp:24-112): post_force source term on Q */
+int orc_add_chem_rxn(orc_ctx *c, int groupbit, double k_rate, int nreact, const int *reactants, int nprod,
+                     const int *products);
 
 int orc_setup(orc_ctx *c);              /* Verlet::setup  (verlet.cpp:88-170) */
 int orc_run(orc_ctx *c, int nsteps);    /* Verlet::run    (verlet.cpp:223-354), setup must precede */

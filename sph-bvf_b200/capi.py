@@ -154,6 +154,10 @@ class Engine:
                                              fx["cx"], fx["cy"], fx["length"], fx["width"], fx["value"]))
             elif k == "setforce":
                 self._ck(L.sphbvf_add_setforce(self.h, fx["groupbit"], fx["fx"], fx["fy"], fx["fz"]))
+            elif k == "chem_rxn":
+                r = np.asarray(fx["reactants"], dtype=np.int32)
+                p = np.asarray(fx["products"], dtype=np.int32)
+                self._ck(L.sphbvf_add_chem_rxn(self.h, fx["groupbit"], fx["k"], len(r), _p(r), len(p), _p(p)))
 
     def _ck(self, rc):
         if rc != 0:

@@ -241,6 +241,12 @@ def parse_run(workdir, S, ntypes):
                                           width=float(a[7]), value=float(a[8])))
             elif style == "setforce":
                 meta["fixes"].append(dict(kind="setforce", groupbit=bit, fx=float(a[0]), fy=float(a[1]), fz=float(a[2])))
+            elif style == "ssa_tsdpd/chem_rxn_mass_action":
+                nr = int(a[1])
+                reactants = [int(v) for v in a[2:2 + nr]]
+                npd = int(a[2 + nr])
+                products = [int(v) for v in a[3 + nr:3 + nr + npd]]
+                meta["fixes"].append(dict(kind="chem_rxn", groupbit=bit, k=float(a[0]), reactants=reactants, products=products))
             elif style == "sphbvf/snapshot":
                 pass
             else:
@@ -302,6 +308,50 @@ def make_case(name, deck_text, nsteps, keep_steps, pair_steps, consistent_ghosts
             os.path.getsize(path) / 1e3))
 
 
+REACT2D = """
+# reaction-diffusion in a wall-bounded 2D box: three species, two mass-action reactions and a zeroth-order source
+# (fix ssa_tsdpd/chem_rxn_mass_action, SURVEY.md 8f-3); fixed timestep so that the plain-C oracle restates it
+dimension 2
+units si
+atom_style ssa_tsdpd/atomic 3 0 0
+boundary f f p
+variable n equal 26
+variable d equal 1.0/(v_n-6)
+variable lo equal -3*v_d
+variable hi equal 1.0+3*v_d
+region box block ${lo} ${hi} ${lo} ${hi} 0 ${d} units box
+create_box 2 box
+lattice sq ${d} origin 0.5 0.5 0.0
+create_atoms 2 box
+region inner block 0 1 0 1 0 ${d} units box
+group fluid region inner
+set group fluid type 1
+group solid subtract all fluid
+mass * $(v_d*v_d)
+set group all ssa_tsdpd/rho 1.0
+set group all ssa_tsdpd/e 0.
+variable ca atom 0.5+0.5*sin(PI*x)
+variable cb atom 0.5+0.5*cos(PI*y)
+set group all ssa_tsdpd/C 0 v_ca
+set group all ssa_tsdpd/C 1 v_cb
+set group all ssa_tsdpd/C 2 0.1
+set group solid ssa_tsdpd/solid_tag 1 fixed
+variable h equal 2.5*v_d
+pair_style ssa_tsdpd/bvf/transportVelocity
+pair_coeff * * 1.0 5.0 1e-2 ${h} ${h} 0.0 0.02 0.01 0.005
+variable ux atom 0.6*sin(PI*x)*cos(PI*y)
+variable uy atom -0.6*cos(PI*x)*sin(PI*y)
+velocity fluid set v_ux v_uy 0.0 units box
+fix integ all ssa_tsdpd/bvf/transportVelocity
+fix rxn1 fluid ssa_tsdpd/chem_rxn_mass_action 0.5 2 0 1 1 2
+fix rxn2 fluid ssa_tsdpd/chem_rxn_mass_action 0.7 1 2 1 0
+fix src fluid ssa_tsdpd/chem_rxn_mass_action 0.05 0 1 1
+neighbor $(0.3*v_h) bin
+timestep 2e-4
+run 0
+"""
+
+
 def ref_deck(rel):
     return open(os.path.join(EX, rel)).read()
 
@@ -343,6 +393,8 @@ def main():
         make_case("synth3d_n14", SYNTH3D.format(n=14, perturb=PERTURB), 12, {0, 1, 2, 12}, {0, 12})
     if want("synth3d_n14_lattice"):
         make_case("synth3d_n14_lattice", SYNTH3D.format(n=14, perturb=""), 2, {0, 1, 2}, {0})
+    if want("react2d_n26"):
+        make_case("react2d_n26", REACT2D, 24, {0, 1, 2, 3, 12, 24}, {0, 24})
     for var, pair, fix in (("tv", "ssa_tsdpd/bvf/transportVelocity", "ssa_tsdpd/bvf/transportVelocity"),
                            ("mech", "ssa_tsdpd/bvf/mechanics", "ssa_tsdpd/bvf/mechanics"),
                            ("fsi", "ssa_tsdpd/bvf/fsi", "ssa_tsdpd/bvf/fsi")):

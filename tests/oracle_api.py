@@ -37,6 +37,7 @@ def lib():
         L.orc_add_forcing.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int] + [C.c_double] * 5
         L.orc_add_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int] + [C.c_double] * 5
         L.orc_add_setforce.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 3
+        L.orc_add_chem_rxn.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         for f in ("orc_setup", "orc_build_neighbors", "orc_pair_compute", "orc_nlocal", "orc_nghost", "orc_nbuilds"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.orc_run.argtypes = [C.c_void_p, C.c_int]
@@ -97,6 +98,10 @@ class Oracle:
                                           fx["cx"], fx["cy"], fx["length"], fx["width"], fx["value"]))
             elif k == "setforce":
                 self._ck(L.orc_add_setforce(self.h, fx["groupbit"], fx["fx"], fx["fy"], fx["fz"]))
+            elif k == "chem_rxn":
+                r = np.asarray(fx["reactants"], dtype=np.int32)
+                p = np.asarray(fx["products"], dtype=np.int32)
+                self._ck(L.orc_add_chem_rxn(self.h, fx["groupbit"], fx["k"], len(r), _p(r), len(p), _p(p)))
 
     def _ck(self, rc):
         if rc != 0:
