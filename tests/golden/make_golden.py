@@ -352,6 +352,52 @@ run 0
 """
 
 
+MIXEDH2D = """
+# 2D wall-bounded box with TYPE-PAIR dependent smoothing lengths, viscosities and masses: exercises the per-pair
+# neighbour cutoffs (neighbor.cpp:278-310) and the non-uniform coefficient path of the pair styles
+dimension 2
+units si
+atom_style ssa_tsdpd/atomic 0 0 0
+boundary f f p
+variable n equal 30
+variable d equal 1.0/(v_n-6)
+variable lo equal -3*v_d
+variable hi equal 1.0+3*v_d
+region box block ${lo} ${hi} ${lo} ${hi} 0 ${d} units box
+create_box 3 box
+lattice sq ${d} origin 0.5 0.5 0.0
+create_atoms 3 box
+region inner block 0 1 0 1 0 ${d} units box
+group fluid region inner
+set group fluid type 1
+region blob sphere 0.5 0.5 0.0 0.25 units box
+group heavy region blob
+set group heavy type 2
+group solid subtract all fluid
+mass 1 $(v_d*v_d)
+mass 2 $(1.5*v_d*v_d)
+mass 3 $(v_d*v_d)
+set group all ssa_tsdpd/rho 1.0
+set group heavy ssa_tsdpd/rho 1.5
+set group all ssa_tsdpd/e 0.
+set group solid ssa_tsdpd/solid_tag 1 fixed
+pair_style ssa_tsdpd/bvf/transportVelocity
+pair_coeff 1 1 1.0 10.0 1e-2 $(2.5*v_d) $(2.5*v_d) 0.0
+pair_coeff 1 2 1.0 10.0 2e-2 $(2.8*v_d) $(2.8*v_d) 0.0
+pair_coeff 1 3 1.0 10.0 1e-2 $(2.5*v_d) $(2.5*v_d) 0.0
+pair_coeff 2 2 1.5 8.0 3e-2 $(3.1*v_d) $(3.1*v_d) 0.0
+pair_coeff 2 3 1.5 8.0 2e-2 $(2.2*v_d) $(2.2*v_d) 0.0
+pair_coeff 3 3 1.0 10.0 1e-2 $(2.5*v_d) $(2.5*v_d) 0.0
+variable ux atom 0.8*sin(PI*x)*cos(PI*y)
+variable uy atom -0.8*cos(PI*x)*sin(PI*y)
+velocity fluid set v_ux v_uy 0.0 units box
+fix integ all ssa_tsdpd/bvf/transportVelocity
+neighbor $(0.02*v_d) bin
+timestep 1e-4
+run 0
+"""
+
+
 def ref_deck(rel):
     return open(os.path.join(EX, rel)).read()
 
@@ -393,6 +439,8 @@ def main():
         make_case("synth3d_n14", SYNTH3D.format(n=14, perturb=PERTURB), 12, {0, 1, 2, 12}, {0, 12})
     if want("synth3d_n14_lattice"):
         make_case("synth3d_n14_lattice", SYNTH3D.format(n=14, perturb=""), 2, {0, 1, 2}, {0})
+    if want("mixedh2d_n30"):
+        make_case("mixedh2d_n30", MIXEDH2D, 24, {0, 1, 2, 3, 12, 24}, {0, 12, 24})
     if want("react2d_n26"):
         make_case("react2d_n26", REACT2D, 24, {0, 1, 2, 3, 12, 24}, {0, 24})
     for var, pair, fix in (("tv", "ssa_tsdpd/bvf/transportVelocity", "ssa_tsdpd/bvf/transportVelocity"),
