@@ -46,8 +46,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 B_ALG_PAIR = 240.0      # algorithmic bytes / atom-step of the pair pass
 B_ALG_STEP = 616.0      # whole step
-F_ALG_PAIR = 1.2e4      # FP64 flop / atom-step, 3D bulk (2.8e3 + 9.2e3)
-TRAFFIC_PAIR_B_PER_ATOM = 605.0   # measured DRAM bytes / atom of pair_kernel (profiles/r01g_pair_and_integrate_n200.txt: 3.95 GB read + 0.88 GB written for 8.0 M atoms)
+F_ALG_PAIR_SURVEY = 1.2e4   # FP64 flop / atom-step, 3D bulk, SURVEY.md 8d's paper estimate (2.8e3 + 9.2e3)
+# FP64 flop / atom-step the kernel really executes, re-derived as SURVEY 8(d) asks from ncu's
+# smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on of one launch at 8.0 M atoms (see PROFILE below):
+# (2 x dfma + dmul + dadd) / atoms.  Updated whenever a new --set full capture is committed under profiles/.
+PROFILE = {"file": "profiles/r01g_pair_and_integrate_n200.txt", "kernel": "pair_kernel<TV,0,1,UNIFORM> (gather form)",
+           "flop_per_atom": 7.70e3, "fp64_inst_per_atom": 5.30e3, "dram_bytes_per_atom": 605.0,
+           "l1_data_pipe_busy": 0.81, "fp64_pipe_busy": 0.46, "issue_active": 0.42, "warps_per_sm": 11.2}
+PARITY_FIXTURES = ["synth3d_n14", "solid3d_mech_n10", "cavity_n50"]   # 3D non-periodic, 3D periodic with free solids, 2D
 WEAK_N = {1: 200, 2: 252, 4: 318, 8: 400}
 
 
@@ -225,10 +231,41 @@ def time_lmp_cuda(n, steps, warm, ngpu=1):
         return {"value": None, "error": repr(ex)}
 
 
+def parity_check(pkg, rank, world, dev, dist):
+    """Golden fixtures of the unmodified reference across the `world` bricks of this launch (tests/brick_parity.py):
+    fields within 1e-10 of the field's max-norm, pair sets bit-exact.  -> dict on rank 0, None elsewhere."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from brick_parity import run_fixture
+    t0 = time.perf_counter()
+    out = {"ranks": world, "tolerance": 1e-10, "fixtures": [], "max_err": 0.0, "pairs_equal": True, "ok": True}
+    for name in PARITY_FIXTURES:
+        errors, info, stats, pairs_equal = run_fixture(pkg, name, rank, world, dev, dist)
+        if rank != 0:
+            continue
+        out["fixtures"].append({"name": name, "procgrid": list(info[2]), "steps": stats["steps"], "max_err": stats["max_err"],
+                                "pairs": stats["pairs"], "pairs_equal": bool(pairs_equal), "rebuilds": info[5],
+                                "errors": [list(map(str, e)) for e in errors[:4]]})
+        out["max_err"] = max(out["max_err"], stats["max_err"])
+        out["pairs_equal"] = out["pairs_equal"] and bool(pairs_equal)
+        out["ok"] = out["ok"] and not errors
+    flag = [out["ok"]]
+    if world > 1:
+        dist.broadcast_object_list(flag, src=0)
+    if rank != 0:
+        return {"ok": flag[0]} if not flag[0] else None
+    out["seconds"] = time.perf_counter() - t0
+    return out
+
+
+def pair_kernel_name(eng):
+    mode = eng.pair_mode() if hasattr(eng, "pair_mode") else "gather"
+    return "pair_kernel (fused density/BVF + force pass), %s form" % mode
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, dev):
         super().__init__(daemon=True)
-        self.dev, self.stop_flag, self.rows = dev, False, []
+        self.dev, self.stop_flag, self.rows, self.first, self.last = dev, False, [], 0, None
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -241,15 +278,29 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
+
+    def mark(self):
+        self.first = len(self.rows)
+
+    def stop(self):
+        self.last = len(self.rows)
+        self.stop_flag = True
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        """median SM clock / throttle reasons over the timed region; if it was shorter than a sampling period, over the
+        samples around it (the run is steady state from the warm-up on)"""
+        rows = self.rows[self.first:self.last]
+        window = "timed region"
+        if len(rows) < 2:
+            rows = self.rows[max(0, self.first - 3):(self.last or len(self.rows)) + 1]
+            window = "timed region +- 0.3 s"
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows for k in range(4) if len(r) > 2 + k and r[2 + k].lower().startswith("active")})
+        reasons = sorted({names[k] for r in rows for k in range(4) if len(r) > 2 + k and r[2 + k].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(rows), "samples_whole_run": len(self.rows), "window": window}
 
 
 def measured_peaks():
@@ -270,6 +321,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lammps", action="store_true", help="skip the lmp_cuda drop-in leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the golden-fixture parity check before the timed region")
     ap.add_argument("--lammps-n", type=int, default=160, help="lattice edge of the lmp_cuda drop-in leg")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 3)
@@ -282,20 +334,30 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        ref_steps = max(1, min(K, 5))
+        # bounded sample: EXACTLY the K timed and W warm-up steps that were asked for, on a lattice small enough for the
+        # whole run to end within ~2.5 minutes (the reference does ~6.9e4 atom-steps/s per core; throughput is per
+        # atom-step, so the sample size does not enter the metric)
+        ref_steps, ref_warm = K, W
+        ref_n = args.ref_n
+        for cand in (args.ref_n, 32, 26, 20, 16):
+            ref_n = min(cand, args.ref_n)
+            if (K + W) * ref_n ** 3 / 6.5e4 <= 150.0:
+                break
         cores = host_cores()
-        val, kind, atoms = time_reference(args.ref_n, ref_steps, 1, cores)
+        val, kind, atoms = time_reference(ref_n, ref_steps, ref_warm, cores)
         if kind != "reference":
             cores = 1
+        sample = ("%d independent single-rank replicas of the same deck at n=%d (%d atoms each), one per host core, %d timed "
+                  "steps after %d warm-up: aggregate throughput, an upper bound for one MPI job on these cores (no MPI runtime "
+                  "in the image, no threaded variant of these styles)" % (cores, ref_n, atoms, ref_steps, ref_warm))
         line = {"impl": "reference", "metric": "atom-steps/sec", "value": val, "unit": "atom-steps/s", "n_gpus": args.gpus,
-                "steps": K, "warmup": W, "ms_per_step": 1e3 * atoms * cores / val, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "cpu_sample": "%d replicas x %d^3 = %d atoms, %d timed steps" % (cores, args.ref_n, atoms, ref_steps)},
-                "cpu_baseline": {"value": val, "unit": "atom-steps/s", "cores": cores, "kind": kind,
-                                 "sample": "%d independent single-rank replicas of the same deck at n=%d (%d atoms each), one per "
-                                           "host core, %d steps: aggregate throughput, an upper bound for one MPI job on these cores "
-                                           "(no MPI runtime in the image, no threaded variant of these styles)"
-                                           % (cores, args.ref_n, atoms, ref_steps)},
+                "steps": ref_steps, "warmup": ref_warm, "ms_per_step": 1e3 * atoms * cores / val, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload,
+                           "cpu_sample": "%d replicas x %d^3 = %d atoms, %d timed steps after %d warm-up (throughput is per "
+                                         "atom-step, so the sample size does not enter the metric)"
+                                         % (cores, ref_n, atoms, ref_steps, ref_warm)},
+                "cpu_baseline": {"value": val, "unit": "atom-steps/s", "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": val, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -313,6 +375,22 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+
+    # clocks are sampled from here on (warm-up included) so that the line carries more than one sample
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+
+    # multi-rank correctness on record next to the throughput: golden fixtures of the unmodified reference run
+    # across the SAME N bricks (migration, borders, halo over NCCL), fields reassembled by tag on rank 0
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(pkg, rank, world, dev, dist)
+        if parity is not None and not parity["ok"]:
+            if rank == 0:
+                os.write(real_stdout, (json.dumps({"metric": "atom-steps/sec", "value": None, "n_gpus": world,
+                                                   "error": "parity_check failed", "parity_check": parity}) + "\n").encode())
+            sys.exit(3)
 
     meta = cavity_meta(n)
     prd = [meta["boxhi"][k] - meta["boxlo"][k] for k in range(3)]
@@ -355,13 +433,13 @@ def main():
         return float(ms.item())
 
     eng.run(W)
-    sampler = ClockSampler(dev)
     if rank == 0:
-        sampler.start()
+        sampler.mark()          # the summary's median is over the samples taken from here to stop()
     launches0 = eng.launch_count
     ms = timed(eng.run, K)
     launches = eng.launch_count - launches0
-    sampler.stop_flag = True
+    if rank == 0:
+        sampler.stop()
     value = natoms * K / (ms * 1e-3)
 
     # per-kernel device times (second pass, CUDA events around each kernel family on the lib's stream)
@@ -379,20 +457,26 @@ def main():
     # FP64 vector peak: 64 FMA/clk/SM (ncu sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained
     # = 9472 inst/cycle on 148 SMs) x 2 flop x max SM clock
     fp64_peak = float(os.environ.get("SPHBVF_FP64_PEAK_TFLOPS", "0") or 0) or 148 * 64 * 2 * 1.965e9 / 1e12
-    roof = {"bound": "hbm", "kernel": "pair_kernel (fused density/BVF + force pass)", "achieved": achieved,
+    f_alg = PROFILE["flop_per_atom"]
+    roof = {"bound": "hbm", "kernel": pair_kernel_name(eng), "achieved": achieved,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/): 605 B/atom
-            "traffic": TRAFFIC_PAIR_B_PER_ATOM * eng.nlocal,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch: NOT measured live (ncu cannot run inside a timed
+            # bench); bytes/atom of the committed --set full capture x the atoms of this launch
+            "traffic": PROFILE["dram_bytes_per_atom"] * eng.nlocal, "traffic_source": "profile: " + PROFILE["file"],
             "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650 GB/s",
             "algorithmic_bytes_per_atom_step": B_ALG_PAIR, "pair_ms_per_step": pair_ms,
-            "fp64_tflops_algorithmic": F_ALG_PAIR * eng.nlocal / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0,
-            "note": "the pair pass is FP64-pipe / gather-latency bound (AI ~ 50 flop/B, SURVEY.md 8d); HBM fraction reported "
+            # FP64 work: flop the kernel executes per atom-step by ncu's op_d{fma,mul,add} counters (fma = 2) and, beside
+            # it, SURVEY 8(d)'s paper estimate
+            "fp64_flop_per_atom_step": f_alg, "fp64_flop_source": "ncu op_dfma/dmul/dadd counters, " + PROFILE["file"],
+            "fp64_tflops": f_alg * eng.nlocal / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0,
+            "fp64_tflops_survey_estimate": F_ALG_PAIR_SURVEY * eng.nlocal / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0,
+            "note": "the pair pass is FP64-pipe / on-chip-gather bound (AI ~ 30 flop/B, SURVEY.md 8d); HBM fraction reported "
                     "as the contract asks, fp64_frac is the meaningful roof",
-            "ncu": {"l1_data_pipe_busy": 0.81, "fp64_pipe_busy": 0.46, "issue_active": 0.42, "warps_per_sm": 11.2,
-                    "source": "profiles/r01g_pair_and_integrate_n200.txt (one --set full capture, not live)"}}
+            "ncu": {k: PROFILE[k] for k in ("l1_data_pipe_busy", "fp64_pipe_busy", "issue_active", "warps_per_sm")}}
+    roof["ncu"]["source"] = PROFILE["file"] + " (" + PROFILE["kernel"] + ", one --set full capture, not live)"
     if fp64_peak:
         roof["fp64_peak_tflops"] = fp64_peak
-        roof["fp64_frac"] = roof["fp64_tflops_algorithmic"] / fp64_peak
+        roof["fp64_frac"] = roof["fp64_tflops"] / fp64_peak
 
     # e2e: host-authoritative stepping through the C ABI with pinned host buffers, every rank: per
     # step the integrator/pair inputs go host->device and the step's results device->host (rows in
@@ -462,6 +546,7 @@ def main():
                            "l2": "inputs larger than L2 (state >> 126 MB), no explicit flush",
                            "rebuild": "every 10 steps (delay 10, skin 0.01h), inside the timed region"},
                 "gpu_launches": int(launches), "kernels": fam, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+                "parity_check": parity,
                 "clocks": sampler.summary(), "lammps_dropin": dropin}
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -8,93 +8,20 @@ over NCCL, and rank 0 reassembles the fields by atom tag and compares them with 
 reference produced on one CPU rank (tests/golden/*.npz): same bar as tests/test_gpu_parity.py --
 pair sets bit-exact, consumed fields within 1e-10 of the field's max-norm.
 """
-import ctypes
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from common import load_fixture  # noqa: E402
+from brick_parity import run_fixture as _run_fixture  # noqa: E402
 from conftest import load_package  # noqa: E402
-from refsnap import canonical_pairs  # noqa: E402
-from test_gpu_parity import TOL, field_scale, ref_pairs, skip_field  # noqa: E402
 
 
 def run_fixture(pkg, name, rank, world, dev):
-    meta, z = load_fixture(name)
-    L = pkg.lib()
-    prd = [meta["boxhi"][k] - meta["boxlo"][k] for k in range(3)]
-    grid = (ctypes.c_int * 3)(1, 1, 1)
-    L.sphbvf_proc_grid(world, meta["dim"], (ctypes.c_double * 3)(*prd), ctypes.byref(grid))
-    eng = pkg.Engine(meta, device=dev, procgrid=tuple(grid), rank=rank, nranks=world)
-    ident = [pkg.capi.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ident, src=0)
-    eng.comm_init(ident[0])
-    sublo, subhi = (ctypes.c_double * 3)(), (ctypes.c_double * 3)()
-    L.sphbvf_brick_bounds(ctypes.byref(eng.cfg), rank, ctypes.byref(sublo), ctypes.byref(subhi))
-    x = z["init_x"]
-    mine = np.ones(len(x), bool)
-    for k in range(meta["dim"]):
-        mine &= (x[:, k] >= sublo[k]) & (x[:, k] < subhi[k])
-    sel = lambda key: np.ascontiguousarray(z["init_" + key][mine])
-    eng.set_atoms(sel("tag"), sel("type"), sel("mask"), sel("solid_tag"), sel("fixed_tag"), sel("x"), sel("v"),
-                  sel("rho"), sel("e"), sel("C"), sel("dev"))
-    eng.set_run_length(meta["nsteps"])
-    eng.setup()
-    tags0 = z["init_tag"]
-    order = np.argsort(tags0)
-    errors, step = [], 0
-
-    def gather(field):
-        loc_tag, loc = eng.get("tag", local=True), eng.get(field, local=True)
-        parts = [None] * world
-        dist.all_gather_object(parts, (loc_tag, loc))
-        if rank != 0:
-            return None
-        tg = np.concatenate([p[0] for p in parts])
-        val = np.concatenate([p[1] for p in parts])
-        assert len(tg) == len(tags0) and len(np.unique(tg)) == len(tg), "atoms lost or duplicated: %d of %d" % (len(tg), len(tags0))
-        out = np.empty_like(val)
-        # row of the fixture (input order) for every gathered tag
-        out[order[np.searchsorted(tags0[order], tg)]] = val
-        return out
-
-    for s in meta["steps"]:
-        if name == "solid3d_tv_n10" and s > 12:   # orientation-dependent reference quirk, see test_gpu_parity.py
-            break
-        if s > step:
-            eng.run(s - step)
-            step = s
-        for f in meta["fields"]:
-            if skip_field(meta, f, s):
-                continue
-            got = gather(f)
-            if rank != 0:
-                continue
-            ref = z["s%d_%s" % (s, f)]
-            if f == "f":
-                keep = ~((z["init_solid_tag"] == 1) & (z["init_fixed_tag"] == 1))
-                ref, got = ref[keep], got[keep]
-            fin = np.isfinite(ref)
-            if not np.array_equal(np.isfinite(got), fin):
-                errors.append((name, s, f, "finite mask"))
-                continue
-            err = np.abs(got[fin] - ref[fin]).max() / max(field_scale(z, meta, f), 1e-300) if fin.any() else 0.0
-            if err > TOL:
-                errors.append((name, s, f, float(err)))
-        if s in meta["pair_steps"]:
-            parts = [None] * world
-            dist.all_gather_object(parts, eng.pairs())
-            if rank == 0:
-                got = canonical_pairs(np.concatenate(parts))
-                if not np.array_equal(got, ref_pairs(z, meta, s)):
-                    errors.append((name, s, "pair list", "%d vs %d" % (len(got), len(ref_pairs(z, meta, s)))))
-    info = (name, world, tuple(grid), eng.nlocal, eng.nghost, eng.nbuilds)
-    eng.close()
-    return errors, info
+    errors, info, _, _ = _run_fixture(pkg, name, rank, world, dev, dist)
+    return errors or [], info
 
 
 def main():
