@@ -115,11 +115,11 @@ FixSsaTsdpdBufferCuda::FixSsaTsdpdBufferCuda(LAMMPS *lmp, int narg, char **arg) 
 
 FixSetForceCuda::FixSetForceCuda(LAMMPS *lmp, int narg, char **arg) : FixSphbvfRegistered(lmp, narg, arg)
 {
-  if (narg != 6) error->all(FLERR, "fix setforce/cuda supports the form 'setforce fx fy fz' only; use 'suffix off' around other forms");
+  if (narg != 6) error->all(FLERR, "fix setforce/cuda supports the form 'setforce fx fy fz' only: other forms would act on the stale host copy of the atoms; run this deck without -sf cuda");
   desc.kind = K_SETFORCE;
   for (int k = 0; k < 3; k++) {
     if (strstr(arg[3 + k], "v_") == arg[3 + k] || strcmp(arg[3 + k], "NULL") == 0)
-      error->all(FLERR, "fix setforce/cuda supports numeric constants only; use 'suffix off' around this fix");
+      error->all(FLERR, "fix setforce/cuda supports numeric constants only: a variable-style setforce would act on the stale host copy of the atoms; run this deck without -sf cuda");
     desc.a[k] = force->numeric(FLERR, arg[3 + k]);
   }
 }

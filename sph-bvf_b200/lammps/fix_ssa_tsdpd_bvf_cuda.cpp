@@ -11,8 +11,10 @@
 #include "fix_ssa_tsdpd_bvf_cuda.h"
 #include "sphbvf_lmp.h"
 #include "atom.h"
+#include "comm.h"
 #include "error.h"
 #include "force.h"
+#include "modify.h"
 #include "output.h"
 #include "pair.h"
 #include "update.h"
@@ -56,6 +58,37 @@ void FixSsaTsdpdBvfCuda::init()
   if (engine->variant != variant)
     error->all(FLERR, "fix ssa_tsdpd/bvf/<style>/cuda and pair_style ssa_tsdpd/bvf/<style>/cuda must be the same variant");
   engine->integrate_groupbit = groupbit;
+
+  // Between output steps the host arrays of class Atom are stale: a stock (non-/cuda) fix that integrates or
+  // edits per-atom state would act on dead host data and never reach the device.  Refuse those outright;
+  // stock fixes that only hook end_of_step (fix print, ave/time, ave/atom ...: readers) are served by a full
+  // download before every end_of_step, which is correct but slow, so say so.
+  need_host_every_step = 0;
+  const int writers = INITIAL_INTEGRATE | POST_INTEGRATE | PRE_EXCHANGE | PRE_NEIGHBOR | PRE_FORCE | POST_FORCE |
+                      FINAL_INTEGRATE | INITIAL_INTEGRATE_RESPA | POST_INTEGRATE_RESPA | PRE_FORCE_RESPA |
+                      POST_FORCE_RESPA | FINAL_INTEGRATE_RESPA;
+  for (int i = 0; i < modify->nfix; i++) {
+    const char *fs = modify->fix[i]->style;
+    const size_t n = strlen(fs);
+    if (n >= 5 && strcmp(fs + n - 5, "/cuda") == 0) continue;
+    const int m = modify->fmask[i];
+    if (m & writers) {
+      char msg[512];
+      snprintf(msg, sizeof msg, "fix %s (style %s) has no /cuda version: it would act on the stale host copy of the atoms "
+               "while the ssa_tsdpd/bvf /cuda styles keep them on the device.  Remove it or run without -sf cuda",
+               modify->fix[i]->id, fs);
+      error->all(FLERR, msg);
+    }
+    if (m & END_OF_STEP) {
+      need_host_every_step = 1;
+      if (comm->me == 0) {
+        char msg[512];
+        snprintf(msg, sizeof msg, "fix %s (style %s) reads host data in end_of_step: the /cuda styles download every "
+                 "per-atom field on every step for it", modify->fix[i]->id, fs);
+        error->warning(FLERR, msg);
+      }
+    }
+  }
 }
 
 /* ----------------------------------------------------------------------
@@ -104,7 +137,11 @@ void FixSsaTsdpdBvfCuda::post_integrate() { engine->call(sphbvf_post_integrate);
 
 void FixSsaTsdpdBvfCuda::post_force(int) { engine->call(sphbvf_post_force); }
 
-void FixSsaTsdpdBvfCuda::final_integrate() { engine->call(sphbvf_final_integrate); }
+void FixSsaTsdpdBvfCuda::final_integrate()
+{
+  engine->call(sphbvf_final_integrate);
+  if (need_host_every_step) engine->to_host();   // a stock end_of_step fix reads the host arrays (see init)
+}
 
 void FixSsaTsdpdBvfCuda::end_of_step()
 {

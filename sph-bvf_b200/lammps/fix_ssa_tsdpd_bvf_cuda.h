@@ -40,6 +40,7 @@ class FixSsaTsdpdBvfCuda : public Fix {
 
  protected:
   int variant;
+  int need_host_every_step;   // a stock (non-/cuda) fix hooks end_of_step: refresh the host arrays before it
   class SphbvfLmp *engine;
 };
 
