@@ -171,6 +171,11 @@ int sphbvf_nlocal(const sphbvf_ctx *ctx);
 int sphbvf_nghost(const sphbvf_ctx *ctx);
 long sphbvf_ntimestep(const sphbvf_ctx *ctx);
 int sphbvf_nbuilds(const sphbvf_ctx *ctx);    /* Neighbor::ncalls */
+/* how the current neighbour list is stored and traversed: 1 = tile form (16-bit entries, the candidates of a
+ * 4x4x4-cell tile staged in shared memory, default), 0 = gather form (32-bit entries, records gathered through L1;
+ * chosen at a rebuild when a tile's candidates do not fit, or with SPHBVF_PAIR=gather).  Same pair sets and the same
+ * arithmetic per pair either way; the summation order differs. */
+int sphbvf_pair_mode(const sphbvf_ctx *ctx);
 int sphbvf_ndanger(const sphbvf_ctx *ctx);    /* Neighbor::ndanger */
 /* max over the atoms of `groupbit` (all ranks) of |v|^2 with v the transport velocity (atom->v): the
  * reduction FixDtAdaptive::end_of_step does before its MPI_Allreduce (fix_dt_adaptive.cpp:118-148) */

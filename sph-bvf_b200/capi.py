@@ -37,7 +37,7 @@ SYMBOLS = ["sphbvf_version", "sphbvf_device_count", "sphbvf_create", "sphbvf_des
            "sphbvf_setup_neighbors",
            "sphbvf_initial_integrate", "sphbvf_post_integrate", "sphbvf_neighbor", "sphbvf_pair_compute",
            "sphbvf_virial", "sphbvf_post_force", "sphbvf_setup_post_force", "sphbvf_final_integrate", "sphbvf_end_of_step", "sphbvf_build_neighbors",
-           "sphbvf_nlocal", "sphbvf_nghost", "sphbvf_ntimestep", "sphbvf_nbuilds", "sphbvf_ndanger",
+           "sphbvf_nlocal", "sphbvf_nghost", "sphbvf_ntimestep", "sphbvf_nbuilds", "sphbvf_ndanger", "sphbvf_pair_mode",
            "sphbvf_get_pairs", "sphbvf_sync", "sphbvf_launch_count", "sphbvf_set_profiling", "sphbvf_kernel_ms",
            "sphbvf_stream", "sphbvf_comm_unique_id", "sphbvf_comm_init", "sphbvf_brick_bounds", "sphbvf_proc_grid",
            "sphbvf_comm_plan"]
@@ -77,7 +77,7 @@ def lib():
     L.sphbvf_max_vsq.argtypes = [vp, ci, C.POINTER(cd)]
     L.sphbvf_ke_tensor.argtypes = [vp, ci, vp]
     for f in ("setup", "setup_neighbors", "setup_post_force", "initial_integrate", "post_integrate", "pair_compute", "post_force", "final_integrate",
-              "end_of_step", "build_neighbors", "nlocal", "nghost", "nbuilds", "ndanger", "sync"):
+              "end_of_step", "build_neighbors", "nlocal", "nghost", "nbuilds", "ndanger", "sync", "pair_mode"):
         getattr(L, "sphbvf_" + f).argtypes = [vp]
     L.sphbvf_run.argtypes = [vp, ci]
     L.sphbvf_virial.argtypes = [vp, vp]
@@ -283,6 +283,10 @@ class Engine:
     @property
     def nbuilds(self):
         return lib().sphbvf_nbuilds(self.h)
+
+    def pair_mode(self):
+        """'tile' (16-bit slot list, candidates staged in shared memory) or 'gather' (32-bit list, records through L1)"""
+        return "tile" if lib().sphbvf_pair_mode(self.h) else "gather"
 
     @property
     def ntimestep(self):

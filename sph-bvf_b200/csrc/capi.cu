@@ -12,9 +12,14 @@
 #include <vector>
 
 #include "sphbvf_internal.cuh"
+#include "tile_common.cuh"
 #include "context.cuh"
 
 using namespace sphbvf;
+
+namespace sphbvf {
+thread_local long tl_launches = 0;
+}
 
 // ------------------------------------------------------------------------------------------
 // helpers
@@ -54,8 +59,11 @@ static cudaError_t dev_realloc(T *&p, size_t old_n, size_t new_n, cudaStream_t s
   return cudaSuccess;
 }
 
-void sphbvf_ctx::tic(int fam, int nlaunch) {
-  launches_fam[fam] += nlaunch;
+// tic(fam) ... toc(): every kernel the calling thread launches in between is attributed to `fam` (the launch sites
+// bump sphbvf::tl_launches), and with profiling on the span is bracketed by two CUDA events on the context's stream
+void sphbvf_ctx::tic(int fam) {
+  open_fam = fam;
+  launch_mark = tl_launches;
   if (!profiling) return;
   cudaEvent_t a, b;
   if (ev_pool.size() >= 2) {
@@ -70,6 +78,8 @@ void sphbvf_ctx::tic(int fam, int nlaunch) {
 }
 
 void sphbvf_ctx::toc() {
+  if (open_fam >= 0) launches_fam[open_fam] += tl_launches - launch_mark;
+  open_fam = -1;
   if (!profiling) return;
   cudaEventRecord(ev_open.b, st);
   ev_list.push_back(ev_open);
@@ -134,6 +144,10 @@ static int ensure_capacity(sphbvf_ctx *ctx, int nmax, int nallmax) {
     RE(d.tag, 1, true); RE(d.type, 1, true); RE(d.mask, 1, true); RE(d.solid, 1, true); RE(d.fixed, 1, true); RE(d.slot, 1, true);
     RE(d.x, 3, true); RE(d.v, 3, true); RE(d.vest, 3, true); RE(d.rho, 1, true); RE(d.rhoI, 1, true); RE(d.e, 1, true);
     RE(d.C, S, true); RE(d.dev, 9, true);
+    RE(d.alt.tag, 1, false); RE(d.alt.type, 1, false); RE(d.alt.mask, 1, false); RE(d.alt.solid, 1, false);
+    RE(d.alt.fixed, 1, false); RE(d.alt.slot, 1, false);
+    RE(d.alt.x, 3, false); RE(d.alt.v, 3, false); RE(d.alt.vest, 3, false); RE(d.alt.rho, 1, false); RE(d.alt.rhoI, 1, false);
+    RE(d.alt.e, 1, false); RE(d.alt.C, S, false); RE(d.alt.dev, 9, false);
     RE(d.f, 3, true); RE(d.nw, 3, true); RE(d.ddv, 3, true); RE(d.ddx, 3, true); RE(d.drho, 1, true); RE(d.phi, 1, true);
     RE(d.nd, 1, true); RE(d.rhoAux1, 1, true); RE(d.rhoAux2, 1, true); RE(d.Pnew, 1, true); RE(d.ddev, 9, true); RE(d.Q, S, true);
     RE(d.xhold, 3, true); RE(d.numneigh, 1, true);
@@ -146,12 +160,12 @@ static int ensure_capacity(sphbvf_ctx *ctx, int nmax, int nallmax) {
       ctx->w.tmp_perm_bytes = (size_t)9 * n * sizeof(double);
       CK(cudaMalloc(&ctx->w.tmp_perm, ctx->w.tmp_perm_bytes));
     }
-    // neighbour list storage is tied to the stride = nmax
-    if (d.maxneigh > 0) {
-      if (d.neigh) cudaFree(d.neigh);
-      d.neigh = nullptr;
-      CK(cudaMalloc((void **)&d.neigh, sizeof(int) * (size_t)d.maxneigh * n));
-    }
+    // neighbour list storage is tied to nmax (stride of the gather form, rows of the tile form): dropped here,
+    // re-created by ensure_neigh at the next rebuild (growth only happens on the way into one)
+    if (d.neigh) cudaFree(d.neigh);
+    if (d.neigh16) cudaFree(d.neigh16);
+    d.neigh = nullptr;
+    d.neigh16 = nullptr;
     d.stride = nmax;
     d.nmax = nmax;
   }
@@ -178,13 +192,19 @@ static int ensure_cells(sphbvf_ctx *ctx, long ncells) {
   return ensure_scan(ctx, cap);
 }
 
+// storage of the Verlet list in the encoding d.list16 selects, for `maxneigh` entries per atom
 static int ensure_neigh(sphbvf_ctx *ctx, int maxneigh) {
   DevState &d = ctx->d;
-  if (maxneigh <= d.maxneigh && d.neigh) return 0;
-  if (d.neigh) cudaFree(d.neigh);
-  d.neigh = nullptr;
-  d.maxneigh = maxneigh;
-  CK(cudaMalloc((void **)&d.neigh, sizeof(int) * (size_t)d.maxneigh * d.stride));
+  if (maxneigh > d.maxneigh) {   // growth invalidates both encodings
+    if (d.neigh) cudaFree(d.neigh);
+    if (d.neigh16) cudaFree(d.neigh16);
+    d.neigh = nullptr;
+    d.neigh16 = nullptr;
+    d.maxneigh = maxneigh;
+  }
+  d.pitch16 = (d.maxneigh + 7) & ~7;
+  if (d.list16 && !d.neigh16) CK(cudaMalloc((void **)&d.neigh16, sizeof(unsigned short) * (size_t)d.pitch16 * d.nmax));
+  if (!d.list16 && !d.neigh) CK(cudaMalloc((void **)&d.neigh, sizeof(int) * (size_t)d.maxneigh * d.stride));
   return 0;
 }
 
@@ -255,26 +275,30 @@ static int fetch_flags(sphbvf_ctx *ctx) {
 // ---- pieces of the rebuild branch of verlet.cpp:268-296, shared by the single-rank path below and
 // the brick-decomposed path in comm_nccl.cu -----------------------------------------------------
 
+// every primary array gathered through w.perm (new -> old) into the second buffer, then the buffers swap
+int permute_state(sphbvf_ctx *ctx, int n, bool always_dev) {
+  DevState &d = ctx->d;
+  StateArrays cur = {d.tag, d.type, d.mask, d.solid, d.fixed, d.slot, d.x, d.v, d.vest, d.rho, d.rhoI, d.e, d.C, d.dev};
+  launch_gather_state(cur, d.alt, ctx->w.perm, n, ctx->co.nspecies, ctx->with_dev || always_dev, ctx->st);
+  CKLAUNCH();
+  const StateArrays nw = d.alt;
+  d.alt = cur;
+  d.tag = nw.tag; d.type = nw.type; d.mask = nw.mask; d.solid = nw.solid; d.fixed = nw.fixed; d.slot = nw.slot;
+  d.x = nw.x; d.v = nw.v; d.vest = nw.vest; d.rho = nw.rho; d.rhoI = nw.rhoI; d.e = nw.e; d.C = nw.C; d.dev = nw.dev;
+  if (!(ctx->with_dev || always_dev)) std::swap(d.dev, d.alt.dev);   // not gathered (identically zero): keep the buffer
+  if (!ctx->co.nspecies) std::swap(d.C, d.alt.C);
+  return 0;
+}
+
 // Domain::pbc + cell ids + counting sort + permutation of every primary array into cell order
 int rebuild_sort(sphbvf_ctx *ctx) {
   DevState &d = ctx->d;
   NeighWork &w = ctx->w;
   cudaStream_t st = ctx->st;
-  const Coeffs &co = ctx->co;
   launch_cell_ids(d, ctx->grid, ctx->box, w, st);
   launch_sort_owned(d, ctx->grid, w, st);
-  const int n = d.nlocal, S = co.nspecies;
-  launch_permute(d.x, w.tmp_perm, w.perm, n, 3, 8, st);
-  launch_permute(d.v, w.tmp_perm, w.perm, n, 3, 8, st);
-  launch_permute(d.vest, w.tmp_perm, w.perm, n, 3, 8, st);
-  launch_permute(d.rho, w.tmp_perm, w.perm, n, 1, 8, st);
-  launch_permute(d.rhoI, w.tmp_perm, w.perm, n, 1, 8, st);
-  launch_permute(d.e, w.tmp_perm, w.perm, n, 1, 8, st);
-  if (S) launch_permute(d.C, w.tmp_perm, w.perm, n, S, 8, st);
-  if (ctx->with_dev) launch_permute(d.dev, w.tmp_perm, w.perm, n, 9, 8, st);
-  for (int *p : {d.tag, d.type, d.mask, d.solid, d.fixed, d.slot}) launch_permute(p, w.tmp_perm, w.perm, n, 1, 4, st);
   CKLAUNCH();
-  return 0;
+  return permute_state(ctx, d.nlocal, false);
 }
 
 // ghosts are in place (packed records of owned + ghost atoms written): bin ghosts, Verlet list, xhold
@@ -286,6 +310,12 @@ int rebuild_finish(sphbvf_ctx *ctx) {
   int rc;
   launch_bin_ghosts(d, ctx->grid, w, st);
   CKLAUNCH();
+  // Encoding of this rebuild's list.  The tile form (16-bit slots, candidates of a tile staged in shared memory by
+  // pair_tile_kernel) is tried first unless SPHBVF_PAIR=gather / SPHBVF_LIST_BUILD=thread ask for the gather form; the
+  // builder reports the largest candidate count of a tile, and if that does not fit 12-bit slots or the shared
+  // memory of one CTA (worst-case instantiation: 96-byte records + index map) the list is built again in the gather form.
+  const char *lb = getenv("SPHBVF_LIST_BUILD");
+  bool want_tile = ctx->pair_pref == 0 && !(lb && lb[0] == 't') && tile_form_possible(ctx->grid);
   for (int attempt = 0; attempt < 3; attempt++) {
     if (d.maxneigh == 0) {
       // first guess from the number density: neighbours within cutneighmax of a uniform fluid
@@ -294,17 +324,31 @@ int rebuild_finish(sphbvf_ctx *ctx) {
       for (int k = 0; k < b.dim; k++) vol *= (b.subhi[k] - b.sublo[k]);
       const double dens = d.nlocal / std::max(vol, 1e-300);
       const double sph = b.dim == 3 ? 4.18879 * pow(ctx->cutneighmax, 3) : 3.14159 * pow(ctx->cutneighmax, 2);
-      if ((rc = ensure_neigh(ctx, std::max(16, (int)(1.3 * dens * sph) + 8)))) return rc;
+      d.maxneigh = std::max(16, (int)(1.3 * dens * sph) + 8);
     }
+    d.list16 = want_tile;
+    if ((rc = ensure_neigh(ctx, d.maxneigh))) return rc;
     CK(cudaMemsetAsync(w.flags + 2, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(w.flags + 4, 0, sizeof(int), st));
     launch_build_list(d, ctx->grid, co, w, st);
     CKLAUNCH();
     if ((rc = fetch_flags(ctx))) return rc;
-    if (ctx->h_flags[2] <= d.maxneigh) break;
+    if (d.list16) {
+      const int cap = (ctx->h_flags[4] + 7) & ~7;
+      if (ctx->h_flags[4] > TILE_MAX_SLOTS || pair_tile_smem(cap, 6, true) + 6144 > (size_t)ctx->smem_optin) {
+        want_tile = false;   // dense tiles: gather form for this rebuild interval
+        attempt--;
+        continue;
+      }
+      d.tile_cap = std::max(cap, 8);
+    }
+    const int capacity = d.list16 ? d.pitch16 : d.maxneigh;
+    if (ctx->h_flags[2] <= capacity) break;
     if (attempt == 2) return ctx->fail(SPHBVF_EOVERFLOW, "Neighbor list overflow");
     if ((rc = ensure_neigh(ctx, ctx->h_flags[2] + ctx->h_flags[2] / 8 + 4))) return rc;
   }
   ctx->maxneigh_seen = ctx->h_flags[2];
+  ctx->expanded_valid = 0;
   launch_copy_xhold(d, st);
   ctx->ago = 0;
   ctx->nbuilds++;
@@ -321,7 +365,7 @@ static int rebuild(sphbvf_ctx *ctx) {
   cudaStream_t st = ctx->st;
   const Coeffs &co = ctx->co;
   int rc;
-  ctx->tic(K_NEIGH, 40);
+  ctx->tic(K_NEIGH);
   CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * 8, st));
   if ((rc = rebuild_sort(ctx))) return rc;
   const int n = d.nlocal;
@@ -424,6 +468,9 @@ int sphbvf_create(const sphbvf_config *cfg, sphbvf_ctx **out) {
   cudaMemset(ctx->w.flags, 0, sizeof(int) * 8);
   ctx->run_nsteps_user = -1;
   { const char *e = getenv("SPHBVF_NO_FUSE"); ctx->fuse = !(e && atoi(e)); }
+  { const char *e = getenv("SPHBVF_PAIR"); ctx->pair_pref = (e && e[0] == 'g') ? 1 : 0; }   // gather | tile (default)
+  if (cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device) != cudaSuccess)
+    ctx->smem_optin = 48 * 1024;
   *out = ctx;
   return 0;
 }
@@ -438,6 +485,8 @@ void sphbvf_destroy(sphbvf_ctx *ctx) {
   DevState &d = ctx->d;
   void *ptrs[] = {d.tag, d.type, d.mask, d.solid, d.fixed, d.slot, d.x, d.v, d.vest, d.rho, d.rhoI, d.e, d.C, d.dev,
                   d.f, d.nw, d.ddv, d.ddx, d.drho, d.phi, d.nd, d.rhoAux1, d.rhoAux2, d.Pnew, d.ddev, d.Q,
+                  d.alt.tag, d.alt.type, d.alt.mask, d.alt.solid, d.alt.fixed, d.alt.slot, d.alt.x, d.alt.v, d.alt.vest,
+                  d.alt.rho, d.alt.rhoI, d.alt.e, d.alt.C, d.alt.dev, d.neigh16,
                   d.prec, d.pD, d.pCs, d.pdev, d.pflags, d.ptag, d.xhold, d.gowner, d.gshift, d.neigh,
                   d.numneigh, ctx->w.cellid, ctx->w.perm, ctx->w.cell_count, ctx->w.cell_start, ctx->w.gcell_count,
                   ctx->w.gcell_start, ctx->w.gorder, ctx->w.scan_tmp, ctx->w.nimg, ctx->w.flags, ctx->w.tmp_perm};
@@ -459,6 +508,7 @@ int sphbvf_set_type(sphbvf_ctx *ctx, int t, double mass, double rho0, double c0,
   co.c0[t] = c0;
   co.B[t] = c0 * c0 * rho0 / 7.0;   // pair_...transport_velocity.cpp:981
   co.G0[t] = G0;
+  co.kp[t] = (c0 * c0) / (mass * mass);   // prr_from_v
   return 0;
 }
 
@@ -606,11 +656,10 @@ static int run_fixes(sphbvf_ctx *ctx, int hook, bool in_setup = false) {
     if (!fix_runs(ctx->fixes[q], hook, ctx->ntimestep)) continue;
     if (!any) {
       FLUSH();
-      ctx->tic(K_FIX, 0);
+      ctx->tic(K_FIX);
       any = true;
       if (hook == 0) ctx->pack_valid = 0;   // post_integrate fixes edit vest / C after the records were written
     }
-    ctx->launches_fam[K_FIX]++;
     launch_fix(ctx->d, ctx->co, ctx->fixes[q], hook, ctx->ntimestep, ctx->st);
   }
   if (any) { ctx->toc(); CKLAUNCH(); }
@@ -725,7 +774,7 @@ int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt) {
   if (flag) return ctx->cfg.nranks > 1 ? comm_rebuild(ctx) : rebuild(ctx);
   // Comm::forward_comm (comm_brick.cpp:460-520): refresh the packed records of owned atoms and ghosts
   if (pack_valid && ctx->cfg.nranks == 1 && !ctx->d.nghost) return 0;   // records are current, nothing to refresh
-  ctx->tic(K_PACK, pack_valid ? 0 : 1);
+  ctx->tic(K_PACK);
   if (!pack_valid) launch_pack(ctx->d, ctx->co, ctx->with_dev, ctx->st);
   if (ctx->cfg.nranks > 1) { if ((rc = comm_forward(ctx))) return rc; }
   else launch_ghost_refresh(ctx->d, ctx->co, ctx->with_dev, ctx->st);
@@ -738,7 +787,7 @@ int sphbvf_pair_compute(sphbvf_ctx *ctx) {
   if (!ctx->setup_done) return ctx->fail(SPHBVF_ESTATE, "pair_compute before setup");
   FLUSH();
   ctx->tic(K_PAIR);
-  launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->st);
+  launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->grid, ctx->w, ctx->st);
   ctx->toc();
   CKLAUNCH();
   return 0;
@@ -757,7 +806,7 @@ int sphbvf_virial(sphbvf_ctx *ctx, double *virial6) {
   FLUSH();
   if (!ctx->d_virial) CK(cudaMalloc((void **)&ctx->d_virial, sizeof(double) * 6));
   CK(cudaMemsetAsync(ctx->d_virial, 0, sizeof(double) * 6, ctx->st));
-  launch_virial(ctx->d, ctx->co, pair_flags(ctx), ctx->d_virial, ctx->st);
+  launch_virial(ctx->d, ctx->co, pair_flags(ctx), ctx->grid, ctx->w, ctx->d_virial, ctx->st);
   CKLAUNCH();
   CK(cudaMemcpyAsync(virial6, ctx->d_virial, sizeof(double) * 6, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
@@ -839,6 +888,7 @@ int sphbvf_nlocal(const sphbvf_ctx *ctx) { return ctx->d.nlocal; }
 int sphbvf_nghost(const sphbvf_ctx *ctx) { return ctx->d.nghost; }
 long sphbvf_ntimestep(const sphbvf_ctx *ctx) { return ctx->ntimestep; }
 int sphbvf_nbuilds(const sphbvf_ctx *ctx) { return ctx->nbuilds; }
+int sphbvf_pair_mode(const sphbvf_ctx *ctx) { return ctx->d.list16; }
 int sphbvf_ndanger(const sphbvf_ctx *ctx) { return ctx->ndanger; }
 void *sphbvf_stream(sphbvf_ctx *ctx) { return (void *)ctx->st; }
 
@@ -986,8 +1036,16 @@ int sphbvf_upload(sphbvf_ctx *ctx, int field, const void *host) {
 long sphbvf_get_pairs(sphbvf_ctx *ctx, int *out, long cap) {
   DevState &d = ctx->d;
   const int n = d.nlocal, nall = d.nlocal + d.nghost;
-  if (!d.neigh || !n) return 0;
+  if (!n || !(d.list16 ? (void *)d.neigh16 : (void *)d.neigh)) return 0;
   cudaSetDevice(ctx->cfg.device);
+  if (d.list16 && !ctx->expanded_valid) {   // tile form: expand the 16-bit slot entries into the gather form first
+    if (!d.neigh && cudaMalloc((void **)&d.neigh, sizeof(int) * (size_t)d.maxneigh * d.stride) != cudaSuccess) {
+      ctx->fail(SPHBVF_ECUDA, "get_pairs: out of device memory for the expanded list");
+      return -1;
+    }
+    launch_expand_list(d, ctx->grid, ctx->w, ctx->st);
+    ctx->expanded_valid = 1;
+  }
   cudaStreamSynchronize(ctx->st);
   std::vector<int> nn(n), ptag(nall), gowner(std::max(d.nghost, 1));
   std::vector<double> gshift(3 * (size_t)std::max(d.nghost, 1));

@@ -61,6 +61,7 @@ NcclApi *nccl_api() {
 }
 
 constexpr int ND = 27;       // directions (dx+1) + 3 (dy+1) + 9 (dz+1); 13 = stay
+constexpr int NDX = 32;      // stride of a rank's count vector: ND counts + [27] non-finite flag, [28] lost flag, [29] status
 constexpr int NHALO = 16;    // pA pB pC pD
 struct DirTable {
   int peer[ND];
@@ -78,7 +79,7 @@ struct CommState {
   int send_cap = 0;
   double *sendbuf = nullptr, *recvbuf = nullptr;
   size_t buf_cap = 0;        // doubles
-  int *d_counts = nullptr;   // [ND] local counters | [ND] cursors | [ND * nranks] gathered | [1] vote
+  int *d_counts = nullptr;   // [NDX] local counters + flags | [NDX] cursors | [NDX * nranks] gathered | [16] scratch
   int *h_counts = nullptr;   // pinned mirror
   int *d_dir = nullptr;      // [nmax] migration direction of each owned atom
   int dir_cap = 0;
@@ -330,18 +331,34 @@ static int ensure_dir(sphbvf_ctx *ctx, int n) {
   return 0;
 }
 
-// all ranks learn every rank's per-direction counts: recvcnt[d'] = what peer(d') sends towards -d'
-static int exchange_counts(sphbvf_ctx *ctx, const int *d_local, int *sendcnt, int *recvcnt) {
+// all ranks learn every rank's per-direction counts: recvcnt[d'] = what peer(d') sends towards -d'.
+// The error decision rides on the same all-gather (slots 27..29 of each rank's vector: non-finite positions,
+// lost atoms, local status), so that EVERY rank returns the same error before any payload is posted -- a rank
+// that left alone would leave its peers spinning in ncclSend/ncclRecv.
+static int exchange_counts(sphbvf_ctx *ctx, int *d_local, int *sendcnt, int *recvcnt, const char *lost_msg, int rc_local) {
   CommState *c = ctx->comm;
   const int P = ctx->cfg.nranks;
-  int *gathered = c->d_counts + 2 * ND;
-  NK(nccl_api()->AllGather(d_local, gathered, ND, ncclInt, c->comm, ctx->st));
-  CK(cudaMemcpyAsync(c->h_counts, gathered, sizeof(int) * ND * P, cudaMemcpyDeviceToHost, ctx->st));
+  int *gathered = c->d_counts + 2 * NDX;
+  CK(cudaMemcpyAsync(d_local + ND, ctx->w.flags, sizeof(int) * 2, cudaMemcpyDeviceToDevice, ctx->st));
+  int *h_rc = c->h_counts + NDX * P + 8;   // pinned scratch behind the gathered counts
+  *h_rc = rc_local ? -rc_local : 0;
+  CK(cudaMemcpyAsync(d_local + ND + 2, h_rc, sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  NK(nccl_api()->AllGather(d_local, gathered, NDX, ncclInt, c->comm, ctx->st));
+  CK(cudaMemcpyAsync(c->h_counts, gathered, sizeof(int) * NDX * P, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
+  for (int r = 0; r < P; r++) {
+    const int *v = c->h_counts + r * NDX;
+    if (v[ND]) return ctx->fail(SPHBVF_ENONFINITE, "Non-numeric positions - simulation unstable%s", r == ctx->cfg.rank ? "" : " (on another GPU)");
+    if (v[ND + 1]) return ctx->fail(SPHBVF_ELOST, "%s%s", lost_msg, r == ctx->cfg.rank ? "" : " (on another GPU)");
+  }
+  if (rc_local) return rc_local;   // keep the local message
+  for (int r = 0; r < P; r++)
+    if (c->h_counts[r * NDX + ND + 2])
+      return ctx->fail(-c->h_counts[r * NDX + ND + 2], "GPU %d of this run failed with status %d (see its message)", r, -c->h_counts[r * NDX + ND + 2]);
   for (int dcode = 0; dcode < ND; dcode++) {
-    sendcnt[dcode] = c->send.peer[dcode] >= 0 ? c->h_counts[ctx->cfg.rank * ND + dcode] : 0;
+    sendcnt[dcode] = c->send.peer[dcode] >= 0 ? c->h_counts[ctx->cfg.rank * NDX + dcode] : 0;
     const int p = c->recv.peer[dcode];
-    recvcnt[dcode] = p >= 0 ? c->h_counts[p * ND + (ND - 1 - dcode)] : 0;
+    recvcnt[dcode] = p >= 0 ? c->h_counts[p * NDX + (ND - 1 - dcode)] : 0;
   }
   sendcnt[13] = recvcnt[13] = 0;
   return 0;
@@ -383,24 +400,27 @@ static int halo(sphbvf_ctx *ctx, int border) {
   const int R = NHALO + S + (ctx->with_dev ? 9 : 0) + (border ? 2 : 0);
   int rc;
   if ((rc = ensure_buf(ctx, (size_t)std::max(c->nsend, d.nghost) * R + 64))) return rc;
-  if (c->nsend)
+  if (c->nsend) {
     halo_pack_kernel<<<nblocks(c->nsend, 256), 256, 0, ctx->st>>>(d, S, ctx->with_dev, border, c->nsend, c->sendidx,
                                                                    c->send, c->sendbuf);
+    SPHBVF_LAUNCHED(1);
+  }
   int sendcnt[ND], recvcnt[ND];
   for (int k = 0; k < ND; k++) {
     sendcnt[k] = c->send.off[k + 1] - c->send.off[k];
     recvcnt[k] = c->recv.off[k + 1] - c->recv.off[k];
   }
   if ((rc = exchange_payload(ctx, sendcnt, c->send.off, recvcnt, c->recv.off, R))) return rc;
-  if (d.nghost)
+  if (d.nghost) {
     halo_unpack_kernel<<<nblocks(d.nghost, 256), 256, 0, ctx->st>>>(d, S, ctx->with_dev, border, c->recv, c->recvbuf);
+    SPHBVF_LAUNCHED(1);
+  }
   CK(cudaGetLastError());
   return 0;
 }
 
 int comm_forward(sphbvf_ctx *ctx) {
   if (!ctx->comm) return ctx->fail(SPHBVF_ECOMM, "sphbvf_comm_init has not been called");
-  ctx->launches_fam[K_PACK] += 2;
   return halo(ctx, 0);
 }
 
@@ -409,7 +429,7 @@ int comm_allreduce_max(sphbvf_ctx *ctx, int *vals, int n) {
   CommState *c = ctx->comm;
   if (!c) return ctx->fail(SPHBVF_ECOMM, "sphbvf_comm_init has not been called");
   if (n > 8) return ctx->fail(SPHBVF_EINVAL, "comm_allreduce_max: n > 8");
-  int *v = c->d_counts + 2 * ND + ND * ctx->cfg.nranks;
+  int *v = c->d_counts + 2 * NDX + NDX * ctx->cfg.nranks;
   for (int k = 0; k < n; k++) c->h_counts[k] = vals[k];
   CK(cudaMemcpyAsync(v, c->h_counts, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->st));
   NK(nccl_api()->AllReduce(v, v, n, ncclInt, ncclMax, c->comm, ctx->st));
@@ -421,10 +441,21 @@ int comm_allreduce_max(sphbvf_ctx *ctx, int *vals, int n) {
 
 int comm_vote(sphbvf_ctx *ctx, int *flag) { return comm_allreduce_max(ctx, flag, 1); }
 
+// Collective status: every rank passes the code of the local work it just did and all of them return the same
+// decision, so that nobody goes on to post sends / receives towards a rank that has already given up.
+static int comm_agree(sphbvf_ctx *ctx, int rc_local) {
+  int worst = rc_local ? -rc_local : 0;   // codes are negative
+  const int rc = comm_allreduce_max(ctx, &worst, 1);
+  if (rc_local) return rc_local;          // keep the local message
+  if (rc) return rc;
+  if (worst) return ctx->fail(-worst, "another GPU of this run failed with status %d (see its message)", -worst);
+  return 0;
+}
+
 int comm_allreduce_max_double(sphbvf_ctx *ctx, double *val) {
   CommState *c = ctx->comm;
   if (!c) return ctx->fail(SPHBVF_ECOMM, "sphbvf_comm_init has not been called");
-  double *v = (double *)(c->d_counts + ((2 * ND + ND * ctx->cfg.nranks + 9) & ~1));   // 8-byte aligned scratch
+  double *v = (double *)(c->d_counts + 2 * NDX + NDX * ctx->cfg.nranks + 8);   // 8-byte aligned scratch (NDX is even)
   double *h = (double *)(c->h_counts + 2);
   *h = *val;
   CK(cudaMemcpyAsync(v, h, sizeof(double), cudaMemcpyHostToDevice, ctx->st));
@@ -435,7 +466,37 @@ int comm_allreduce_max_double(sphbvf_ctx *ctx, double *val) {
   return 0;
 }
 
-// the rebuild branch of verlet.cpp:268-296 on a brick: pbc, exchange, sort, borders, list
+// the rebuild branch of verlet.cpp:268-296 on a brick: pbc, exchange, sort, borders, list.
+// Error protocol: rank-local work (allocations, launches) never returns between two collectives; its status goes
+// through comm_agree / the flag slots of exchange_counts, so all ranks leave with the same decision.
+static int migrate_prepare(sphbvf_ctx *ctx, const int *sendoff, int nleave, int narrive, int *cur) {
+  CommState *c = ctx->comm;
+  DevState &d = ctx->d;
+  NeighWork &w = ctx->w;
+  cudaStream_t st = ctx->st;
+  const int S = ctx->co.nspecies;
+  const int NM = 26 + S;
+  const int nstay = d.nlocal - nleave;
+  int rc;
+  if ((rc = ensure_buf(ctx, (size_t)std::max(nleave, narrive) * NM + 64))) return rc;
+  if (nstay + narrive > d.nmax) {
+    if ((rc = ctx_ensure_capacity(ctx, nstay + narrive + (nstay + narrive) / 8 + 1024, d.nallmax))) return rc;
+    if ((rc = ensure_dir(ctx, d.nmax))) return rc;
+  }
+  if (nleave) {
+    DirTable t = c->send;
+    for (int k = 0; k <= ND; k++) t.off[k] = sendoff[k];
+    keep_flag_kernel<<<nblocks(d.nlocal + 1, 256), 256, 0, st>>>(d.nlocal, c->d_dir, c->d_keep);
+    exclusive_scan(c->d_keep, c->d_pos, d.nlocal + 1, w.scan_tmp, st);
+    pack_leavers_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, S, c->d_dir, c->d_pos, w.perm, t, cur, c->sendbuf);
+    SPHBVF_LAUNCHED(2);
+    // compaction of the stayers, order preserved
+    if ((rc = permute_state(ctx, nstay, true))) return rc;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int comm_rebuild(sphbvf_ctx *ctx) {
   CommState *c = ctx->comm;
   if (!c) return ctx->fail(SPHBVF_ECOMM, "sphbvf_comm_init has not been called");
@@ -445,67 +506,51 @@ int comm_rebuild(sphbvf_ctx *ctx) {
   const int S = ctx->co.nspecies;
   const BrickGeom bg = geom(ctx);
   int rc;
-  ctx->tic(K_NEIGH, 48);
+  ctx->tic(K_NEIGH);
   CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * 8, st));
 
   // ---- migration (Comm::exchange)
-  if ((rc = ensure_dir(ctx, d.nlocal))) return rc;
-  int *cnt = c->d_counts, *cur = c->d_counts + ND;
-  CK(cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * ND, st));
-  if (d.nlocal) classify_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, bg, c->d_dir, cnt, w.flags);
+  rc = ensure_dir(ctx, d.nlocal);
+  int *cnt = c->d_counts, *cur = c->d_counts + NDX;
+  CK(cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * NDX, st));
+  if (!rc && d.nlocal) {
+    classify_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, bg, c->d_dir, cnt, w.flags);
+    SPHBVF_LAUNCHED(1);
+  }
   int sendcnt[ND], recvcnt[ND], sendoff[ND + 1], recvoff[ND + 1];
-  if ((rc = exchange_counts(ctx, cnt, sendcnt, recvcnt))) return rc;
-  if ((rc = ctx_fetch_flags(ctx))) return rc;
-  if (ctx->h_flags[0]) return ctx->fail(SPHBVF_ENONFINITE, "Non-numeric positions - simulation unstable");
-  if (ctx->h_flags[1]) return ctx->fail(SPHBVF_ELOST, "Lost atoms: an atom moved further than the neighbouring brick");
+  if ((rc = exchange_counts(ctx, cnt, sendcnt, recvcnt, "Lost atoms: an atom moved further than the neighbouring brick", rc))) return rc;
   sendoff[0] = recvoff[0] = 0;
   for (int k = 0; k < ND; k++) {
     sendoff[k + 1] = sendoff[k] + sendcnt[k];
     recvoff[k + 1] = recvoff[k] + recvcnt[k];
   }
   const int nleave = sendoff[ND], narrive = recvoff[ND];
+  rc = (nleave || narrive) ? migrate_prepare(ctx, sendoff, nleave, narrive, cur) : 0;
+  if ((rc = comm_agree(ctx, rc))) return rc;
   if (nleave || narrive) {
     const int NM = 26 + S;
     const int nstay = d.nlocal - nleave;
-    if ((rc = ensure_buf(ctx, (size_t)std::max(nleave, narrive) * NM + 64))) return rc;
-    if (nstay + narrive > d.nmax) {
-      if ((rc = ctx_ensure_capacity(ctx, nstay + narrive + (nstay + narrive) / 8 + 1024, d.nallmax))) return rc;
-      if ((rc = ensure_dir(ctx, d.nmax))) return rc;
-    }
-    if (nleave) {
-      DirTable t = c->send;
-      for (int k = 0; k <= ND; k++) t.off[k] = sendoff[k];
-      keep_flag_kernel<<<nblocks(d.nlocal + 1, 256), 256, 0, st>>>(d.nlocal, c->d_dir, c->d_keep);
-      exclusive_scan(c->d_keep, c->d_pos, d.nlocal + 1, w.scan_tmp, st);
-      pack_leavers_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, S, c->d_dir, c->d_pos, w.perm, t, cur, c->sendbuf);
-      // compaction of the stayers, order preserved
-      launch_permute(d.x, w.tmp_perm, w.perm, nstay, 3, 8, st);
-      launch_permute(d.v, w.tmp_perm, w.perm, nstay, 3, 8, st);
-      launch_permute(d.vest, w.tmp_perm, w.perm, nstay, 3, 8, st);
-      launch_permute(d.rho, w.tmp_perm, w.perm, nstay, 1, 8, st);
-      launch_permute(d.rhoI, w.tmp_perm, w.perm, nstay, 1, 8, st);
-      launch_permute(d.e, w.tmp_perm, w.perm, nstay, 1, 8, st);
-      if (S) launch_permute(d.C, w.tmp_perm, w.perm, nstay, S, 8, st);
-      launch_permute(d.dev, w.tmp_perm, w.perm, nstay, 9, 8, st);
-      for (int *p : {d.tag, d.type, d.mask, d.solid, d.fixed, d.slot}) launch_permute(p, w.tmp_perm, w.perm, nstay, 1, 4, st);
-    }
     if ((rc = exchange_payload(ctx, sendcnt, sendoff, recvcnt, recvoff, NM))) return rc;
     d.nlocal = nstay;
-    if (narrive) unpack_arrivals_kernel<<<nblocks(narrive, 256), 256, 0, st>>>(d, S, nstay, narrive, c->recvbuf);
+    if (narrive) {
+      unpack_arrivals_kernel<<<nblocks(narrive, 256), 256, 0, st>>>(d, S, nstay, narrive, c->recvbuf);
+      SPHBVF_LAUNCHED(1);
+    }
     d.nlocal = nstay + narrive;
     ctx->migrated = 1;
     CK(cudaGetLastError());
   }
 
   // ---- sort into cell order
-  if ((rc = rebuild_sort(ctx))) return rc;
+  rc = rebuild_sort(ctx);
 
   // ---- borders: who is a ghost of which neighbour brick (frozen until the next rebuild)
-  CK(cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * ND, st));
-  if (d.nlocal) border_kernel<false><<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, bg, ctx->cutneighmax, c->send, cnt, nullptr);
-  if ((rc = exchange_counts(ctx, cnt, sendcnt, recvcnt))) return rc;
-  if ((rc = ctx_fetch_flags(ctx))) return rc;
-  if (ctx->h_flags[1]) return ctx->fail(SPHBVF_ELOST, "Lost atoms: an owned atom left the cell grid of its brick");
+  CK(cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * NDX, st));
+  if (!rc && d.nlocal) {
+    border_kernel<false><<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, bg, ctx->cutneighmax, c->send, cnt, nullptr);
+    SPHBVF_LAUNCHED(1);
+  }
+  if ((rc = exchange_counts(ctx, cnt, sendcnt, recvcnt, "Lost atoms: an owned atom left the cell grid of its brick", rc))) return rc;
   c->send.off[0] = c->recv.off[0] = 0;
   for (int k = 0; k < ND; k++) {
     c->send.off[k + 1] = c->send.off[k] + sendcnt[k];
@@ -513,20 +558,33 @@ int comm_rebuild(sphbvf_ctx *ctx) {
   }
   c->nsend = c->send.off[ND];
   const int nghost = c->recv.off[ND];
-  if (c->nsend > c->send_cap) {
-    if (c->sendidx) cudaFree(c->sendidx);
-    c->send_cap = c->nsend + c->nsend / 4 + 1024;
-    CK(cudaMalloc((void **)&c->sendidx, sizeof(int) * (size_t)c->send_cap));
-  }
-  if (d.nlocal + nghost > d.nallmax)
-    if ((rc = ctx_ensure_capacity(ctx, d.nmax, d.nlocal + nghost + nghost / 4 + 1024))) return rc;
+  rc = [&]() -> int {
+    if (c->nsend > c->send_cap) {
+      if (c->sendidx) cudaFree(c->sendidx);
+      c->sendidx = nullptr;
+      c->send_cap = c->nsend + c->nsend / 4 + 1024;
+      CK(cudaMalloc((void **)&c->sendidx, sizeof(int) * (size_t)c->send_cap));
+    }
+    if (d.nlocal + nghost > d.nallmax) {
+      int rc2;
+      if ((rc2 = ctx_ensure_capacity(ctx, d.nmax, d.nlocal + nghost + nghost / 4 + 1024))) return rc2;
+    }
+    const int S2 = ctx->co.nspecies;
+    const int R = NHALO + S2 + (ctx->with_dev ? 9 : 0) + 2;
+    return ensure_buf(ctx, (size_t)std::max(c->nsend, nghost) * R + 64);
+  }();
+  if ((rc = comm_agree(ctx, rc))) return rc;
   d.nghost = nghost;
-  if (c->nsend) border_kernel<true><<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, bg, ctx->cutneighmax, c->send, cur, c->sendidx);
+  if (c->nsend) {
+    border_kernel<true><<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, bg, ctx->cutneighmax, c->send, cur, c->sendidx);
+    SPHBVF_LAUNCHED(1);
+  }
   CK(cudaMemcpyAsync(d.ptag, d.tag, sizeof(int) * (size_t)d.nlocal, cudaMemcpyDeviceToDevice, st));
   launch_pack(d, ctx->co, ctx->with_dev, st);
   if ((rc = halo(ctx, 1))) return rc;
 
-  if ((rc = rebuild_finish(ctx))) return rc;
+  rc = rebuild_finish(ctx);
+  if ((rc = comm_agree(ctx, rc))) return rc;
   ctx->toc();
   return 0;
 }
@@ -563,8 +621,8 @@ extern "C" int sphbvf_comm_init(sphbvf_ctx *ctx, const void *id128) {
   ncclUniqueId id;
   memcpy(&id, id128, sizeof id);
   NK(nccl_api()->CommInitRank(&c->comm, P, id, ctx->cfg.rank));
-  CK(cudaMalloc((void **)&c->d_counts, sizeof(int) * (2 * ND + ND * P + 16)));
-  CK(cudaMallocHost((void **)&c->h_counts, sizeof(int) * (ND * P + 8)));
+  CK(cudaMalloc((void **)&c->d_counts, sizeof(int) * (2 * NDX + NDX * P + 16)));
+  CK(cudaMallocHost((void **)&c->h_counts, sizeof(int) * (NDX * P + 16)));
   double shift[ND * 3];
   int rc = sphbvf_comm_plan(&ctx->cfg, ctx->cfg.rank, c->send.peer, shift);
   if (rc) return ctx->fail(rc, "sphbvf_comm_plan failed");

@@ -34,6 +34,11 @@ struct sphbvf_ctx {
   int fuse = 1, final_pending = 0, pack_valid = 0;
   double pend_dt = 0.0;
   long pend_step = 0;
+  int pair_pref = 0;           // 0: tile form when it fits (default), 1: gather form (SPHBVF_PAIR=gather)
+  int smem_optin = 0;          // cudaDevAttrMaxSharedMemoryPerBlockOptin of the device
+  int expanded_valid = 0;      // d.neigh holds the expansion of the current tile-form list (sphbvf_get_pairs)
+  int open_fam = -1;           // kernel family of the open tic()
+  long launch_mark = 0;
   int random_set = 0;
   double kboltz = 0.0;
   unsigned long long seed = 0;
@@ -52,13 +57,14 @@ struct sphbvf_ctx {
   EvPair ev_open{};
 
   int fail(int code, const char *fmt, ...);
-  void tic(int fam, int nlaunch = 1);
+  void tic(int fam);
   void toc();
   void drain_events();
 };
 
 // capi.cu: rebuild pieces shared with the brick-decomposed path
 int rebuild_sort(sphbvf_ctx *ctx);       // pbc + cell sort + permutation of the primary arrays
+int permute_state(sphbvf_ctx *ctx, int n, bool always_dev);   // primary arrays gathered through w.perm, buffers swapped
 int rebuild_finish(sphbvf_ctx *ctx);     // ghost binning + Verlet list + xhold
 int ctx_ensure_capacity(sphbvf_ctx *ctx, int nmax, int nallmax);
 int ctx_fetch_flags(sphbvf_ctx *ctx);    // w.flags -> h_flags[0..8), synchronises the stream

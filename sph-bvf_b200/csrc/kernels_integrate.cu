@@ -22,7 +22,9 @@ __global__ void setup_pre_force_kernel(const DevState d, int groupbit) {
 }
 
 void launch_setup_pre_force(const DevState &d, int groupbit, cudaStream_t st) {
-  if (d.nlocal) setup_pre_force_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, groupbit);
+  if (!d.nlocal) return;
+  setup_pre_force_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, groupbit);
+  SPHBVF_LAUNCHED(1);
 }
 
 __device__ __forceinline__ void damp_factors(int variant, long ntimestep, double &damp, double &dampSolid) {
@@ -44,22 +46,24 @@ __device__ __forceinline__ int ldi(const int *p) {
 }
 
 // pack: primary state -> pair input records.  Holds every per-particle division of the pair pass:
-// V = m/rho, P/rho^2 with P = 7 B (rho/rho0 - 1) (pair_...transport_velocity.cpp:298-299), and the
-// scalar artificial stress of a stress-free solid (:454-461 with dev = 0).  Shared by pack_kernel and
-// the fused integrator so both produce the same bits.
+// V = m/rho, P/rho^2 = kp V (m - rho0 V) (the Tait law P = c0^2 (rho - rho0) of pair_...transport_velocity.cpp:298-299
+// written in terms of V, prr_from_v: the tile-staged pair kernel recomputes it from V with the same operations),
+// u = rho (vest - v), and the scalar artificial stress of a stress-free solid (:454-461 with dev = 0).  Shared by
+// pack_kernel and the fused integrator so both produce the same bits.
 __device__ __forceinline__ void pack_atom(const DevState &d, const Coeffs &co, const int i, const int t, const int solid,
                                           const int fixed, const double *x, const double *v, const double *vest,
                                           const double rho, const double rhoI, const double e, const int with_dev) {
   const double irho = 1.0 / rho;
-  const double P = 7.0 * co.B[t] * (rho / co.rho0[t] - 1.0);
-  const double Prr = P * irho * irho;
+  const double V = co.mass[t] * irho;
+  const double Prr = prr_from_v(co.kp[t], co.rho0[t], co.mass[t], V);
   Prec r;
-  r.A = make_rec4(x[0], x[1], x[2], rho);
-  r.B = make_rec4(vest[0], vest[1], vest[2], co.mass[t] * irho);
-  r.C = make_rec4(vest[0] - v[0], vest[1] - v[1], vest[2] - v[2], Prr);
+  r.A = make_rec4(x[0], x[1], x[2], V);
+  r.B = make_rec4(vest[0], vest[1], vest[2], rho * (vest[0] - v[0]));
+  r.C = make_rec4(rho * (vest[1] - v[1]), rho * (vest[2] - v[2]), rho, Prr);
   d.prec[i] = r;
   double art = 0.0;
   if (solid) {
+    const double P = 7.0 * co.B[t] * (rho / co.rho0[t] - 1.0);
     const double c_art = co.variant == SPHBVF_FSI ? 0.1 : 0.35;
     const double Ps = co.variant == SPHBVF_MECHANICS ? fabs(P) : P;
     const double ts = -Ps;
@@ -270,6 +274,7 @@ static void launch_integrate(const DevState &d, const Coeffs &co, const IntegArg
   if (co.variant == SPHBVF_TV) integrate_kernel<SPHBVF_TV, MODE><<<b, 256, 0, st>>>(d, co, a);
   else if (co.variant == SPHBVF_MECHANICS) integrate_kernel<SPHBVF_MECHANICS, MODE><<<b, 256, 0, st>>>(d, co, a);
   else integrate_kernel<SPHBVF_FSI, MODE><<<b, 256, 0, st>>>(d, co, a);
+  SPHBVF_LAUNCHED(1);
 }
 
 void launch_initial_integrate(const DevState &d, const Coeffs &co, double dt, long ntimestep, int groupbit,
@@ -360,7 +365,9 @@ __global__ void max_vsq_kernel(const DevState d, const int groupbit, unsigned lo
 }
 
 void launch_max_vsq(const DevState &d, int groupbit, unsigned long long *out, cudaStream_t st) {
-  if (d.nlocal) max_vsq_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, groupbit, out);
+  if (!d.nlocal) return;
+  max_vsq_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, groupbit, out);
+  SPHBVF_LAUNCHED(1);
 }
 
 // sum over the atoms of `groupbit` of m v_a v_b (v = atom->v), LAMMPS order xx yy zz xy xz yz: what
@@ -416,6 +423,7 @@ void launch_ke_tensor(const DevState &d, const Coeffs &co, int groupbit, double 
   const int nb = nblocks(d.nlocal > 0 ? d.nlocal : 1, 256);
   ke_partial_kernel<<<nb, 256, 0, st>>>(d, co, groupbit, scratch);
   ke_final_kernel<<<1, 256, 0, st>>>(scratch, nb, out6);
+  SPHBVF_LAUNCHED(2);
 }
 
 // hook: 0 post_integrate, 1 post_force, 2 end_of_step
@@ -434,7 +442,9 @@ bool fix_runs(const FixDesc &fx, int hook, long ntimestep) {
 
 void launch_fix(const DevState &d, const Coeffs &co, const FixDesc &fx, int hook, long ntimestep, cudaStream_t st) {
   if (!d.nlocal) return;
-  if (fix_runs(fx, hook, ntimestep)) fix_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, co, fx, hook);
+  if (!fix_runs(fx, hook, ntimestep)) return;
+  fix_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, co, fx, hook);
+  SPHBVF_LAUNCHED(1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -453,7 +463,9 @@ pack_kernel(const DevState d, const __grid_constant__ Coeffs co, const int with_
 }
 
 void launch_pack(const DevState &d, const Coeffs &co, int with_dev, cudaStream_t st) {
-  if (d.nlocal) pack_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, co, with_dev);
+  if (!d.nlocal) return;
+  pack_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, co, with_dev);
+  SPHBVF_LAUNCHED(1);
 }
 
 // self-image ghosts (periodic boundaries inside one rank): copy the owner's packed record and
@@ -478,7 +490,9 @@ __global__ void ghost_refresh_kernel(const DevState d, const int S, const int wi
 }
 
 void launch_ghost_refresh(const DevState &d, const Coeffs &co, int with_dev, cudaStream_t st) {
-  if (d.nghost) ghost_refresh_kernel<<<nblocks(d.nghost, 256), 256, 0, st>>>(d, co.nspecies, with_dev);
+  if (!d.nghost) return;
+  ghost_refresh_kernel<<<nblocks(d.nghost, 256), 256, 0, st>>>(d, co.nspecies, with_dev);
+  SPHBVF_LAUNCHED(1);
 }
 
 }  // namespace sphbvf

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "sphbvf_internal.cuh"
+#include "tile_common.cuh"
 
 namespace sphbvf {
 
@@ -36,7 +37,9 @@ __global__ void check_distance_kernel(const DevState d, const double triggersq, 
 }
 
 void launch_check_distance(const DevState &d, double triggersq, int *flag_moved, cudaStream_t st) {
-  if (d.nlocal) check_distance_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, triggersq, flag_moved);
+  if (!d.nlocal) return;
+  check_distance_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, triggersq, flag_moved);
+  SPHBVF_LAUNCHED(1);
 }
 
 __device__ __forceinline__ int cell_of(const Grid &g, double x, double y, double z, bool &ok) {
@@ -73,7 +76,9 @@ __global__ void pbc_cellid_kernel(const DevState d, const Box b, const Grid g, i
 
 void launch_cell_ids(const DevState &d, const Grid &g, const Box &b, const NeighWork &w, cudaStream_t st) {
   cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (g.ncells + 1), st);
-  if (d.nlocal) pbc_cellid_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, b, g, w.cellid, w.cell_count, w.flags);
+  if (!d.nlocal) return;
+  pbc_cellid_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, b, g, w.cellid, w.cell_count, w.flags);
+  SPHBVF_LAUNCHED(1);
 }
 
 // ---------------------------------------------------------------- exclusive scan (int32)
@@ -134,11 +139,13 @@ void exclusive_scan(const int *in, int *out, long n, int *tmp, cudaStream_t st) 
   const long nb = (n + SCAN_B - 1) / SCAN_B;
   if (nb == 1) {
     scan_block_kernel<<<1, SCAN_T, 0, st>>>(in, out, n, nullptr);
+    SPHBVF_LAUNCHED(1);
     return;
   }
   scan_block_kernel<<<(int)nb, SCAN_T, 0, st>>>(in, out, n, tmp);
   exclusive_scan(tmp, tmp, nb, tmp + nb, st);
   scan_add_kernel<<<(int)nb, SCAN_T, 0, st>>>(out, n, tmp);
+  SPHBVF_LAUNCHED(2);
 }
 
 // ---------------------------------------------------------------- counting sort of owned atoms
@@ -171,6 +178,7 @@ void launch_sort_owned(const DevState &d, const Grid &g, const NeighWork &w, cud
   if (!d.nlocal) return;
   scatter_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d.nlocal, w.cellid, w.cell_start, w.cell_count, w.perm);
   cell_order_kernel<<<nblocks(g.ncells, 256), 256, 0, st>>>(g.ncells, w.cell_start, w.perm, d.tag);
+  SPHBVF_LAUNCHED(2);
 }
 
 template <typename T>
@@ -187,7 +195,40 @@ void launch_permute(void *arr, void *tmp, const int *perm, int n, int ncols, int
   const long tot = (long)n * ncols;
   if (elem_bytes == 8) permute_kernel<double><<<nblocks(tot, 256), 256, 0, st>>>((const double *)arr, (double *)tmp, perm, n, ncols);
   else permute_kernel<int><<<nblocks(tot, 256), 256, 0, st>>>((const int *)arr, (int *)tmp, perm, n, ncols);
+  SPHBVF_LAUNCHED(1);
   cudaMemcpyAsync(arr, tmp, (size_t)tot * elem_bytes, cudaMemcpyDeviceToDevice, st);
+}
+
+// Every primary array in one pass: out.<f>[i] = in.<f>[perm[i]].  One thread per atom; the reads of a warp are a
+// near-sequential gather (a rebuild moves atoms by a few cells), the writes are coalesced.  The caller swaps the two
+// buffers afterwards, so nothing is copied back (the per-array permute above wrote a staging buffer and copied it
+// back: twice the bytes and 28 launches per rebuild).
+__global__ void __launch_bounds__(256)
+gather_state_kernel(const StateArrays in, const StateArrays out, const int *__restrict__ perm, const int n, const int S,
+                    const int with_dev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int o = perm[i];
+  const size_t i3 = 3 * (size_t)i, o3 = 3 * (size_t)o;
+  const int tag = in.tag[o], type = in.type[o], mask = in.mask[o], solid = in.solid[o], fixed = in.fixed[o], slot = in.slot[o];
+  double x[3], v[3], ve[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { x[k] = in.x[o3 + k]; v[k] = in.v[o3 + k]; ve[k] = in.vest[o3 + k]; }
+  const double rho = in.rho[o], rhoI = in.rhoI[o], e = in.e[o];
+  out.tag[i] = tag; out.type[i] = type; out.mask[i] = mask; out.solid[i] = solid; out.fixed[i] = fixed; out.slot[i] = slot;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { out.x[i3 + k] = x[k]; out.v[i3 + k] = v[k]; out.vest[i3 + k] = ve[k]; }
+  out.rho[i] = rho; out.rhoI[i] = rhoI; out.e[i] = e;
+  for (int k = 0; k < S; k++) out.C[(size_t)i * S + k] = in.C[(size_t)o * S + k];
+  if (with_dev)
+    for (int k = 0; k < 9; k++) out.dev[9 * (size_t)i + k] = in.dev[9 * (size_t)o + k];
+}
+
+void launch_gather_state(const StateArrays &in, const StateArrays &out, const int *perm, int n, int S, int with_dev,
+                         cudaStream_t st) {
+  if (!n) return;
+  gather_state_kernel<<<nblocks(n, 256), 256, 0, st>>>(in, out, perm, n, S, with_dev);
+  SPHBVF_LAUNCHED(1);
 }
 
 // ---------------------------------------------------------------- periodic self-image ghosts
@@ -235,11 +276,14 @@ __global__ void fill_images_kernel(const DevState d, const Box b, const double c
 
 void launch_count_images(const DevState &d, const Box &b, double cutghost, const NeighWork &w, cudaStream_t st) {
   count_images_kernel<<<nblocks(d.nlocal + 1, 256), 256, 0, st>>>(d, b, cutghost, w.nimg);
+  SPHBVF_LAUNCHED(1);
   exclusive_scan(w.nimg, w.nimg, d.nlocal + 1, w.scan_tmp, st);
 }
 
 void launch_fill_images(const DevState &d, const Box &b, double cutghost, const NeighWork &w, cudaStream_t st) {
-  if (d.nlocal) fill_images_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, b, cutghost, w.nimg);
+  if (!d.nlocal) return;
+  fill_images_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, b, cutghost, w.nimg);
+  SPHBVF_LAUNCHED(1);
 }
 
 // ---------------------------------------------------------------- ghosts into cells (index sort)
@@ -271,6 +315,7 @@ void launch_bin_ghosts(const DevState &d, const Grid &g, const NeighWork &w, cud
   cudaMemsetAsync(w.gcell_count, 0, sizeof(int) * (g.ncells + 1), st);
   ghost_scatter_kernel<<<nblocks(d.nghost, 256), 256, 0, st>>>(d, w.cellid, w.gcell_start, w.gcell_count, w.gorder);
   cell_order_kernel<<<nblocks(g.ncells, 256), 256, 0, st>>>(g.ncells, w.gcell_start, w.gorder, d.ptag + d.nlocal);
+  SPHBVF_LAUNCHED(3);
 }
 
 // ---------------------------------------------------------------- Verlet list
@@ -301,20 +346,17 @@ void launch_bin_ghosts(const DevState &d, const Grid &g, const NeighWork &w, cud
 constexpr int TB_U = TB_UNROLL;               // unroll factor of the sweep
 constexpr int TB_T = TB_THREADS;              // threads per CTA: a bulk 3D tile holds 125..216 atoms (one batch)
 constexpr int TB_CH = 1536;                   // staged candidates per chunk (48 KB, dynamic): a bulk halo is <= 11^3
-constexpr int TB_NH = 1;                      // 2: stage the halo as two y-halves (24 KB chunks, 8 CTAs/SM): measured slower
-constexpr int TB_MAXROW = 64;                 // (y,z) rows of the halo: 8 x 8 in 3D, 12 x 1 in 2D
-constexpr int TB_MAXSEG = TB_MAXROW * 3 * 2;  // x-parts per row (<= 3 tiles) x {owned, ghost}
-constexpr int TB_MAXLAY = 12;                 // z-layers of the halo (8 in 3D, 1 in 2D)
 
 struct __align__(16) Cand {   // two LDS.128 broadcasts per candidate: {x, y} and {z, entry}
   double2 xy;
   double2 ze;
 };
 
-// TB_NH == 2 stages the halo in two halves (low-y rows, then high-y rows): every warp has work in both halves (a
-// warp's atoms span the tile in y) and inside a half the rows stay z-major, so the z-layers a warp can reach are
-// still one contiguous range.  With TB_NH == 1 the second half is empty.
-template <bool UNIFORM>
+// LIST16 = false: gather form, 32-bit entries j | type_j << 27 | solid_j << 30 written transposed (neigh[k * stride + i]).
+// LIST16 = true:  tile form, 16-bit entries slot | type_j << 12 | solid_j << 15 written row-major; a thread collects
+//                 four entries in a 64-bit shift register and stores 8 aligned bytes at a time (a quarter of the
+//                 scattered store instructions of the 4-byte emission, which cost 3.4 of 10.3 ms per rebuild).
+template <bool UNIFORM, bool LIST16>
 __global__ void __launch_bounds__(TB_T)
 build_list_tile_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_constant__ Coeffs co,
                        const int *__restrict__ cell_start, const int *__restrict__ gcell_start,
@@ -323,77 +365,18 @@ build_list_tile_kernel(const DevState d, const __grid_constant__ Grid g, const _
   Cand *cand = reinterpret_cast<Cand *>(tb_smem);
   __shared__ int seg_src[TB_MAXSEG];
   __shared__ int seg_off[TB_MAXSEG + 1];
-  __shared__ int layer_off[2][TB_MAXLAY + 1];
+  __shared__ int layer_off[TB_MAXLAY + 1];
 
   const int tid = threadIdx.x;
-  const int bits = g.tb[0] + g.tb[1] + g.tb[2];
-  const int tile = blockIdx.x;
-  const int first = cell_start[(long)tile << bits], last = cell_start[((long)tile + 1) << bits];
-  if (first == last) return;   // empty tile (whole CTA)
-  const int tx = tile % g.nt[0], ty = (tile / g.nt[0]) % g.nt[1], tz = tile / (g.nt[0] * g.nt[1]);
-  const int x0 = tx << g.tb[0], y0 = ty << g.tb[1], z0 = tz << g.tb[2];
-  const int hx0 = max(x0 - g.s[0], 0), hx1 = min(x0 + (1 << g.tb[0]) - 1 + g.s[0], g.n[0] - 1);
-  const int hy0 = max(y0 - g.s[1], 0), hy1 = min(y0 + (1 << g.tb[1]) - 1 + g.s[1], g.n[1] - 1);
-  const int hz0 = max(z0 - g.s[2], 0), hz1 = min(z0 + (1 << g.tb[2]) - 1 + g.s[2], g.n[2] - 1);
-  const int ny = hy1 - hy0 + 1, nz = hz1 - hz0 + 1;
-  const int nya = TB_NH == 2 ? (ny + 1) >> 1 : ny;   // rows of the first half; the second has ny - nya
-  const int nseg_a = nz * nya * 6, nseg = nz * ny * 6;
-  const int tmask = (1 << g.tb[0]) - 1;
-  const bool have_ghosts = d.nghost > 0;
-
-  // ---- segment table: (half, z, y, x-part, owned|ghost) -> contiguous source range
-  for (int sid = tid; sid < nseg; sid += TB_T) {
-    const int half = sid >= nseg_a;
-    const int rs = half ? sid - nseg_a : sid, nyh = half ? ny - nya : nya;
-    const int pass = rs & 1, part = (rs >> 1) % 3, row = rs / 6;
-    const int y = hy0 + (half ? nya : 0) + row % nyh, z = hz0 + row / nyh;
-    int x = hx0, xe = min(hx1, x | tmask);
-    for (int q = 0; q < part && x <= hx1; q++) { x = xe + 1; xe = min(hx1, x | tmask); }
-    int a = 0, len = 0;
-    if (x <= hx1 && (pass == 0 || have_ghosts)) {
-      const int *start = pass ? gcell_start : cell_start;
-      const int c0 = cell_index(g, x, y, z), c1 = c0 + (xe - x);
-      a = start[c0];
-      len = start[c1 + 1] - a;
-    }
-    seg_src[sid] = a | (pass << 31);
-    seg_off[sid] = len;
-  }
+  TileGeom t;
+  if (!tile_geometry(g, blockIdx.x, cell_start, t)) return;   // empty tile (whole CTA)
+  const int first = t.first, last = t.last, hz0 = t.hz0, hz1 = t.hz1, nz = t.nz, nseg = t.nseg;
+  tile_segments(g, t, cell_start, gcell_start, d.nghost > 0, seg_src, seg_off);
+  if (tid <= nz) layer_off[tid] = seg_off[tid * t.ny * 6];
+  if (tid == 0) atomicMax(&flags[4], seg_off[nseg]);
   __syncthreads();
-  if (tid < 32) {   // exclusive scan of <= 384 lengths: 12 per lane
-    constexpr int PER = TB_MAXSEG / 32;
-    int v[PER], sum = 0;
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-      const int sid = tid * PER + k;
-      v[k] = sid < nseg ? seg_off[sid] : 0;
-      sum += v[k];
-    }
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (tid >= o) incl += y;
-    }
-    int run = incl - sum;
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-      const int sid = tid * PER + k;
-      if (sid <= nseg) seg_off[sid] = run;
-      run += v[k];
-    }
-    if (tid == 31) seg_off[nseg] = run;   // nseg == TB_MAXSEG: no lane owns that slot
-  }
-  __syncthreads();
-  if (tid <= nz) {
-    layer_off[0][tid] = seg_off[tid * nya * 6];
-    layer_off[1][tid] = seg_off[nseg_a + tid * (ny - nya) * 6];
-  }
-  __syncthreads();
+  const int total = seg_off[nseg];
   const size_t stride = d.stride;
-#ifdef TB_DIAG_NOSTORE
-  const bool nostore = flags[7] != 0;
-#endif
 
   for (int base = first; base < last; base += TB_T) {
     const int i = base + tid;
@@ -403,7 +386,7 @@ build_list_tile_kernel(const DevState d, const __grid_constant__ Grid g, const _
     if (valid) { Ai = d.prec[i].A; ti = d.pflags[i] & 7; }
     double cut_i[MAXT];
 #pragma unroll
-    for (int t = 0; t < MAXT; t++) cut_i[t] = UNIFORM ? cutmaxsq : co.cutneighsq[ti][t];
+    for (int q = 0; q < MAXT; q++) cut_i[q] = UNIFORM ? cutmaxsq : co.cutneighsq[ti][q];
     // halo z-layers this WARP can reach
     int llo = TB_MAXLAY, lhi = -1;
     if (valid) {
@@ -419,60 +402,93 @@ build_list_tile_kernel(const DevState d, const __grid_constant__ Grid g, const _
     }
     int n = 0;
     int *out = d.neigh + (valid ? i : first);
-    const int maxn = valid ? d.maxneigh : 0;
+    const int maxn = valid ? (LIST16 ? d.pitch16 : d.maxneigh) : 0;
+    unsigned long long *row64 = LIST16 ? reinterpret_cast<unsigned long long *>(d.neigh16 + (size_t)(valid ? i : first) * d.pitch16) : nullptr;
+    unsigned long long acc = 0;
+    const int wq0 = lhi >= 0 ? layer_off[llo] : 0, wq1 = lhi >= 0 ? layer_off[lhi + 1] : 0;
 
-    for (int half = 0; half < 2; half++) {
-      const int h0 = half ? seg_off[nseg_a] : 0, h1 = half ? seg_off[nseg] : seg_off[nseg_a];
-      const int wq0 = lhi >= 0 ? layer_off[half][llo] : 0, wq1 = lhi >= 0 ? layer_off[half][lhi + 1] : 0;
-      for (int clo = h0; clo < h1; clo += TB_CH) {
-        const int chi = min(h1, clo + TB_CH);
-        // ---- stage candidates clo .. chi
-        for (int q = clo + tid; q < chi; q += TB_T) {
-          int lo = 0, hi = nseg;   // largest sid with seg_off[sid] <= q
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (seg_off[mid] <= q) lo = mid; else hi = mid;
-          }
-          const int src = seg_src[lo];
-          const int p = (src & 0x7fffffff) + (q - seg_off[lo]);
-          const int j = src < 0 ? d.nlocal + gorder[p] : p;
-          const Rec4 A = d.prec[j].A;
-          const int fj = d.pflags[j];
-          Cand c;
-          c.xy = make_double2(A.x, A.y);
-          c.ze = make_double2(A.z, __hiloint2double(0, j | ((fj & 7) << NEIGH_JBITS) | (((fj >> 4) & 1) << 30)));
-          cand[q - clo] = c;
+    for (int clo = 0; clo < total; clo += TB_CH) {
+      const int chi = min(total, clo + TB_CH);
+      // ---- stage candidates clo .. chi
+      for (int q = clo + tid; q < chi; q += TB_T) {
+        int lo = 0, hi = nseg;   // largest sid with seg_off[sid] <= q
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (seg_off[mid] <= q) lo = mid; else hi = mid;
         }
-        __syncthreads();
-        // ---- converged sweep with the exact criterion
-        const int qa = max(wq0, clo) - clo, qb = min(wq1, chi) - clo;
+        const int j = tile_source(seg_src[lo], q - seg_off[lo], d.nlocal, gorder);
+        const Rec4 A = d.prec[j].A;
+        const int fj = d.pflags[j];
+        Cand c;
+        c.xy = make_double2(A.x, A.y);
+        c.ze = make_double2(A.z, __hiloint2double(0, j | ((fj & 7) << NEIGH_JBITS) | (((fj >> 4) & 1) << 30)));
+        cand[q - clo] = c;
+      }
+      __syncthreads();
+      // ---- converged sweep with the exact criterion
+      const int qa = max(wq0, clo) - clo, qb = min(wq1, chi) - clo;
 #pragma unroll TB_U
-        for (int q = qa; q < qb; q++) {
-          const double2 cxy = cand[q].xy, cze = cand[q].ze;
-          const int ent = __double2loint(cze.y);
-          const double rsq = rsq_nofma(Ai.x - cxy.x, Ai.y - cxy.y, Ai.z - cze.x);
-          double cut = cut_i[0];
-          if (!UNIFORM) {
-            const int tj = (ent >> NEIGH_JBITS) & 7;
+      for (int q = qa; q < qb; q++) {
+        const double2 cxy = cand[q].xy, cze = cand[q].ze;
+        const int ent = __double2loint(cze.y);
+        const double rsq = rsq_nofma(Ai.x - cxy.x, Ai.y - cxy.y, Ai.z - cze.x);
+        double cut = cut_i[0];
+        if (!UNIFORM) {
+          const int tj = (ent >> NEIGH_JBITS) & 7;
 #pragma unroll
-            for (int t = 1; t < MAXT; t++) cut = tj == t ? cut_i[t] : cut;
-          }
-          if (rsq <= cut && (ent & NEIGH_JMASK) != i) {
-#ifdef TB_DIAG_NOSTORE   // tools/: measure what the scattered emission costs (the list keeps its previous content)
-            if (n < maxn && !nostore) out[(size_t)n * stride] = ent;
-#else
+          for (int q2 = 1; q2 < MAXT; q2++) cut = tj == q2 ? cut_i[q2] : cut;
+        }
+        if (rsq <= cut && (ent & NEIGH_JMASK) != i) {
+          if (LIST16) {
+            const unsigned e16 = (unsigned)(q + clo) | (((unsigned)ent >> NEIGH_JBITS) & 7u) << TILE_SLOT_BITS | (((unsigned)ent >> 30) & 1u) << 15;
+            acc = (acc >> 16) | ((unsigned long long)e16 << 48);
+            n++;
+            if ((n & 3) == 0 && n <= maxn) row64[(n >> 2) - 1] = acc;
+          } else {
             if (n < maxn) out[(size_t)n * stride] = ent;
-#endif
             n++;
           }
         }
-        // the staging area is reused only if another chunk, half or batch of atoms follows (CTA-uniform)
-        if (chi < h1 || (half == 0 && seg_off[nseg] > seg_off[nseg_a]) || base + TB_T < last) __syncthreads();
       }
+      // the staging area is reused only if another chunk or batch of atoms follows (CTA-uniform)
+      if (chi < total || base + TB_T < last) __syncthreads();
     }
     if (valid) {
-      d.numneigh[i] = n < d.maxneigh ? n : d.maxneigh;
+      if (LIST16 && (n & 3) && n < maxn) row64[n >> 2] = acc >> (16 * (4 - (n & 3)));   // partial last word (maxn is a multiple of 8)
+      d.numneigh[i] = n < maxn ? n : maxn;
       atomicMax(&flags[2], n);
+    }
+  }
+}
+
+// tile form -> gather form: d.neigh[k * stride + i] = j | type_j << 27 | solid_j << 30 for every 16-bit entry.  One CTA
+// per tile; slot -> global index through the same enumeration the builder used.  For sphbvf_get_pairs and for tests
+// that run the gather kernel on a list built in tile form; never on the timestep path.
+__global__ void __launch_bounds__(256)
+expand_list_kernel(const DevState d, const __grid_constant__ Grid g, const int *__restrict__ cell_start,
+                   const int *__restrict__ gcell_start, const int *__restrict__ gorder) {
+  __shared__ int seg_src[TB_MAXSEG];
+  __shared__ int seg_off[TB_MAXSEG + 1];
+  __shared__ int gidx[TILE_MAX_SLOTS];
+  TileGeom t;
+  if (!tile_geometry(g, blockIdx.x, cell_start, t)) return;
+  tile_segments(g, t, cell_start, gcell_start, d.nghost > 0, seg_src, seg_off);
+  const int total = min(seg_off[t.nseg], TILE_MAX_SLOTS);
+  for (int q = threadIdx.x; q < total; q += blockDim.x) {
+    int lo = 0, hi = t.nseg;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (seg_off[mid] <= q) lo = mid; else hi = mid;
+    }
+    gidx[q] = tile_source(seg_src[lo], q - seg_off[lo], d.nlocal, gorder);
+  }
+  __syncthreads();
+  for (int i = t.first + threadIdx.x; i < t.last; i += blockDim.x) {
+    const int nn = d.numneigh[i];
+    const unsigned short *row = d.neigh16 + (size_t)i * d.pitch16;
+    for (int k = 0; k < nn; k++) {
+      const unsigned e = row[k];
+      d.neigh[(size_t)k * d.stride + i] = gidx[e & TILE_SLOT_MASK] | (int)((e >> TILE_SLOT_BITS) & 7u) << NEIGH_JBITS | (int)(e >> 15) << 30;
     }
   }
 }
@@ -554,6 +570,14 @@ build_list_kernel(const DevState d, const __grid_constant__ Grid g, const __grid
   atomicMax(&flags[2], n);
 }
 
+bool tile_form_possible(const Grid &g) {
+  // the halo of a tile must fit the segment tables: stencil half-width <= 2 cells (always true for cells of
+  // cutneigh/2, init_neighbor), <= 64 (y,z) rows, <= 12 z-layers
+  const int ny = (1 << g.tb[1]) + 2 * g.s[1], nz = g.dim == 3 ? (1 << g.tb[2]) + 2 * g.s[2] : 1;
+  return ny * nz <= TB_MAXROW && nz <= TB_MAXLAY;
+}
+
+// d.list16 selects the encoding (and with it the builder: the tile form exists only for the tile builder)
 void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const NeighWork &w, cudaStream_t st) {
   double cutmax = 0.0;
   bool uniform = true;
@@ -564,33 +588,40 @@ void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const
     }
   if (!d.nlocal) return;
   const char *env = getenv("SPHBVF_LIST_BUILD");   // read per rebuild so that tests can compare both builders
-  const bool per_thread = env && env[0] == 't';
-  // the tile builder needs the halo of a tile to fit its tables: stencil half-width <= 2 cells (always true for
-  // cells of cutneigh/2, init_neighbor) and <= 64 (y,z) rows
-  const int ny = (1 << g.tb[1]) + 2 * g.s[1], nz = g.dim == 3 ? (1 << g.tb[2]) + 2 * g.s[2] : 1;
-  if (!per_thread && ny * nz <= TB_MAXROW && nz <= TB_MAXLAY) {
+  const bool per_thread = env && env[0] == 't' && !d.list16;
+  if (!per_thread && tile_form_possible(g)) {
     const long ntiles = (long)g.nt[0] * g.nt[1] * g.nt[2];
     constexpr int smem = TB_CH * (int)sizeof(Cand);
-#ifdef TB_DIAG_NOSTORE
-    { const char *e = getenv("SPHBVF_TB_NOSTORE"); const int v = e && atoi(e); cudaMemcpyAsync(w.flags + 7, &v, sizeof(int), cudaMemcpyHostToDevice, st); cudaStreamSynchronize(st); }
-#endif
     // the opt-in to > 48 KB of dynamic shared memory is per device (one process may drive several GPUs, each from
     // its own thread): setting it again is harmless, missing it is a launch failure
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      cudaFuncSetAttribute(build_list_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      cudaFuncSetAttribute(build_list_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(build_list_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(build_list_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(build_list_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(build_list_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    if (uniform) build_list_tile_kernel<true><<<(int)ntiles, TB_T, smem, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
-    else build_list_tile_kernel<false><<<(int)ntiles, TB_T, smem, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
+#define TBK(U, L) build_list_tile_kernel<U, L><<<(int)ntiles, TB_T, smem, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags)
+    if (d.list16) { if (uniform) TBK(true, true); else TBK(false, true); }
+    else { if (uniform) TBK(true, false); else TBK(false, false); }
+#undef TBK
+    SPHBVF_LAUNCHED(1);
     return;
   }
   const int nb = nblocks(d.nlocal, 128);
   if (uniform) build_list_kernel<true><<<nb, 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
   else build_list_kernel<false><<<nb, 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
+  SPHBVF_LAUNCHED(1);
+}
+
+void launch_expand_list(const DevState &d, const Grid &g, const NeighWork &w, cudaStream_t st) {
+  if (!d.nlocal) return;
+  const long ntiles = (long)g.nt[0] * g.nt[1] * g.nt[2];
+  expand_list_kernel<<<(int)ntiles, 256, 0, st>>>(d, g, w.cell_start, w.gcell_start, w.gorder);
+  SPHBVF_LAUNCHED(1);
 }
 
 void launch_copy_xhold(const DevState &d, cudaStream_t st) {

@@ -9,50 +9,51 @@
 // The reference's sweep A (number density, Shepard sums, transport-velocity correction ddv, ddx)
 // and sweep B (forces, drho, phi, wall normal, Jaumann rate, species flux) read only particle
 // state and write disjoint outputs, so they share one loop, one sqrt and one set of neighbour
-// loads.  Sweep C (v_weighted_solid / a_weighted_solid) is never consumed and the
-// random stress term is omitted (reference seed is clock(); exactly zero in all decks with e=0).
+// loads.  Sweep C (v_weighted_solid / a_weighted_solid) is never consumed.  The
+// stochastic stress (active when some ssa_tsdpd/e != 0) is a counter-based pair noise (Philox), see RANDOM below.
 //
-// Mapping: one thread per owned atom, 128-thread CTAs, atoms in tile-major cell order so a CTA
-// covers a compact cube.  The kernel is FP64-pipe / latency bound, not HBM bound (ncu, profiles/):
-//   * the neighbour loop is software pipelined by hand: while neighbour k is evaluated, the three
-//     32-byte records of neighbour k+1 (one 256-bit LDG each) and the list entry k+2 are in
-//     flight, so an L2 round trip is overlapped with ~75 FP64 instructions of useful work;
-//   * list entries are read transposed (coalesced) and carry type_j and solid_tag_j, so the hot
-//     loop has no flag gather;
-//   * every per-particle division lives in the pack kernel (V = m/rho, P/rho^2), sqrt is a
-//     branch-free Goldschmidt iteration on MUFU.RSQ64H (7 FP64 ops, < 1 ulp);
-//   * per-type-pair coefficients: when every type pair shares h, eta and mass (all cavity decks
-//     and the synthetic lattice) they are kernel-argument constants; otherwise rows of a small
-//     shared-memory table (conflict-free broadcast) instead of divergent constant-bank reads.
+// Two traversals share ONE arithmetic body (PairAcc::visit), so they differ only in summation order:
+//
+//  * pair_tile_kernel (tile form, default): one CTA per tile of the cell grid (4x4x4 cells, ~145 atoms).  The
+//    records of every candidate of the tile (the atoms of the <= 8x8x8 cells within stencil reach, ~1160) are
+//    staged ONCE in shared memory with cp.async (80 B per candidate as five 16-byte granule arrays, bank =
+//    slot mod 8), the Verlet list holds 16-bit slot numbers, and EIGHT lanes share one atom: at every step they
+//    take eight consecutive entries of its sorted list -- mostly consecutive slots, i.e. conflict-free LDS.128 --
+//    and their partial sums are combined once per atom by a halving butterfly.  No L2 round trip remains inside
+//    the neighbour loop (the gather form's limiter: 16 % L1 misses put a ~600-cycle L2 latency on nearly every
+//    warp-visit), and the list costs 2 B instead of 4 B per neighbour.
+//
+//  * pair_kernel (gather form): one thread per owned atom, 192-thread CTAs, 96-byte records gathered through L1
+//    with a hand software pipeline (records of neighbour k+1 in flight while k is evaluated, list entries through a
+//    cp.async ring).  Used when a tile's candidates do not fit (dense cells, > 4095 candidates, exotic stencils),
+//    with SPHBVF_PAIR=gather, and as the cross-check of the tile form in the tests.
+//
+// Common to both: every per-particle division lives in the pack kernel (V = m/rho, P/rho^2, u = rho (vest - v)),
+// sqrt is a branch-free Goldschmidt iteration on MUFU.RSQ64H (7 FP64 ops, < 1 ulp), per-type-pair coefficients are
+// kernel-argument constants when every type pair shares them (all cavity decks and the synthetic lattice) and
+// rows of a small shared-memory table otherwise.
+#include <stdlib.h>
 #include <string.h>
 
 #include "sphbvf_internal.cuh"
+#include "tile_common.cuh"
 
 namespace sphbvf {
 
-// ---- compile-time tuning switches.  The defaults are what ships; every other setting is a measured and rejected
-// experiment kept buildable so that it can be re-measured (tools/build_variant.sh; pair kernel ms
-// at 8 M atoms on one B200, default 5.71):
-//   PAIR_PIPE      records in flight per warp in the register pipeline: 0 = none (one buffer, 128 registers, 16 warps
-//                  per SM: 7.01), 1 = default (two buffers, 160 registers, 12 warps), 2 = two (four buffers, 204
-//                  registers, 8 warps: 6.34)
-//   PAIR_TMA = D   records through the bulk-copy engine into a shared-memory ring D deep (16.3 with D = 4)
-//   PAIR_L2HINT    evict-first on the list / output streams (1) and evict-last on the record gathers (2): 5.84 / 5.90
-//   PAIR_PFL2 = D  prefetch.global.L2 of the records 2 D entries ahead: 7.33 with D = 2
-//   PAIR_DIAG_SMEM ballast dynamic shared memory (occupancy probe: 7.70 at 2 CTAs, 13.4 at 1 CTA per SM)
-//   PAIR_MINB / PAIR_T  resident CTAs per SM the kernel is compiled for / threads per CTA (MINB x T x registers <= 64 K,
-//                  split over four register files: only 8 / 12 / 16 warps at <= 255 / 168 / 128 registers exist)
-#ifndef PAIR_PIPE
-#define PAIR_PIPE 1
-#endif
-#ifndef PAIR_TMA
-#define PAIR_TMA 0
-#endif
+// ---- compile-time tuning switches (tools/build_variant.sh; DESIGN.md section 3 has the measurements)
+//   PAIR_T / PAIR_MINB   gather form: threads per CTA / resident CTAs per SM it is compiled for
+//   PT_T / PT_MINB       tile form: threads per CTA (multiple of 32) / resident CTAs per SM
 #ifndef PAIR_T
-#define PAIR_T (PAIR_PIPE == 1 ? 192 : 128)   // 12 warps as 2 x 192 threads: 5.63 (3 x 128: 5.71, 6 x 64: 5.73, 1 x 384: 5.66)
+#define PAIR_T 192   // 12 warps as 2 x 192 threads: 5.63 ms (3 x 128: 5.71, 6 x 64: 5.73, 1 x 384: 5.66)
 #endif
 #ifndef PAIR_MINB
-#define PAIR_MINB (PAIR_PIPE == 2 ? 2 : (PAIR_PIPE == 0 ? 4 : (PAIR_T == 192 ? 2 : 3)))
+#define PAIR_MINB 2
+#endif
+#ifndef PT_T
+#define PT_T 256
+#endif
+#ifndef PT_MINB
+#define PT_MINB 2
 #endif
 
 // one row per (type_i, type_j); 8 doubles = 64 B so a row is two LDS.128 x2
@@ -61,13 +62,19 @@ struct __align__(16) PairRow {
   double mimj, eta, iwdelta, h2eps;  // m_i m_j, eta, 1/W(delta), 0.01 h^2
 };
 
+// per type: what the body needs about atom j's type beyond the pair row
+struct __align__(16) TypeRow {
+  double imass, mass, rho0, kp;    // 1/m, m, rho0, c0^2/m^2 (prr_from_v)
+  double c0, G0, pad0, pad1;
+};
+
 struct PairTables {
   PairRow row[MAXT * MAXT];
+  TypeRow type[MAXT];
   double cwfdc[MAXT][MAXT];  // same as cwfd with h = cutc
   double hc2eps[MAXT][MAXT]; // 0.01 cutc^2
   double mred2[MAXT][MAXT];  // 2 mi mj / (mi + mj)
   double geff[MAXT][MAXT];   // 2 Gi Gj / (Gi + Gj + 1e-12)
-  double imass[MAXT];
 };
 
 static bool make_tables(const Coeffs &co, PairTables &t) {
@@ -75,7 +82,14 @@ static bool make_tables(const Coeffs &co, PairTables &t) {
   memset(&t, 0, sizeof t);
   bool uniform = true;
   for (int i = 1; i <= co.ntypes; i++) {
-    t.imass[i] = 1.0 / co.mass[i];
+    t.type[i].imass = 1.0 / co.mass[i];
+    t.type[i].mass = co.mass[i];
+    t.type[i].rho0 = co.rho0[i];
+    t.type[i].kp = co.kp[i];
+    t.type[i].c0 = co.c0[i];
+    t.type[i].G0 = co.G0[i];
+    // the constant-coefficient path also takes the per-type constants of atom j from type 1
+    if (co.mass[i] != co.mass[1] || co.rho0[i] != co.rho0[1] || co.c0[i] != co.c0[1]) uniform = false;
     for (int j = 1; j <= co.ntypes; j++) {
       auto coef = [&](double h, double &cwfd, double &cwf) {
         double ih = 1.0 / h, ihsq = ih * ih;
@@ -134,74 +148,6 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(y, e, y);
 }
 
-constexpr int RING = 16;  // list-entry prefetch depth (rows); power of two
-constexpr int TMA_RSTRIDE = 112;   // bytes per staged record: 96 + 16 pad, so that the 16-byte LDS of 8 lanes hit 32 banks
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *b, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-  } while (!ok);
-}
-// one bulk copy per calling lane: `bytes` (multiple of 16) from global to this CTA's shared memory, completion on `b`
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *b) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
-}
-
-// L2 residency (tuning switches):
-//   PAIR_L2HINT >= 1: the streams that are touched once per launch (list entries in, per-atom outputs out) are
-//                     marked evict-first so they do not push the gathered records out of L2;
-//   PAIR_L2HINT >= 2: the record gathers are marked evict-last on top of that;
-//   PAIR_PFL2 = D > 0: the records of the entries 2*D ahead of the register pipeline are prefetched into L2.
-#ifndef PAIR_L2HINT
-#define PAIR_L2HINT 0
-#endif
-#ifndef PAIR_PFL2
-#define PAIR_PFL2 0
-#endif
-
-__device__ __forceinline__ void cp_async4(int *smem_dst, const int *gsrc, unsigned long long pol) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-#if PAIR_L2HINT >= 1
-  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(sa), "l"(gsrc), "l"(pol) : "memory");
-#else
-  (void)pol;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
-#endif
-}
-
-__device__ __forceinline__ Rec4 ld_rec(const Rec4 *p) {
-#if PAIR_L2HINT >= 2
-  Rec4 r;
-  asm("ld.global.L2::evict_last.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-  return r;
-#else
-  return *p;
-#endif
-}
-
-__device__ __forceinline__ void st_out(double *p, double v) {
-#if PAIR_L2HINT >= 1
-  __stcs(p, v);
-#else
-  *p = v;
-#endif
-}
-
-__device__ __forceinline__ void prefetch_rec_l2(const Prec *p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-  asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)p + 64));
-}
-
 // ---- counter-based randomness for the stochastic stress term: Philox-4x32-10 (Salmon et al. 2011)
 __device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
 #pragma unroll
@@ -225,94 +171,91 @@ __device__ __forceinline__ void gauss2(unsigned a, unsigned b, double &g0, doubl
   g1 = rad * sn;
 }
 
-// SOLIDS: 0 = no atom has solid_tag, 1 = solids whose deviatoric stress is identically zero
-// (rigid walls: G0 == 0, dev == 0), 2 = elastic solids (deviatoric tensors gathered)
-// VIRIAL = true turns the kernel into the ghost part of Pair::virial_fdotr_compute (pair.cpp:1511): no
-// per-atom output is written; for every neighbour that is a periodic image (shift s != 0) the force
-// F it exerts on atom i is obtained as the change of the force accumulator and -1/2 s (x) F is summed
-// into virial_out[6] (see sphbvf_virial in capi.cu for the derivation).
-template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL = false>
-__global__ void __launch_bounds__(PAIR_T, PAIR_MINB)
-pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
-            const double damp, const double rand_pref, const unsigned long long seed, const long ntimestep,
-            double *virial_out = nullptr) {
-  __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
-  __shared__ int ring[RING][PAIR_T];
-  if (!UNIFORM) {
-    for (int q = threadIdx.x; q < MAXT * MAXT; q += blockDim.x) srow[q] = tb.row[q];
-    __syncthreads();
+// kernel-wide scalars of one pair pass
+struct PairConsts {
+  double damp, rand_pref;
+  unsigned long long seed;
+  long ntimestep;
+};
+
+// ------------------------------------------------------------------------------------------
+// The arithmetic of one atom i and of one neighbour visit, shared by both traversals.
+//   SOLIDS: 0 = no atom has solid_tag, 1 = solids whose deviatoric stress is identically zero
+//   (rigid walls: G0 == 0, dev == 0), 2 = elastic solids (deviatoric tensors gathered)
+// A neighbour is handed over as the fields of its record; `j` (its global index) is only used by the
+// instantiations that gather extras (species, deviatoric tensors, stochastic term).
+// ------------------------------------------------------------------------------------------
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM>
+struct PairAcc {
+  // atom i
+  double xi, yi, zi, Vi, vxi, vyi, vzi, uxi, uyi, uzi, rhoi, Prri;
+  double Vi2, c0i, Pi, irhoi, G0i, ei, arti;
+  int ti, tagi;
+  bool si;
+  double devi[9], Ri[9], Cspec_i[MAXS];
+  const PairRow *myrow;
+  // sums
+  double fx, fy, fz, drho, nd, rA1, rA2, phi, ddvx, ddvy, ddvz, nwx, nwy, nwz, ddxx, ddxy, ddxz, spi;
+  double ddev[9], Qs[MAXS];
+
+  __host__ __device__ static constexpr double c_art() { return VARIANT == SPHBVF_FSI ? 0.1 : 0.35; }
+
+  __device__ __forceinline__ void init(const DevState &d, const Coeffs &co, const PairTables &tb, const PairRow *srow,
+                                       const int i, const int fl, const Rec4 &A, const Rec4 &B, const Rec4 &C) {
+    ti = fl & 7;
+    si = SOLIDS && ((fl >> 4) & 1);
+    xi = A.x; yi = A.y; zi = A.z; Vi = A.w;
+    vxi = B.x; vyi = B.y; vzi = B.z; uxi = B.w;
+    uyi = C.x; uzi = C.y; rhoi = C.z; Prri = C.w;
+    Vi2 = Vi * Vi;
+    c0i = co.c0[ti];
+    Pi = Prri * rhoi * rhoi;
+    irhoi = Vi * tb.type[ti].imass;
+    myrow = srow + (UNIFORM ? 0 : ti * MAXT);
+    arti = 0.0;
+    // stress-free solid (dev == 0): R = -c_art max(0, -Psigma)/rho^2 = c_art P/rho^2 where P < 0 (TV, fsi);
+    // mechanics uses |P| (:471,487) so the bracket is never positive
+    if (SOLIDS == 1) arti = (si && VARIANT != SPHBVF_MECHANICS && Prri < 0.0) ? c_art() * Prri : 0.0;
+    if (SOLIDS == 2) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) devi[k] = si ? d.pdev[9 * (size_t)i + k] : 0.0;
+      const double Ps = VARIANT == SPHBVF_MECHANICS ? fabs(Pi) : Pi;
+#pragma unroll
+      for (int m = 0; m < 3; m++)
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+          double ts = devi[3 * m + n] - (m == n ? Ps : 0.0);
+          Ri[3 * m + n] = (si && ts > 0.0) ? -c_art() * ts * irhoi * irhoi : 0.0;
+        }
+    }
+    if (SPECIES)
+      for (int k = 0; k < co.nspecies; k++) Cspec_i[k] = d.pCs[(size_t)i * co.nspecies + k];
+    ei = RANDOM ? d.pD[i].w : 0.0;
+    tagi = RANDOM ? d.ptag[i] : 0;
+    G0i = co.G0[ti];
+    if (VARIANT == SPHBVF_FSI && SPECIES) G0i = co.G0[ti] * (1.0 - 0.99 * Cspec_i[0]);
+    fx = fy = fz = drho = nd = rA1 = rA2 = phi = 0.0;
+    ddvx = ddvy = ddvz = nwx = nwy = nwz = 0.0;
+    ddxx = ddxy = ddxz = 0.0;
+    spi = 0.0;   // sum_j s_ij q_i: the i-side transport term is vest_i times this
+    if (SOLIDS == 2)
+#pragma unroll
+      for (int k = 0; k < 9; k++) ddev[k] = 0.0;
+    if (SPECIES)
+#pragma unroll
+      for (int k = 0; k < MAXS; k++) Qs[k] = 0.0;
   }
-#if PAIR_TMA
-  extern __shared__ __align__(128) unsigned char pair_dyn[];
-  unsigned long long *mbar_all = reinterpret_cast<unsigned long long *>(pair_dyn + (size_t)PAIR_TMA * PAIR_T * TMA_RSTRIDE);
-  if (threadIdx.x < (PAIR_T / 32) * PAIR_TMA) mbar_init(mbar_all + threadIdx.x, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-  // every lane stays alive (warp-wide mbarrier protocol): lanes past the last atom shadow atom 0 with an empty list
-  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = gi < d.nlocal;
-  const int i = live ? gi : 0;
-#else
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.nlocal) return;
-#endif
 
-  const int fl = d.pflags[i];
-  const int ti = fl & 7;
-  const bool si = SOLIDS && ((fl >> 4) & 1);
-  const Rec4 Ai = d.prec[i].A, Bi = d.prec[i].B, Ci = d.prec[i].C;
-  const double rhoi = Ai.w, Vi = Bi.w, Vi2 = Vi * Vi, Prri = Ci.w;
-  const double c0i = co.c0[ti];
-  const double Pi = Prri * rhoi * rhoi;
-  const double irhoi = Vi * tb.imass[ti];
-  const PairRow *myrow = srow + (UNIFORM ? 0 : ti * MAXT);
-
-  double devi[9];
-  double arti = 0.0;        // scalar artificial stress when dev == 0
-  double Ri[9];             // artificial stress tensor when dev != 0
-  const double c_art = VARIANT == SPHBVF_FSI ? 0.1 : 0.35;
-  // stress-free solid (dev == 0): R = -c_art max(0, -Psigma)/rho^2 = c_art P/rho^2 where P < 0 (TV, fsi);
-  // mechanics uses |P| (:471,487) so the bracket is never positive
-  if (SOLIDS == 1) arti = (si && VARIANT != SPHBVF_MECHANICS && Prri < 0.0) ? c_art * Prri : 0.0;
-  if (SOLIDS == 2) {
-#pragma unroll
-    for (int k = 0; k < 9; k++) devi[k] = si ? d.pdev[9 * (size_t)i + k] : 0.0;
-    const double Ps = VARIANT == SPHBVF_MECHANICS ? fabs(Pi) : Pi;
-#pragma unroll
-    for (int m = 0; m < 3; m++)
-#pragma unroll
-      for (int n = 0; n < 3; n++) {
-        double ts = devi[3 * m + n] - (m == n ? Ps : 0.0);
-        Ri[3 * m + n] = (si && ts > 0.0) ? -c_art * ts * irhoi * irhoi : 0.0;
-      }
-  }
-  double Cspec_i[MAXS];
-  if (SPECIES)
-    for (int k = 0; k < co.nspecies; k++) Cspec_i[k] = d.pCs[(size_t)i * co.nspecies + k];
-  const double ei = RANDOM ? d.pD[i].w : 0.0;
-  const int tagi = RANDOM ? d.ptag[i] : 0;
-  double G0i = co.G0[ti];
-  if (VARIANT == SPHBVF_FSI && SPECIES) G0i = co.G0[ti] * (1.0 - 0.99 * Cspec_i[0]);
-
-  double fx = 0, fy = 0, fz = 0, drho = 0, nd = 0, rA1 = 0, rA2 = 0, phi = 0;
-  double ddvx = 0, ddvy = 0, ddvz = 0, nwx = 0, nwy = 0, nwz = 0;
-  double ddxx = 0, ddxy = 0, ddxz = 0;
-  double spi = 0;           // sum_j s_ij rho_i a_i: the i-side transport term is vest_i times this
-  double ddev[9];
-  double Qs[MAXS];
-  if (SOLIDS == 2)
-#pragma unroll
-    for (int k = 0; k < 9; k++) ddev[k] = 0.0;
-  if (SPECIES)
-#pragma unroll
-    for (int k = 0; k < MAXS; k++) Qs[k] = 0.0;
-
-  // ------------------------------------------------------------------ one neighbour
-  auto body = [&](const int ent, const Rec4 &Aj, const Rec4 &Bj, const Rec4 &Cj, const double rhoIj) {
-    const int j = ent & NEIGH_JMASK;
-    const int tj = (ent >> NEIGH_JBITS) & 7;
-    const bool sj = SOLIDS && ((ent >> 30) & 1);
-    const double delx = Ai.x - Aj.x, dely = Ai.y - Aj.y, delz = Ai.z - Aj.z;
+  // HAVE_RP: rhoj and Prrj come with the record; otherwise (80-byte staged records) P/rho^2 is recomputed from V
+  // with the pack kernel's own operations (same bits) and rho_j, needed by the solid-i viscosity only, is m_j / V_j
+  template <bool HAVE_RP>
+  __device__ __forceinline__ void visit(const DevState &d, const Coeffs &co, const PairTables &tb, const PairConsts &pc,
+                                        const int tj, const bool sj_in, const int j, const double xj, const double yj,
+                                        const double zj, const double Vj, const double vxj, const double vyj,
+                                        const double vzj, const double uxj, const double uyj, const double uzj,
+                                        double rhoj, double Prrj, const double rhoIj) {
+    const bool sj = SOLIDS && sj_in;
+    const double delx = xi - xj, dely = yi - yj, delz = zi - zj;
     const double rsq = delx * delx + dely * dely + delz * delz;
     double cutsq, h, cwfd, cwf, mm, eta;
     if (UNIFORM) {
@@ -325,17 +268,21 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     if (!(rsq < cutsq)) return;
     const double iwdelta = UNIFORM ? tb.row[MAXT + 1].iwdelta : myrow[tj].iwdelta;
     const double h2eps = UNIFORM ? tb.row[MAXT + 1].h2eps : myrow[tj].h2eps;
+    const TypeRow &tyj = tb.type[UNIFORM ? 1 : tj];
+    if (!HAVE_RP) Prrj = prr_from_v(tyj.kp, tyj.rho0, tyj.mass, Vj);
 
     const double r = fast_sqrt(rsq);
     const double t = h - r, t2 = t * t;
     const double wfd = cwfd * t2;
     const double wf = cwf * t2 * t * (h + 3. * r);
-    const double rhoj = Aj.w, Vj = Bj.w, Vj2 = Vj * Vj, Prrj = Cj.w;
-    const double velx = Bi.x - Bj.x, vely = Bi.y - Bj.y, velz = Bi.z - Bj.z;
+    const double Vj2 = Vj * Vj;
+    const double velx = vxi - vxj, vely = vyi - vyj, velz = vzi - vzj;
     const double dvr = delx * velx + dely * vely + delz * velz;
-    const double ai = Ci.x * delx + Ci.y * dely + Ci.z * delz;   // (v_i - vt_i) . del
-    const double aj = Cj.x * delx + Cj.y * dely + Cj.z * delz;
-    const double qi = rhoi * ai, qj = rhoj * aj;
+    // q = rho (v - vt) . del, straight from the stored u = rho (vest - v); a = (v - vt) . del = q / rho = q V / m
+    const double qi = uxi * delx + uyi * dely + uzi * delz;
+    const double qj = uxj * delx + uyj * dely + uzj * delz;
+    const double irhoj = Vj * tyj.imass;
+    const double aj = qj * irhoj;
     const double S2 = Vi2 + Vj2;
     const double S2w = S2 * wfd;
 
@@ -361,7 +308,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     if (SOLIDS == 1) {
       if (si || sj) {
         const double q = wf * iwdelta, q2 = q * q;
-        const double artj = (sj && VARIANT != SPHBVF_MECHANICS && Prrj < 0.0) ? c_art * Prrj : 0.0;
+        const double artj = (sj && VARIANT != SPHBVF_MECHANICS && Prrj < 0.0) ? c_art() * Prrj : 0.0;
         const double cc = mmw * q2 * q2 * (arti + artj);
         fartx = cc * delx; farty = cc * dely; fartz = cc * delz;
       }
@@ -369,7 +316,6 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
 
     double devj[9];
     if (SOLIDS == 2) {
-      const double irhoj = Vj * tb.imass[tj];
       if (si || sj) {
 #pragma unroll
         for (int k = 0; k < 9; k++) devj[k] = sj ? d.pdev[9 * (size_t)j + k] : 0.0;
@@ -383,7 +329,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
 #pragma unroll
           for (int n = 0; n < 3; n++) {
             double ts = devj[3 * m + n] - (m == n ? Psj : 0.0);
-            double Rj = (sj && ts > 0.0) ? -c_art * ts * irhoj * irhoj : 0.0;
+            double Rj = (sj && ts > 0.0) ? -c_art() * ts * irhoj * irhoj : 0.0;
             R[3 * m + n] = Ri[3 * m + n] + Rj;
           }
         fartx = pre * (delx * R[0] + dely * R[3] + delz * R[6]);
@@ -392,10 +338,10 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
       }
       // ---- Jaumann rate for solid i (:435-451)
       if (si) {
-        double G0j = co.G0[tj];
+        double G0j = tyj.G0;
         double geff;
         if (VARIANT == SPHBVF_FSI && SPECIES) {
-          G0j = co.G0[tj] * (1.0 - 0.99 * d.pCs[(size_t)j * co.nspecies]);
+          G0j = tyj.G0 * (1.0 - 0.99 * d.pCs[(size_t)j * co.nspecies]);
           geff = (2.0 * G0i * G0j) / (G0i + G0j + 1e-12);
         } else geff = tb.geff[ti][tj];
         const double hw = -0.5 * Vj * wfd;   // 0.5 * Vj * wfd * (v_j - v_i) = hw * vel
@@ -424,14 +370,14 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     // ---- momentum (:497-529)
     if (!si) {
       // chained FMAs into the accumulators (4 per component instead of 7 separately rounded ops);
-      // the i-side transport term s rho_i a_i vest_i has a per-atom constant vector: summed as a scalar
+      // the i-side transport term s q_i vest_i has a per-atom constant vector: summed as a scalar
       const double fvisc = S2w * eta;
       const double s = -0.5 * S2w;
       const double pj_ = s * qj;
       spi = fma(s, qi, spi);
       fx = fma(fvisc, velx, fx); fy = fma(fvisc, vely, fy); fz = fma(fvisc, velz, fz);
       fx = fma(-fpair, delx, fx); fy = fma(-fpair, dely, fy); fz = fma(-fpair, delz, fz);
-      fx = fma(pj_, Bj.x, fx); fy = fma(pj_, Bj.y, fy); fz = fma(pj_, Bj.z, fz);
+      fx = fma(pj_, vxj, fx); fy = fma(pj_, vyj, fy); fz = fma(pj_, vzj, fz);
       if (SOLIDS) { fx += fartx; fy += farty; fz += fartz; }
       if (RANDOM) {
         // f_rand = sqrt(-4 kB e m_i m_j wfd / (rho_i rho_j dt)) / (r + 0.01 h) * (Wn . del)   (:403-431), with
@@ -440,10 +386,11 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
         // computes the same one with del -> -del: equal and opposite forces.
         const double eij = 0.5 * (ei + d.pD[j].w);
         const int tagj = d.ptag[j];
-        const double pref = sqrt(fmax(-rand_pref * eij * (Vi * Vj) * wfd, 0.0)) * fast_rcp(r + 0.01 * h);
-        const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+        const double pref = sqrt(fmax(-pc.rand_pref * eij * (Vi * Vj) * wfd, 0.0)) * fast_rcp(r + 0.01 * h);
+        const uint2 key = make_uint2((unsigned)pc.seed, (unsigned)(pc.seed >> 32));
         const unsigned tlo = (unsigned)min(tagi, tagj), thi = (unsigned)max(tagi, tagj);
-        const uint4 r0 = philox4x32(make_uint4(tlo, thi, (unsigned)ntimestep, (unsigned)(ntimestep >> 32) << 1), key);
+        const long ns = pc.ntimestep;
+        const uint4 r0 = philox4x32(make_uint4(tlo, thi, (unsigned)ns, (unsigned)(ns >> 32) << 1), key);
         double g0, g1, g2, g3;
         gauss2(r0.x, r0.y, g0, g1);
         gauss2(r0.z, r0.w, g2, g3);
@@ -453,7 +400,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
           wxx = 0.5 * (g0 - g1); wyy = -wxx; wzz = 0.0;
           wxy = 0.5 * (g2 + g3);
         } else {
-          const uint4 r1 = philox4x32(make_uint4(tlo, thi, (unsigned)ntimestep, ((unsigned)(ntimestep >> 32) << 1) | 1u), key);
+          const uint4 r1 = philox4x32(make_uint4(tlo, thi, (unsigned)ns, ((unsigned)(ns >> 32) << 1) | 1u), key);
           double g4, g5, g6, g7;
           gauss2(r1.x, r1.y, g4, g5);
           gauss2(r1.z, r1.w, g6, g7);
@@ -470,15 +417,15 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     } else {
       double fviscs = 0.;
       if (dvr < 0.) {
+        if (!HAVE_RP) rhoj = tyj.mass * fast_rcp(Vj);
         const double mu = h * dvr * fast_rcp(rsq + h2eps);
-        fviscs = mmw * (-(c0i + co.c0[tj]) * mu + 2.0 * mu * mu) * fast_rcp(rhoi + rhoj);
+        fviscs = mmw * (-(c0i + tyj.c0) * mu + 2.0 * mu * mu) * fast_rcp(rhoi + rhoj);
       }
       const double cc = -(fpair + fviscs);
       fx += cc * delx + fartx;
       fy += cc * dely + farty;
       fz += cc * delz + fartz;
       if (SOLIDS == 2) {
-        const double irhoj = Vj * tb.imass[tj];
         const double ii = irhoi * irhoi, jj = irhoj * irhoj;
         fx += mmw * (delx * (devi[0] * ii + devj[0] * jj) + dely * (devi[3] * ii + devj[3] * jj) + delz * (devi[6] * ii + devj[6] * jj));
         fy += mmw * (delx * (devi[1] * ii + devj[1] * jj) + dely * (devi[4] * ii + devj[4] * jj) + delz * (devi[7] * ii + devj[7] * jj));
@@ -486,12 +433,12 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
       }
     }
 
-    // ---- density rate (:548-555); (vt_i - vt_j).del = dvr - ai + aj
+    // ---- density rate (:548-555); (vt_i - vt_j).del = dvr - a_i + a_j
     {
       // rho_i (dvr - a_i + a_j) - (rho_i a_i + rho_j a_j) = rho_i (dvr + a_j) - 2 q_i - q_j
       double inner = fma(-2.0, qi, fma(rhoi, dvr + aj, -qj));
       if (VARIANT == SPHBVF_FSI)
-        inner -= damp * 2.0 * h * c0i * (rhoj - rhoi) * (rsq * fast_rcp(rsq + h2eps));
+        inner -= pc.damp * 2.0 * h * c0i * (rhoj - rhoi) * (rsq * fast_rcp(rsq + h2eps));
       drho = fma(wfd * Vj, inner, drho);
     }
 
@@ -508,7 +455,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
       if (r < hc) {
         const double tc = hc - r;
         const double wfdc = tb.cwfdc[ti][tj] * tc * tc;
-        const double irhoj = Vj * tb.imass[tj];
+        const double ai = qi * irhoi;
         const double q0 = tb.mred2[ti][tj] * (irhoi + irhoj) * rsq * wfdc / (rsq + tb.hc2eps[ti][tj]);
         for (int k = 0; k < co.nspecies; k++) {
           const double Cjk = d.pCs[(size_t)j * co.nspecies + k];
@@ -518,18 +465,66 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
         }
       }
     }
-  };
+  }
+
+  // force on atom i so far (the i-side transport term folded in): used by the virial pass
+  __device__ __forceinline__ void force_now(double &Fx, double &Fy, double &Fz) const {
+    Fx = fx + spi * vxi; Fy = fy + spi * vyi; Fz = fz + spi * vzi;
+  }
+};
+
+// does this instantiation read per-neighbour data that is not in the record (through the neighbour's global index)?
+template <bool SPECIES, int SOLIDS, bool FILTER, bool RANDOM, bool VIRIAL>
+struct NeedsJ { static constexpr bool value = SPECIES || SOLIDS == 2 || FILTER || RANDOM || VIRIAL; };
+
+// ==========================================================================================
+// gather form
+// ==========================================================================================
+constexpr int RING = 16;  // list-entry prefetch depth (rows); power of two
+
+__device__ __forceinline__ void cp_async4(int *smem_dst, const int *gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+
+// VIRIAL = true turns a pair kernel into the ghost part of Pair::virial_fdotr_compute (pair.cpp:1511): no
+// per-atom output is written; for every neighbour that is a periodic image (shift s != 0) the force
+// F it exerts on atom i is obtained as the change of the force accumulator and -1/2 s (x) F is summed
+// into virial_out[6] (see sphbvf_virial in capi.cu for the derivation).
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL = false>
+__global__ void __launch_bounds__(PAIR_T, PAIR_MINB)
+pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
+            const PairConsts pc, double *virial_out = nullptr) {
+  __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
+  __shared__ int ring[RING][PAIR_T];
+  if (!UNIFORM) {
+    for (int q = threadIdx.x; q < MAXT * MAXT; q += blockDim.x) srow[q] = tb.row[q];
+    __syncthreads();
+  }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.nlocal) return;
+
+  PairAcc<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM> acc;
+  acc.init(d, co, tb, srow, i, d.pflags[i], d.prec[i].A, d.prec[i].B, d.prec[i].C);
 
   double vir[6] = {0, 0, 0, 0, 0, 0};
   auto visit = [&](const int ent, const Rec4 &Aj, const Rec4 &Bj, const Rec4 &Cj, const double rhoIj) {
-    if (!VIRIAL) { body(ent, Aj, Bj, Cj, rhoIj); return; }
-    const int g = (ent & NEIGH_JMASK) - d.nlocal;
+    const int j = ent & NEIGH_JMASK;
+    const int tj = (ent >> NEIGH_JBITS) & 7;
+    const bool sj = (ent >> 30) & 1;
+    if (!VIRIAL) {
+      acc.template visit<true>(d, co, tb, pc, tj, sj, j, Aj.x, Aj.y, Aj.z, Aj.w, Bj.x, Bj.y, Bj.z, Bj.w, Cj.x, Cj.y, Cj.z, Cj.w, rhoIj);
+      return;
+    }
+    const int g = j - d.nlocal;
     if (g < 0) return;
     const double sx = d.gshift[3 * (size_t)g], sy = d.gshift[3 * (size_t)g + 1], sz = d.gshift[3 * (size_t)g + 2];
     if (sx == 0.0 && sy == 0.0 && sz == 0.0) return;
-    const double f0x = fx + spi * Bi.x, f0y = fy + spi * Bi.y, f0z = fz + spi * Bi.z;
-    body(ent, Aj, Bj, Cj, rhoIj);
-    const double Fx = (fx + spi * Bi.x) - f0x, Fy = (fy + spi * Bi.y) - f0y, Fz = (fz + spi * Bi.z) - f0z;
+    double f0x, f0y, f0z, f1x, f1y, f1z;
+    acc.force_now(f0x, f0y, f0z);
+    acc.template visit<true>(d, co, tb, pc, tj, sj, j, Aj.x, Aj.y, Aj.z, Aj.w, Bj.x, Bj.y, Bj.z, Bj.w, Cj.x, Cj.y, Cj.z, Cj.w, rhoIj);
+    acc.force_now(f1x, f1y, f1z);
+    const double Fx = f1x - f0x, Fy = f1y - f0y, Fz = f1z - f0z;
     vir[0] -= 0.5 * sx * Fx; vir[1] -= 0.5 * sy * Fy; vir[2] -= 0.5 * sz * Fz;
     vir[3] -= 0.5 * sx * Fy; vir[4] -= 0.5 * sx * Fz; vir[5] -= 0.5 * sy * Fz;
   };
@@ -539,87 +534,22 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   // entries RING rows ahead into a shared-memory ring with cp.async (no registers, no barrier:
   // a thread only ever reads the slots it wrote).  The records of neighbour k+1 are requested
   // before neighbour k is evaluated.
-#if PAIR_TMA
-  const int nn = live ? d.numneigh[i] : 0;
-#else
   const int nn = d.numneigh[i];
-#endif
   const int *np = d.neigh + i;
   const size_t stride = d.stride;
   int *myring = &ring[0][threadIdx.x];
-  unsigned long long pol = 0;
-#if PAIR_L2HINT >= 1
-  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-#endif
-#if PAIR_TMA
-  // ------------------------------------------------------------------ TMA traversal
-  // Per lane, the 96-byte record of entry k + D is copied global -> shared memory by the bulk-copy engine while entry k
-  // is evaluated: D records in flight per thread without a single register, and the L1/LSU pipe only sees conflict-free
-  // LDS.128 reads (24 wavefronts per visit instead of 66 for three gathers).  One mbarrier per (warp, slot): lane 0
-  // posts the expected byte count of the warp's active lanes, each lane's copy completes its share, all lanes wait.
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int nnmax = nn;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) nnmax = max(nnmax, __shfl_xor_sync(0xffffffffu, nnmax, o));
-    unsigned char *myrec = pair_dyn + (size_t)threadIdx.x * TMA_RSTRIDE;
-    unsigned long long *mbar = mbar_all + warp * PAIR_TMA;
-    auto fetch1 = [&](int k) {
-      if (k < nn) cp_async4(myring + (k % RING) * PAIR_T, np + (size_t)k * stride, pol);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto issue = [&](int k) {   // warp-uniform call, k < nnmax, entry k has landed in the ring
-      const int slot = k % PAIR_TMA;
-      const bool act = k < nn;
-      const unsigned m = __ballot_sync(0xffffffffu, act);
-      if (lane == 0) mbar_expect_tx(mbar + slot, 96u * (unsigned)__popc(m));
-      __syncwarp();
-      if (act) {
-        const int e = myring[(k % RING) * PAIR_T];
-        bulk_g2s(myrec + (size_t)slot * PAIR_T * TMA_RSTRIDE, d.prec + (e & NEIGH_JMASK), 96u, mbar + slot);
-      }
-    };
-#pragma unroll
-    for (int k = 0; k < RING; k++) fetch1(k);
-    asm volatile("cp.async.wait_group %0;" ::"n"(RING - PAIR_TMA) : "memory");   // entries < D landed
-    __syncwarp();
-    for (int k = 0; k < PAIR_TMA && k < nnmax; k++) issue(k);
-    for (int k = 0; k < nnmax; k++) {
-      const bool act = k < nn;
-      const int e = act ? myring[(k % RING) * PAIR_T] : 0;
-      fetch1(k + RING);
-      asm volatile("cp.async.wait_group %0;" ::"n"(RING - PAIR_TMA) : "memory");   // entries <= k + D landed
-      mbar_wait(mbar + (k % PAIR_TMA), (unsigned)((k / PAIR_TMA) & 1));
-      if (act) {
-        const double2 *r = reinterpret_cast<const double2 *>(myrec + (size_t)(k % PAIR_TMA) * PAIR_T * TMA_RSTRIDE);
-        const double2 a0 = r[0], a1 = r[1], b0 = r[2], b1 = r[3], c0 = r[4], c1 = r[5];
-        const Rec4 Aj = make_rec4(a0.x, a0.y, a1.x, a1.y), Bj = make_rec4(b0.x, b0.y, b1.x, b1.y),
-                   Cj = make_rec4(c0.x, c0.y, c1.x, c1.y);
-        visit(e, Aj, Bj, Cj, FILTER ? d.pD[e & NEIGH_JMASK].x : 0.0);
-      }
-      __syncwarp();
-      if (k + PAIR_TMA < nnmax) issue(k + PAIR_TMA);
-    }
-  }
-#else
   auto fetch2 = [&](int k) {   // entries k, k+1 -> ring slots k % RING, (k+1) % RING; one group
-    if (k < nn) cp_async4(myring + (k % RING) * PAIR_T, np + (size_t)k * stride, pol);
-    if (k + 1 < nn) cp_async4(myring + ((k + 1) % RING) * PAIR_T, np + (size_t)(k + 1) * stride, pol);
+    if (k < nn) cp_async4(myring + (k % RING) * PAIR_T, np + (size_t)k * stride);
+    if (k + 1 < nn) cp_async4(myring + ((k + 1) % RING) * PAIR_T, np + (size_t)(k + 1) * stride);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   // groups allowed in flight after a wait: entries <= kk + 17 - 2 * PEND have landed
-  constexpr int PEND = RING / 2 - 2 - PAIR_PFL2;
-  static_assert(PEND >= 2, "prefetch distance too large for the ring");
+  constexpr int PEND = RING / 2 - 2;
 #pragma unroll
   for (int k = 0; k < RING; k += 2) fetch2(k);
-  asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries 0..3 (+ 2 PFL2) landed
+  asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries 0..3 landed
   int e0 = nn > 0 ? myring[0] : 0;
   int e1 = nn > 1 ? myring[PAIR_T] : 0;
-#if PAIR_PFL2 > 0
-#pragma unroll
-  for (int q = 2; q < 4 + 2 * PAIR_PFL2; q++)
-    if (q < nn) prefetch_rec_l2(d.prec + (myring[(q % RING) * PAIR_T] & NEIGH_JMASK));
-#endif
   // Register pipeline: while the record of one neighbour is evaluated, the record of the next one is in flight.
   // ptxas puts all six record loads of the loop on ONE scoreboard, and a scoreboard is a counter: the first use of a
   // record waits until EVERY load issued before it has returned.  Issued in source order (next record's loads, then
@@ -627,116 +557,36 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   // full memory latency exposed on every second visit (ncu source page: one DADD held 33 % of all stall samples).
   // The loads of record k+1 are therefore made DATA dependent on the first use of record k (`gate`: a NaN test the
   // compiler cannot fold), so they are issued right after record k has arrived and have a whole visit to complete.
-#if PAIR_PIPE == 0
-  // No register pipeline at all: one record buffer, the latency of every record is covered by other warps only
-  // (<= 128 registers -> four CTAs, 16 warps per SM).
-  for (int kk = 0; kk < nn; kk += 2) {
-    fetch2(kk + RING);
-    asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");
-    const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * PAIR_T] : 0;
-    const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * PAIR_T] : 0;
-    {
-      const Prec *p = d.prec + (e0 & NEIGH_JMASK);
-      const Rec4 A = ld_rec(&p->A), B = ld_rec(&p->B), C = ld_rec(&p->C);
-      visit(e0, A, B, C, FILTER ? d.pD[e0 & NEIGH_JMASK].x : 0.0);
-    }
-    if (kk + 1 < nn) {
-      const Prec *p = d.prec + (e1 & NEIGH_JMASK);
-      const Rec4 A = ld_rec(&p->A), B = ld_rec(&p->B), C = ld_rec(&p->C);
-      visit(e1, A, B, C, FILTER ? d.pD[e1 & NEIGH_JMASK].x : 0.0);
-    }
-    e0 = e2;
-    e1 = e3;
-  }
-
-#elif PAIR_PIPE == 2
-  // Two records in flight per warp: the records of the NEXT TWO neighbours are requested (one batch of six loads, gated
-  // on the first use of the current pair so that the single scoreboard wait of the loop covers exactly one batch) while
-  // the current two are evaluated.  Four record buffers: ~210 registers, two CTAs per SM -- 8 warps x 2 records = 16
-  // records in flight per SM instead of 12 x 1.
-  Rec4 A0, B0, C0, A1, B1, C1, A2, B2, C2, A3, B3, C3;
-  double D0 = 0.0, D1 = 0.0, D2 = 0.0, D3 = 0.0;
-  auto gate = [&](const Rec4 &A) { const double g = Ai.x - A.x; return g != g ? 1 : 0; };
-  {
-    const Prec *p = d.prec + (e0 & NEIGH_JMASK);
-    A0 = ld_rec(&p->A); B0 = ld_rec(&p->B); C0 = ld_rec(&p->C);
-    if (FILTER) D0 = d.pD[e0 & NEIGH_JMASK].x;
-    const Prec *q = d.prec + (e1 & NEIGH_JMASK);
-    A1 = ld_rec(&q->A); B1 = ld_rec(&q->B); C1 = ld_rec(&q->C);
-    if (FILTER) D1 = d.pD[e1 & NEIGH_JMASK].x;
-  }
-  for (int kk = 0; kk < nn; kk += 4) {
-    // ---- half 1: evaluate e0, e1 (records 0, 1); request records 2, 3 for e2, e3
-    fetch2(kk + RING);
-    asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries <= kk+5 landed
-    const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * PAIR_T] : 0;
-    const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * PAIR_T] : 0;
-    {
-      const int g = gate(A0);
-      const int j2 = (e2 & NEIGH_JMASK) + g, j3 = (e3 & NEIGH_JMASK) + g;
-      const Prec *p = d.prec + j2, *q = d.prec + j3;
-      A2 = ld_rec(&p->A); B2 = ld_rec(&p->B); C2 = ld_rec(&p->C);
-      A3 = ld_rec(&q->A); B3 = ld_rec(&q->B); C3 = ld_rec(&q->C);
-      if (FILTER) { D2 = d.pD[j2].x; D3 = d.pD[j3].x; }
-    }
-    visit(e0, A0, B0, C0, D0);
-    if (kk + 1 < nn) visit(e1, A1, B1, C1, D1);
-    if (kk + 2 >= nn) break;
-    // ---- half 2: evaluate e2, e3 (records 2, 3); request records 0, 1 for e4, e5
-    fetch2(kk + 2 + RING);
-    asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries <= kk+7 landed
-    e0 = kk + 4 < nn ? myring[((kk + 4) % RING) * PAIR_T] : 0;
-    e1 = kk + 5 < nn ? myring[((kk + 5) % RING) * PAIR_T] : 0;
-    {
-      const int g = gate(A2);
-      const int j0 = (e0 & NEIGH_JMASK) + g, j1 = (e1 & NEIGH_JMASK) + g;
-      const Prec *p = d.prec + j0, *q = d.prec + j1;
-      A0 = ld_rec(&p->A); B0 = ld_rec(&p->B); C0 = ld_rec(&p->C);
-      A1 = ld_rec(&q->A); B1 = ld_rec(&q->B); C1 = ld_rec(&q->C);
-      if (FILTER) { D0 = d.pD[j0].x; D1 = d.pD[j1].x; }
-    }
-    visit(e2, A2, B2, C2, D2);
-    if (kk + 3 < nn) visit(e3, A3, B3, C3, D3);
-  }
-
-#else
   Rec4 A0, B0, C0, A1, B1, C1;
   double D0 = 0.0, D1 = 0.0;   // rhoI_j of the Shepard numerator, part of the pipeline on filter steps
-  auto gate = [&](const Rec4 &A) { const double g = Ai.x - A.x; return g != g ? 1 : 0; };
+  auto gate = [&](const Rec4 &A) { const double g = acc.xi - A.x; return g != g ? 1 : 0; };
   {
     const Prec *p = d.prec + (e0 & NEIGH_JMASK);
-    A0 = ld_rec(&p->A); B0 = ld_rec(&p->B); C0 = ld_rec(&p->C);
+    A0 = p->A; B0 = p->B; C0 = p->C;
     if (FILTER) D0 = d.pD[e0 & NEIGH_JMASK].x;
   }
   for (int kk = 0; kk < nn; kk += 2) {
     {
       const int j1 = (e1 & NEIGH_JMASK) + gate(A0);
       const Prec *p = d.prec + j1;
-      A1 = ld_rec(&p->A); B1 = ld_rec(&p->B); C1 = ld_rec(&p->C);
+      A1 = p->A; B1 = p->B; C1 = p->C;
       if (FILTER) D1 = d.pD[j1].x;
     }
     fetch2(kk + RING);   // slots of entries kk, kk+1: already in e0, e1
-    asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries <= kk+5 (+ 2 PFL2) landed
+    asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries <= kk+5 landed
     const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * PAIR_T] : 0;
     const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * PAIR_T] : 0;
-#if PAIR_PFL2 > 0
-    if (kk + 4 + 2 * PAIR_PFL2 < nn) prefetch_rec_l2(d.prec + (myring[((kk + 4 + 2 * PAIR_PFL2) % RING) * PAIR_T] & NEIGH_JMASK));
-    if (kk + 5 + 2 * PAIR_PFL2 < nn) prefetch_rec_l2(d.prec + (myring[((kk + 5 + 2 * PAIR_PFL2) % RING) * PAIR_T] & NEIGH_JMASK));
-#endif
     visit(e0, A0, B0, C0, D0);
     {
       const int j2 = (e2 & NEIGH_JMASK) + gate(A1);
       const Prec *p = d.prec + j2;
-      A0 = ld_rec(&p->A); B0 = ld_rec(&p->B); C0 = ld_rec(&p->C);
+      A0 = p->A; B0 = p->B; C0 = p->C;
       if (FILTER) D0 = d.pD[j2].x;
     }
     if (kk + 1 < nn) visit(e1, A1, B1, C1, D1);
     e0 = e2;
     e1 = e3;
   }
-
-#endif
-#endif   // PAIR_TMA
 
   if (VIRIAL) {
     // only atoms next to a periodic face have anything to add: plain atomics
@@ -745,76 +595,306 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
       if (vir[q] != 0.0) atomicAdd(virial_out + q, vir[q]);
     return;
   }
-#if PAIR_TMA
-  if (!live) return;
-#endif
-  const double ddvc = 10.0 * 7.0 * co.B[ti];
+  const double ddvc = 10.0 * 7.0 * co.B[acc.ti];
   const size_t i3 = 3 * (size_t)i;
-  st_out(d.f + i3, fma(spi, Bi.x, fx)); st_out(d.f + i3 + 1, fma(spi, Bi.y, fy)); st_out(d.f + i3 + 2, fma(spi, Bi.z, fz));
-  st_out(d.drho + i, drho);
-  st_out(d.nd + i, nd);
-  st_out(d.rhoAux1 + i, rA1);
-  st_out(d.rhoAux2 + i, rA2);
-  st_out(d.phi + i, phi);
-  st_out(d.nw + i3, nwx); st_out(d.nw + i3 + 1, nwy); st_out(d.nw + i3 + 2, nwz);
-  st_out(d.ddv + i3, ddvc * ddvx); st_out(d.ddv + i3 + 1, ddvc * ddvy); st_out(d.ddv + i3 + 2, ddvc * ddvz);
+  d.f[i3] = fma(acc.spi, acc.vxi, acc.fx); d.f[i3 + 1] = fma(acc.spi, acc.vyi, acc.fy); d.f[i3 + 2] = fma(acc.spi, acc.vzi, acc.fz);
+  d.drho[i] = acc.drho;
+  d.nd[i] = acc.nd;
+  d.rhoAux1[i] = acc.rA1;
+  d.rhoAux2[i] = acc.rA2;
+  d.phi[i] = acc.phi;
+  d.nw[i3] = acc.nwx; d.nw[i3 + 1] = acc.nwy; d.nw[i3 + 2] = acc.nwz;
+  d.ddv[i3] = ddvc * acc.ddvx; d.ddv[i3 + 1] = ddvc * acc.ddvy; d.ddv[i3 + 2] = ddvc * acc.ddvz;
   if (VARIANT != SPHBVF_TV) {
-    d.ddx[i3] = ddxx; d.ddx[i3 + 1] = ddxy; d.ddx[i3 + 2] = ddxz;
-    d.Pnew[i] = Pi;   // pair_ssa_tsdpd_bvf_mechanics.cpp:188
+    d.ddx[i3] = acc.ddxx; d.ddx[i3 + 1] = acc.ddxy; d.ddx[i3 + 2] = acc.ddxz;
+    d.Pnew[i] = acc.Pi;   // pair_ssa_tsdpd_bvf_mechanics.cpp:188
   }
   if (SOLIDS == 2)
 #pragma unroll
-    for (int k = 0; k < 9; k++) d.ddev[9 * (size_t)i + k] = si ? ddev[k] : 0.0;
+    for (int k = 0; k < 9; k++) d.ddev[9 * (size_t)i + k] = acc.si ? acc.ddev[k] : 0.0;
   if (SPECIES)
-    for (int k = 0; k < co.nspecies; k++) d.Q[(size_t)i * co.nspecies + k] = Qs[k];
+    for (int k = 0; k < co.nspecies; k++) d.Q[(size_t)i * co.nspecies + k] = acc.Qs[k];
+}
+
+// ==========================================================================================
+// tile form
+// ==========================================================================================
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+
+// sum of x over the 8 lanes of an octet (xor butterfly): for the rarely used sums
+__device__ __forceinline__ double octet_sum(double x) {
+  x += __shfl_xor_sync(0xffffffffu, x, 4);
+  x += __shfl_xor_sync(0xffffffffu, x, 2);
+  x += __shfl_xor_sync(0xffffffffu, x, 1);
+  return x;
+}
+
+// Halving butterfly over the 8 lanes of an octet: every lane enters with its partial sums v[0..15] and leaves with
+// the octet totals of TWO of them in v[0], v[1]: lane l (0..7 within the octet) holds the totals of the
+// original indices 8 b2 + 4 b1 + 2 b0 and that + 1, with b2 b1 b0 the bits of l.  14 shuffle+add pairs instead of 48.
+__device__ __forceinline__ void octet_reduce16(double (&v)[16], const int lane) {
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const double send = up ? v[k] : v[k + 8], keep = up ? v[k + 8] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double send = up ? v[k] : v[k + 4], keep = up ? v[k + 4] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+  }
+  {
+    const bool up = lane & 1;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const double send = up ? v[k] : v[k + 2], keep = up ? v[k + 2] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+  }
+}
+
+// NG = 16-byte granules staged per candidate: 5 (80 B) in the hot instantiations, 6 when the body reads rho_j
+template <int VARIANT, int SOLIDS>
+struct TileGranules { static constexpr int value = (VARIANT == SPHBVF_FSI || SOLIDS == 2) ? 6 : PREC_GRANULES_HOT; };
+
+size_t pair_tile_smem(int cap, int granules, bool index_map) { return (size_t)cap * (granules * 16 + (index_map ? 4 : 0)); }
+
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL = false>
+__global__ void __launch_bounds__(PT_T, (SOLIDS == 2 || SPECIES || RANDOM) ? 1 : PT_MINB)   // the heavy instantiations get 255 registers
+pair_tile_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_constant__ Coeffs co,
+                 const __grid_constant__ PairTables tb, const int *__restrict__ cell_start,
+                 const int *__restrict__ gcell_start, const int *__restrict__ gorder, const PairConsts pc,
+                 double *virial_out = nullptr) {
+  constexpr int NG = TileGranules<VARIANT, SOLIDS>::value;
+  constexpr bool NEEDJ = NeedsJ<SPECIES, SOLIDS, FILTER, RANDOM, VIRIAL>::value;
+  extern __shared__ __align__(16) unsigned char pt_smem[];
+  __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
+  __shared__ int seg_src[TB_MAXSEG];
+  __shared__ int seg_off[TB_MAXSEG + 1];
+  __shared__ int next_group;
+
+  TileGeom t;
+  if (!tile_geometry(g, blockIdx.x, cell_start, t)) return;   // no owned atom in this tile (whole CTA)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cap = d.tile_cap;
+  double2 *rec = reinterpret_cast<double2 *>(pt_smem);        // rec[gr * cap + slot], cap a multiple of 8: bank group = slot mod 8
+  int *gidx = reinterpret_cast<int *>(pt_smem + (size_t)NG * 16 * cap);   // [cap] global index of a slot (NEEDJ only)
+  if (!UNIFORM)
+    for (int q = tid; q < MAXT * MAXT; q += PT_T) srow[q] = tb.row[q];
+  if (tid == 0) next_group = 0;
+  tile_segments(g, t, cell_start, gcell_start, d.nghost > 0, seg_src, seg_off);   // ends with a barrier
+
+  // ---- stage the candidates' records: one warp per segment (a contiguous index range, or ghosts through gorder),
+  // lanes over (atom, granule) so that consecutive lanes copy consecutive 16-byte pieces of global memory
+  for (int sid = warp; sid < t.nseg; sid += PT_T / 32) {
+    const int s0 = seg_off[sid], len = seg_off[sid + 1] - s0;
+    if (len <= 0) continue;
+    const int src = seg_src[sid];
+    for (int idx = lane; idx < len * NG; idx += 32) {
+      const int k = idx / NG, gr = idx - k * NG;
+      const int j = tile_source(src, k, d.nlocal, gorder);
+      cp_async16(&rec[(size_t)gr * cap + s0 + k], reinterpret_cast<const char *>(d.prec + j) + 16 * gr);
+      if (NEEDJ && gr == 0) gidx[s0 + k] = j;
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- octets: 8 lanes per atom, 4 atoms per warp at a time; groups of 4 atoms are handed out dynamically
+  const int sub = lane & 7, oct = lane >> 3;
+  const int natoms = t.last - t.first;
+  for (;;) {
+    int gbase = 0;
+    if (lane == 0) gbase = atomicAdd(&next_group, 4);
+    gbase = __shfl_sync(0xffffffffu, gbase, 0);
+    if (gbase >= natoms) break;
+    const bool valid = gbase + oct < natoms;
+    const int i = t.first + (valid ? gbase + oct : 0);
+    const int nn = valid ? d.numneigh[i] : 0;
+    int nnmax = nn;
+    nnmax = max(nnmax, __shfl_xor_sync(0xffffffffu, nnmax, 8));
+    nnmax = max(nnmax, __shfl_xor_sync(0xffffffffu, nnmax, 16));
+    const unsigned short *row = d.neigh16 + (size_t)i * d.pitch16 + sub;   // entry k of my lane at step s: k = 8 s + sub
+    // entries of the first block of 8 steps (64 entries of the row), requested with the atom's own record
+    unsigned e_cur[8], e_nxt[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) e_cur[q] = (8 * q + sub < nn) ? row[8 * q] : 0u;
+
+    PairAcc<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM> acc;
+    acc.init(d, co, tb, srow, i, d.pflags[i], d.prec[i].A, d.prec[i].B, d.prec[i].C);
+    double vir[6] = {0, 0, 0, 0, 0, 0};
+
+    for (int s0 = 0; 8 * s0 < nnmax; s0 += 8) {
+      // the entries of the NEXT block of 8 steps are requested before this block is evaluated
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int k = 8 * (s0 + 8 + q) + sub;
+        e_nxt[q] = k < nn ? row[8 * (s0 + 8 + q)] : 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int k = 8 * (s0 + q) + sub;
+        if (8 * (s0 + q) >= nnmax) break;   // warp-uniform
+        const unsigned e = e_cur[q];
+        const int slot = e & TILE_SLOT_MASK;
+        const double2 g0 = rec[slot], g1 = rec[cap + slot], g2 = rec[2 * cap + slot], g3 = rec[3 * cap + slot],
+                      g4 = rec[4 * cap + slot];
+        double rhoj = 0.0, Prrj = 0.0;
+        if (NG == 6) { const double2 g5 = rec[5 * cap + slot]; rhoj = g5.x; Prrj = g5.y; }
+        if (k < nn) {
+          const int tj = (e >> TILE_SLOT_BITS) & 7;
+          const bool sj = (e >> 15) & 1;
+          const int j = NEEDJ ? gidx[slot] : 0;
+          const double rhoIj = FILTER ? d.pD[j].x : 0.0;
+          if (!VIRIAL) {
+            acc.template visit<NG == 6>(d, co, tb, pc, tj, sj, j, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y, g4.x, g4.y,
+                                        rhoj, Prrj, rhoIj);
+          } else {
+            const int gh = j - d.nlocal;
+            if (gh >= 0) {
+              const double sx = d.gshift[3 * (size_t)gh], sy = d.gshift[3 * (size_t)gh + 1], sz = d.gshift[3 * (size_t)gh + 2];
+              if (sx != 0.0 || sy != 0.0 || sz != 0.0) {
+                double f0x, f0y, f0z, f1x, f1y, f1z;
+                acc.force_now(f0x, f0y, f0z);
+                acc.template visit<NG == 6>(d, co, tb, pc, tj, sj, j, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y, g4.x,
+                                            g4.y, rhoj, Prrj, rhoIj);
+                acc.force_now(f1x, f1y, f1z);
+                const double Fx = f1x - f0x, Fy = f1y - f0y, Fz = f1z - f0z;
+                vir[0] -= 0.5 * sx * Fx; vir[1] -= 0.5 * sy * Fy; vir[2] -= 0.5 * sz * Fz;
+                vir[3] -= 0.5 * sx * Fy; vir[4] -= 0.5 * sx * Fz; vir[5] -= 0.5 * sy * Fz;
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++) e_cur[q] = e_nxt[q];
+    }
+
+    if (VIRIAL) {
+#pragma unroll
+      for (int q = 0; q < 6; q++)
+        if (vir[q] != 0.0) atomicAdd(virial_out + q, vir[q]);
+      continue;
+    }
+
+    // ---- combine the 8 partial sums of every atom and write its outputs (each written once, no atomics)
+    const double ddvc = 10.0 * 7.0 * co.B[acc.ti];
+    double v[16] = {fma(acc.spi, acc.vxi, acc.fx), fma(acc.spi, acc.vyi, acc.fy), fma(acc.spi, acc.vzi, acc.fz), acc.drho,
+                    acc.nd, acc.rA1, acc.rA2, acc.phi,
+                    acc.nwx, acc.nwy, acc.nwz, 0.0,
+                    ddvc * acc.ddvx, ddvc * acc.ddvy, ddvc * acc.ddvz, 0.0};
+    octet_reduce16(v, lane);
+    if (valid) {
+      const size_t i3 = 3 * (size_t)i;
+      switch (sub) {   // lane b2 b1 b0 holds the totals of indices 8 b2 + 4 b1 + 2 b0 (+1)
+        case 0: d.f[i3] = v[0]; d.f[i3 + 1] = v[1]; break;
+        case 1: d.f[i3 + 2] = v[0]; d.drho[i] = v[1]; break;
+        case 2: d.nd[i] = v[0]; d.rhoAux1[i] = v[1]; break;
+        case 3: d.rhoAux2[i] = v[0]; d.phi[i] = v[1]; break;
+        case 4: d.nw[i3] = v[0]; d.nw[i3 + 1] = v[1]; break;
+        case 5: d.nw[i3 + 2] = v[0]; break;
+        case 6: d.ddv[i3] = v[0]; d.ddv[i3 + 1] = v[1]; break;
+        default: d.ddv[i3 + 2] = v[0]; break;
+      }
+    }
+    if (VARIANT != SPHBVF_TV) {
+      const double sx = octet_sum(acc.ddxx), sy = octet_sum(acc.ddxy), sz = octet_sum(acc.ddxz);
+      if (valid && sub == 0) {
+        const size_t i3 = 3 * (size_t)i;
+        d.ddx[i3] = sx; d.ddx[i3 + 1] = sy; d.ddx[i3 + 2] = sz;
+        d.Pnew[i] = acc.Pi;   // pair_ssa_tsdpd_bvf_mechanics.cpp:188
+      }
+    }
+    if (SOLIDS == 2) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        const double sk = octet_sum(acc.ddev[k]);
+        if (valid && sub == 0) d.ddev[9 * (size_t)i + k] = acc.si ? sk : 0.0;
+      }
+    }
+    if (SPECIES) {
+#pragma unroll
+      for (int k = 0; k < MAXS; k++) {
+        const double sk = octet_sum(acc.Qs[k]);
+        if (valid && sub == 0 && k < co.nspecies) d.Q[(size_t)i * co.nspecies + k] = sk;
+      }
+    }
+  }
+}
+
+// ==========================================================================================
+// dispatch
+// ==========================================================================================
+struct TileArgs {
+  const Grid *g;
+  const NeighWork *w;
+};
+
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL>
+static void launch_one(const DevState &d, const Coeffs &co, const PairTables &tb, const PairConsts &pc, const TileArgs &ta,
+                       double *vout, cudaStream_t st) {
+  if (d.list16) {
+    const size_t smem = pair_tile_smem(d.tile_cap, TileGranules<VARIANT, SOLIDS>::value, NeedsJ<SPECIES, SOLIDS, FILTER, RANDOM, VIRIAL>::value);
+    auto kern = pair_tile_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL>;
+    // opt-in to > 48 KB of dynamic shared memory: per function and per device; repeated only when the size grows
+    static size_t opted[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || opted[dev] < smem) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      // two CTAs of ~110 KB per SM need the whole shared-memory carve-out
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (dev >= 0 && dev < 64) opted[dev] = smem;
+    }
+    const long ntiles = (long)ta.g->nt[0] * ta.g->nt[1] * ta.g->nt[2];
+    kern<<<(int)ntiles, PT_T, smem, st>>>(d, *ta.g, co, tb, ta.w->cell_start, ta.w->gcell_start, ta.w->gorder, pc, vout);
+  } else {
+    const int blocks = (d.nlocal + PAIR_T - 1) / PAIR_T;
+    pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<blocks, PAIR_T, 0, st>>>(d, co, tb, pc, vout);
+  }
+  SPHBVF_LAUNCHED(1);
 }
 
 template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM>
-static void launch_filter(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf,
-                          cudaStream_t st) {
-  const int threads = PAIR_T;
-  const int blocks = (d.nlocal + threads - 1) / threads;
-#if PAIR_TMA
-  constexpr int dyn = PAIR_TMA * PAIR_T * TMA_RSTRIDE + (PAIR_T / 32) * PAIR_TMA * 8;
-  {   // per device: cheap enough to repeat on every launch of this tuning path
-    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-  }
-#define PK(F, R) pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, F, R><<<blocks, threads, dyn, st>>>(d, co, tb, pf.damp, pf.rand_pref, pf.seed, pf.ntimestep)
-#elif defined(PAIR_DIAG_SMEM)   // tools/: occupancy probe -- extra dynamic shared memory limits the resident CTAs per SM
-  cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_DIAG_SMEM);
-#define PK(F, R) pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, F, R><<<blocks, threads, ((F) || (R)) ? 0 : PAIR_DIAG_SMEM, st>>>(d, co, tb, pf.damp, pf.rand_pref, pf.seed, pf.ntimestep)
-#else
-#define PK(F, R) pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, F, R><<<blocks, threads, 0, st>>>(d, co, tb, pf.damp, pf.rand_pref, pf.seed, pf.ntimestep)
-#endif
+static void launch_filter(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf, const PairConsts &pc,
+                          const TileArgs &ta, cudaStream_t st) {
   // the stochastic variant always carries the Shepard numerator (one instantiation less per case)
-  if (pf.random) PK(true, true);
-  else if (pf.filter_step) PK(true, false);
-  else PK(false, false);
-#undef PK
+  if (pf.random) launch_one<VARIANT, SPECIES, SOLIDS, UNIFORM, true, true, false>(d, co, tb, pc, ta, nullptr, st);
+  else if (pf.filter_step) launch_one<VARIANT, SPECIES, SOLIDS, UNIFORM, true, false, false>(d, co, tb, pc, ta, nullptr, st);
+  else launch_one<VARIANT, SPECIES, SOLIDS, UNIFORM, false, false, false>(d, co, tb, pc, ta, nullptr, st);
 }
 
 template <int VARIANT, bool SPECIES>
-static void launch_solids(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf,
-                          bool uniform, cudaStream_t st) {
+static void launch_solids(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf, const PairConsts &pc,
+                          const TileArgs &ta, bool uniform, cudaStream_t st) {
   if (d.nlocal == 0) return;
   const int solids = !pf.any_solid ? 0 : (pf.with_dev ? 2 : 1);
   // the constant-coefficient fast path is instantiated for the rigid-wall / no-solid cases only
   if (solids == 0) {
-    if (uniform) launch_filter<VARIANT, SPECIES, 0, true>(d, co, tb, pf, st);
-    else launch_filter<VARIANT, SPECIES, 0, false>(d, co, tb, pf, st);
+    if (uniform) launch_filter<VARIANT, SPECIES, 0, true>(d, co, tb, pf, pc, ta, st);
+    else launch_filter<VARIANT, SPECIES, 0, false>(d, co, tb, pf, pc, ta, st);
   } else if (solids == 1) {
-    if (uniform) launch_filter<VARIANT, SPECIES, 1, true>(d, co, tb, pf, st);
-    else launch_filter<VARIANT, SPECIES, 1, false>(d, co, tb, pf, st);
-  } else launch_filter<VARIANT, SPECIES, 2, false>(d, co, tb, pf, st);
+    if (uniform) launch_filter<VARIANT, SPECIES, 1, true>(d, co, tb, pf, pc, ta, st);
+    else launch_filter<VARIANT, SPECIES, 1, false>(d, co, tb, pf, pc, ta, st);
+  } else launch_filter<VARIANT, SPECIES, 2, false>(d, co, tb, pf, pc, ta, st);
 }
 
 template <int VARIANT>
-static void launch_species(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf,
-                           bool uniform, cudaStream_t st) {
-  if (co.nspecies > 0) launch_solids<VARIANT, true>(d, co, tb, pf, uniform, st);
-  else launch_solids<VARIANT, false>(d, co, tb, pf, uniform, st);
+static void launch_species(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf, const PairConsts &pc,
+                           const TileArgs &ta, bool uniform, cudaStream_t st) {
+  if (co.nspecies > 0) launch_solids<VARIANT, true>(d, co, tb, pf, pc, ta, uniform, st);
+  else launch_solids<VARIANT, false>(d, co, tb, pf, pc, ta, uniform, st);
 }
 
 // sum_i x_i (x) f_i over the owned atoms, LAMMPS order xx yy zz xy xz yz with virial[ab] = x_a f_b
@@ -844,49 +924,61 @@ __global__ void virial_fdotr_kernel(const DevState d, double *out) {
 
 template <int VARIANT, bool SPECIES>
 static void launch_virial_solids(const DevState &d, const Coeffs &co, const PairTables &tb, const PairFlags &pf,
-                                 double *out, cudaStream_t st) {
-  const int blocks = (d.nlocal + PAIR_T - 1) / PAIR_T;
+                                 const PairConsts &pc, const TileArgs &ta, double *out, cudaStream_t st) {
   const int solids = !pf.any_solid ? 0 : (pf.with_dev ? 2 : 1);
-#if PAIR_TMA
-  constexpr int vdyn = PAIR_TMA * PAIR_T * TMA_RSTRIDE + (PAIR_T / 32) * PAIR_TMA * 8;
-  {
-    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, 0, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vdyn);
-    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, 1, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vdyn);
-    cudaFuncSetAttribute(pair_kernel<VARIANT, SPECIES, 2, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vdyn);
-  }
-#else
-  constexpr int vdyn = 0;
-#endif
-#define VK(S) pair_kernel<VARIANT, SPECIES, S, false, false, false, true><<<blocks, PAIR_T, vdyn, st>>>(d, co, tb, pf.damp, 0.0, 0ULL, pf.ntimestep, out)
-  if (solids == 0) VK(0);
-  else if (solids == 1) VK(1);
-  else VK(2);
-#undef VK
+  if (solids == 0) launch_one<VARIANT, SPECIES, 0, false, false, false, true>(d, co, tb, pc, ta, out, st);
+  else if (solids == 1) launch_one<VARIANT, SPECIES, 1, false, false, false, true>(d, co, tb, pc, ta, out, st);
+  else launch_one<VARIANT, SPECIES, 2, false, false, false, true>(d, co, tb, pc, ta, out, st);
+}
+
+static PairConsts consts_of(const PairFlags &pf) {
+  PairConsts pc;
+  pc.damp = pf.damp;
+  pc.rand_pref = pf.rand_pref;
+  pc.seed = pf.seed;
+  pc.ntimestep = pf.ntimestep;
+  return pc;
 }
 
 // Pair::virial_fdotr_compute for the gather formulation; out[6] must be zeroed by the caller
-void launch_virial(const DevState &d, const Coeffs &co, const PairFlags &pf, double *out, cudaStream_t st) {
+void launch_virial(const DevState &d, const Coeffs &co, const PairFlags &pf, const Grid &g, const NeighWork &w, double *out,
+                   cudaStream_t st) {
   if (!d.nlocal) return;
   virial_fdotr_kernel<<<(d.nlocal + 255) / 256, 256, 0, st>>>(d, out);
+  SPHBVF_LAUNCHED(1);
   if (!d.nghost) return;
+#ifndef SPHBVF_HOT_ONLY
   PairTables tb;
   make_tables(co, tb);
+  PairConsts pc = consts_of(pf);
+  pc.rand_pref = 0.0;
+  pc.seed = 0ULL;
+  const TileArgs ta = {&g, &w};
   const bool sp = co.nspecies > 0;
   switch (co.variant) {
-    case SPHBVF_TV: sp ? launch_virial_solids<SPHBVF_TV, true>(d, co, tb, pf, out, st) : launch_virial_solids<SPHBVF_TV, false>(d, co, tb, pf, out, st); break;
-    case SPHBVF_MECHANICS: sp ? launch_virial_solids<SPHBVF_MECHANICS, true>(d, co, tb, pf, out, st) : launch_virial_solids<SPHBVF_MECHANICS, false>(d, co, tb, pf, out, st); break;
-    default: sp ? launch_virial_solids<SPHBVF_FSI, true>(d, co, tb, pf, out, st) : launch_virial_solids<SPHBVF_FSI, false>(d, co, tb, pf, out, st); break;
+    case SPHBVF_TV: sp ? launch_virial_solids<SPHBVF_TV, true>(d, co, tb, pf, pc, ta, out, st) : launch_virial_solids<SPHBVF_TV, false>(d, co, tb, pf, pc, ta, out, st); break;
+    case SPHBVF_MECHANICS: sp ? launch_virial_solids<SPHBVF_MECHANICS, true>(d, co, tb, pf, pc, ta, out, st) : launch_virial_solids<SPHBVF_MECHANICS, false>(d, co, tb, pf, pc, ta, out, st); break;
+    default: sp ? launch_virial_solids<SPHBVF_FSI, true>(d, co, tb, pf, pc, ta, out, st) : launch_virial_solids<SPHBVF_FSI, false>(d, co, tb, pf, pc, ta, out, st); break;
   }
+#endif
 }
 
-void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, cudaStream_t st) {
+void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, const Grid &g, const NeighWork &w, cudaStream_t st) {
   PairTables tb;
   const bool uniform = make_tables(co, tb);
+  const PairConsts pc = consts_of(pf);
+  const TileArgs ta = {&g, &w};
+#ifdef SPHBVF_HOT_ONLY   // tuning builds (tools/build_variant.sh): only the benchmark's instantiations, seconds to compile
+  (void)uniform;
+  if (d.nlocal) launch_filter<SPHBVF_TV, false, 1, true>(d, co, tb, pf, pc, ta, st);
+  return;
+#else
   switch (co.variant) {
-    case SPHBVF_TV: launch_species<SPHBVF_TV>(d, co, tb, pf, uniform, st); break;
-    case SPHBVF_MECHANICS: launch_species<SPHBVF_MECHANICS>(d, co, tb, pf, uniform, st); break;
-    default: launch_species<SPHBVF_FSI>(d, co, tb, pf, uniform, st); break;
+    case SPHBVF_TV: launch_species<SPHBVF_TV>(d, co, tb, pf, pc, ta, uniform, st); break;
+    case SPHBVF_MECHANICS: launch_species<SPHBVF_MECHANICS>(d, co, tb, pf, pc, ta, uniform, st); break;
+    default: launch_species<SPHBVF_FSI>(d, co, tb, pf, pc, ta, uniform, st); break;
   }
+#endif
 }
 
 }  // namespace sphbvf

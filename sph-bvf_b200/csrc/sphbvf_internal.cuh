@@ -5,15 +5,21 @@
 //     x v vest [n][3] | rho rhoI e [n] | C [n][S] | dev [n][9] | tag type mask solid fixed slot [n]
 //   pair outputs, owned atoms (written once per step by the pair kernel, no atomics, no memset):
 //     f nw ddv ddx [n][3] | drho phi nd rhoAux1 rhoAux2 Pnew [n] | ddev [n][9] | Q [n][S]
-//   packed pair inputs, owned + ghost atoms, 32-byte records so that a neighbour visit is three
-//   aligned 32 B loads (two LDG.128 each) instead of 13 scattered 8 B loads:
-//     pA = {x, y, z, rho}   pB = {vest.x, vest.y, vest.z, V=m/rho}   pC = {w.x, w.y, w.z, P/rho^2}
-//     with w = vest - v (momentum minus transport velocity); pD = {rhoI, art, C0, e} is only read
-//     on Shepard-filter steps / near solids / by the fsi variant; pCs [nall][S], pdev [nall][9].
+//   packed pair inputs, owned + ghost atoms: one 96-byte record of six 16-byte granules per atom (Prec)
+//     {x, y} {z, V} {vest.x, vest.y} {vest.z, u.x} {u.y, u.z} {rho, P/rho^2}
+//     with V = m/rho and u = rho (vest - v) (density times momentum-minus-transport velocity).  The first
+//     FIVE granules (80 B) are all the hot pair pass needs: P/rho^2 = kp V (m - rho0 V) is recomputed from V
+//     with the very operations the pack kernel used, so the tile-staged kernel stages 80 B per candidate;
+//     pD = {rhoI, art, C0, e} is only read on Shepard-filter steps / by the stochastic term;
+//     pCs [nall][S], pdev [nall][9].
 //   neighbour structure: full (both directions) Verlet list of the owned atoms, frozen between
-//   rebuilds exactly like the reference's list, stored TRANSPOSED -- entry k of atom i lives at
-//   neigh[k * stride + i] -- so the 32 lanes of a warp read 128 contiguous bytes per k.  An entry
-//   packs j (27 bits), type_j (3 bits) and solid_tag_j (1 bit): no flag gather in the hot loop.
+//   rebuilds exactly like the reference's list, in one of two encodings chosen at every rebuild:
+//     list16 = 1 (tile form): 16-bit entries = slot of j among the staged candidates of i's tile
+//       (12 bits) | type_j (3 bits) | solid_tag_j (1 bit), row-major neigh16[i * pitch16 + k]: 2 B per
+//       neighbour, consumed by pair_tile_kernel (one CTA per tile, candidates staged in shared memory);
+//     list16 = 0 (gather form): 32-bit entries j (27 bits) | type_j (3) | solid_tag_j (1), stored
+//       TRANSPOSED neigh[k * stride + i] so that the 32 lanes of a warp read 128 contiguous bytes per k,
+//       consumed by pair_kernel (one thread per atom, records gathered through L1).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -36,7 +42,14 @@ struct Coeffs {
   double eta[MAXT][MAXT], cut[MAXT][MAXT], cutsq[MAXT][MAXT], cutc[MAXT][MAXT];
   double cutneighsq[MAXT][MAXT];
   double kappa[MAXT][MAXT][MAXS];
+  double kp[MAXT];   // c0^2 / m^2: P/rho^2 = kp V (m - rho0 V) with V = m/rho  (P = c0^2 (rho - rho0), pair_...:298-299)
 };
+
+// P/rho^2 from V = m/rho.  ONE definition for the pack kernel and for the tile-staged pair kernel, which recomputes
+// the value instead of staging it: same operations, same bits.
+__host__ __device__ __forceinline__ double prr_from_v(double kp, double rho0, double mass, double V) {
+  return kp * V * fma(-rho0, V, mass);
+}
 
 // 32-byte aligned record: one LDG.E.ENL2.256 per gather on sm_100a
 struct __align__(32) Rec4 {
@@ -48,11 +61,12 @@ __host__ __device__ __forceinline__ Rec4 make_rec4(double x, double y, double z,
   return r;
 }
 
-// the three records the pair kernel reads for every neighbour, contiguous: 96 bytes, 32-byte aligned
-// (1.33 particles per 128-byte line, no padding), so a visit touches 1-2 lines instead of 3
+// the record the pair kernels read for every neighbour: 96 bytes, 32-byte aligned (1.33 particles per 128-byte
+// line, no padding); as three Rec4:  A = {x, y, z, V}   B = {vest.x, vest.y, vest.z, u.x}   C = {u.y, u.z, rho, P/rho^2}
 struct __align__(32) Prec {
   Rec4 A, B, C;
 };
+constexpr int PREC_GRANULES_HOT = 5;   // 16-byte granules of a record the hot pair pass needs (no rho, no P/rho^2)
 
 // cell grid used for sorting and for the list build (covers sub-box + ghost shell).
 // Cells are numbered TILE-major: the grid is cut into tiles of 2^tb[0] x 2^tb[1] x 2^tb[2] cells
@@ -101,12 +115,19 @@ struct FixDesc {
   double a[6];
 };
 
+// the primary per-atom state (the arrays a rebuild reorders); DevState holds two sets and swaps them
+struct StateArrays {
+  int *tag, *type, *mask, *solid, *fixed, *slot;
+  double *x, *v, *vest, *rho, *rhoI, *e, *C, *dev;
+};
+
 // device pointers of one context (plain struct so kernels can take it by value)
 struct DevState {
   int nlocal, nghost, nmax, nallmax;
   // primary
   int *tag, *type, *mask, *solid, *fixed, *slot;
   double *x, *v, *vest, *rho, *rhoI, *e, *C, *dev;
+  StateArrays alt;      // second buffer of the primary state: a rebuild gathers into it and swaps (no copy back)
   // pair outputs
   double *f, *nw, *ddv, *ddx, *drho, *phi, *nd, *rhoAux1, *rhoAux2, *Pnew, *ddev, *Q;
   // packed pair inputs (owned + ghost)
@@ -119,11 +140,20 @@ struct DevState {
   // ghosts that image owned atoms of this rank (periodic self images)
   int *gowner;          // owner index (owned atom) of self-image ghost g
   double *gshift;       // [nghost][3]
-  // neighbour list
-  int *neigh;           // [maxneigh][stride]
+  // neighbour list (see the header comment for the two encodings)
+  int *neigh;           // [maxneigh][stride]   gather form (also the expanded copy sphbvf_get_pairs reads)
   int *numneigh;        // [nlocal]
   int stride, maxneigh;
+  unsigned short *neigh16;   // [nmax][pitch16]  tile form
+  int pitch16;          // entries per row, multiple of 8
+  int list16;           // encoding of the CURRENT list
+  int tile_cap;         // tile form: staged slots per tile (>= the largest candidate count, multiple of 8)
 };
+
+// kernels launched by the calling thread (every launch site of the library bumps it); the context attributes the
+// difference between tic() and toc() to a kernel family, so sphbvf_launch_count is a count, not an estimate
+extern thread_local long tl_launches;
+#define SPHBVF_LAUNCHED(n) (::sphbvf::tl_launches += (n))
 
 enum KernelFamily { K_PAIR = 0, K_INITIAL = 1, K_FINAL = 2, K_NEIGH = 3, K_PACK = 4, K_FIX = 5, K_FUSED = 6, K_NFAM = 7 };
 
@@ -151,6 +181,7 @@ void launch_pack(const DevState &d, const Coeffs &co, int with_dev, cudaStream_t
 void launch_ghost_refresh(const DevState &d, const Coeffs &co, int with_dev, cudaStream_t st);
 
 // kernels_pair.cu
+struct NeighWork;
 struct PairFlags {
   int filter_step;   // Shepard sums rhoAux1/2 are consumed this step
   int uniform;       // every type pair shares h, eta and the masses are equal
@@ -162,8 +193,12 @@ struct PairFlags {
   unsigned long long seed;
   long ntimestep;
 };
-void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, cudaStream_t st);
-void launch_virial(const DevState &d, const Coeffs &co, const PairFlags &pf, double *out6, cudaStream_t st);
+void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, const Grid &g, const NeighWork &w, cudaStream_t st);
+void launch_virial(const DevState &d, const Coeffs &co, const PairFlags &pf, const Grid &g, const NeighWork &w, double *out6,
+                   cudaStream_t st);
+// dynamic shared memory pair_tile_kernel needs for `cap` staged slots: `granules` x 16 B per record (5 hot, 6 when the
+// body reads rho_j) and 4 B per slot for the slot -> global index map of the instantiations that gather extras
+size_t pair_tile_smem(int cap, int granules, bool index_map);
 
 // kernels_neigh.cu
 struct NeighWork {      // scratch owned by the context
@@ -176,7 +211,7 @@ struct NeighWork {      // scratch owned by the context
   int *scan_tmp;        // block sums for the scan
   long ncells_cap;
   int *nimg;            // [nmax+1] images per owned atom and its exclusive scan
-  int *flags;           // device flags: [0] nonfinite, [1] lost, [2] max neighbours, [3] moved
+  int *flags;           // device flags: [0] nonfinite, [1] lost, [2] max neighbours, [3] moved, [4] max candidates of a tile
   void *tmp_perm;       // staging buffer for the permutation of one array
   size_t tmp_perm_bytes;
 };
@@ -186,10 +221,15 @@ void launch_cell_ids(const DevState &d, const Grid &g, const Box &b, const Neigh
 void exclusive_scan(const int *in, int *out, long n, int *tmp, cudaStream_t st);  // out has n+1 entries
 void launch_sort_owned(const DevState &d, const Grid &g, const NeighWork &w, cudaStream_t st);
 void launch_permute(void *arr, void *tmp, const int *perm, int n, int ncols, int elem_bytes, cudaStream_t st);
+// out.<field>[i] = in.<field>[perm[i]] for every primary array in ONE pass (dev only if with_dev, C only if S)
+void launch_gather_state(const StateArrays &in, const StateArrays &out, const int *perm, int n, int S, int with_dev, cudaStream_t st);
 void launch_count_images(const DevState &d, const Box &b, double cutghost, const NeighWork &w, cudaStream_t st);
 void launch_fill_images(const DevState &d, const Box &b, double cutghost, const NeighWork &w, cudaStream_t st);
 void launch_bin_ghosts(const DevState &d, const Grid &g, const NeighWork &w, cudaStream_t st);
 void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const NeighWork &w, cudaStream_t st);
+bool tile_form_possible(const Grid &g);   // the halo of a tile fits the tile kernels' tables
+// tile form -> gather form (d.neigh, transposed 32-bit entries) for sphbvf_get_pairs and cross-checks
+void launch_expand_list(const DevState &d, const Grid &g, const NeighWork &w, cudaStream_t st);
 void launch_copy_xhold(const DevState &d, cudaStream_t st);
 long count_pairs_host(const DevState &d, cudaStream_t st);
 
