@@ -123,6 +123,8 @@ int flush_final(sphbvf_ctx *ctx) {
     if (rcf_) return rcf_;                       \
   } while (0)
 
+int make_tile_order(sphbvf_ctx *ctx);
+
 static int ensure_scan(sphbvf_ctx *ctx, long n) {
   const long need = n / 1024 + 8192;
   if (need <= ctx->scan_cap) return 0;
@@ -310,12 +312,28 @@ int rebuild_finish(sphbvf_ctx *ctx) {
   int rc;
   launch_bin_ghosts(d, ctx->grid, w, st);
   CKLAUNCH();
-  // Encoding of this rebuild's list.  The tile form (16-bit slots, candidates of a tile staged in shared memory by
-  // pair_tile_kernel) is tried first unless SPHBVF_PAIR=gather / SPHBVF_LIST_BUILD=thread ask for the gather form; the
-  // builder reports the largest candidate count of a tile, and if that does not fit 12-bit slots or the shared
-  // memory of one CTA (worst-case instantiation: 96-byte records + index map) the list is built again in the gather form.
+  // Encoding of this rebuild's list.  The gather form is the default (faster: DESIGN.md section 3); with
+  // SPHBVF_PAIR=tile the tile form (16-bit slots, candidates of a tile staged in shared memory by pair_tile_kernel) is
+  // tried first: the builder reports the largest candidate count of a tile, and if that does not fit 12-bit slots or
+  // the shared memory of one CTA (96-byte records + index map) the list is built again in the gather form.
+  // multi-rank: the order in which the overlapped pair pass takes the atoms (interior of the brick first); the atom
+  // count of the interior comes back with the flag fetch of the list build below
+  ctx->aorder_valid = 0;
+  if (ctx->cfg.nranks > 1 && ctx->overlap_halo && tile_form_possible(ctx->grid)) {
+    if ((rc = make_tile_order(ctx))) return rc;
+    if (d.nmax > ctx->aorder_cap) {
+      if (ctx->aorder) cudaFree(ctx->aorder);
+      ctx->aorder = nullptr;
+      CK(cudaMalloc((void **)&ctx->aorder, sizeof(int) * (size_t)d.nmax));
+      ctx->aorder_cap = d.nmax;
+    }
+    launch_atom_order(ctx->grid, w, ctx->tile_order, ctx->ntiles_total, ctx->ntiles_interior, ctx->tile_cnt, ctx->tile_off,
+                      ctx->aorder, st);
+    CKLAUNCH();
+    ctx->aorder_valid = 1;
+  }
   const char *lb = getenv("SPHBVF_LIST_BUILD");
-  bool want_tile = ctx->pair_pref == 0 && !(lb && lb[0] == 't') && tile_form_possible(ctx->grid);
+  bool want_tile = ctx->pair_pref == 1 && !(lb && lb[0] == 't' && lb[1] == 'h') && tile_form_possible(ctx->grid);
   for (int attempt = 0; attempt < 3; attempt++) {
     if (d.maxneigh == 0) {
       // first guess from the number density: neighbours within cutneighmax of a uniform fluid
@@ -335,12 +353,15 @@ int rebuild_finish(sphbvf_ctx *ctx) {
     if ((rc = fetch_flags(ctx))) return rc;
     if (d.list16) {
       const int cap = (ctx->h_flags[4] + 7) & ~7;
-      if (ctx->h_flags[4] > TILE_MAX_SLOTS || pair_tile_smem(cap, 6, true) + 6144 > (size_t)ctx->smem_optin) {
+      if (ctx->h_flags[4] > TILE_MAX_SLOTS || pair_tile_smem(cap, true) + 6144 > (size_t)ctx->smem_optin) {
         want_tile = false;   // dense tiles: gather form for this rebuild interval
         attempt--;
         continue;
       }
       d.tile_cap = std::max(cap, 8);
+      if (getenv("SPHBVF_VERBOSE") && ctx->nbuilds < 2)
+        fprintf(stderr, "sphbvf[%d]: tile form, %d candidates in the fullest tile, %zu B of shared memory per CTA\n",
+                ctx->cfg.rank, ctx->h_flags[4], pair_tile_smem(d.tile_cap, false));
     }
     const int capacity = d.list16 ? d.pitch16 : d.maxneigh;
     if (ctx->h_flags[2] <= capacity) break;
@@ -349,9 +370,52 @@ int rebuild_finish(sphbvf_ctx *ctx) {
   }
   ctx->maxneigh_seen = ctx->h_flags[2];
   ctx->expanded_valid = 0;
+  ctx->natoms_interior = ctx->aorder_valid ? ctx->h_flags[5] : 0;
   launch_copy_xhold(d, st);
   ctx->ago = 0;
   ctx->nbuilds++;
+  return 0;
+}
+
+// Tiles in the order the overlapped pair pass wants them: first the tiles whose halo box holds no cell that can
+// contain a ghost (they can run while the per-step halo is still on the wire), then the ones along the brick faces.
+// A function of the cell grid only, so it is rebuilt when the grid changes, not at every rebuild.
+int make_tile_order(sphbvf_ctx *ctx) {
+  const Grid &g = ctx->grid;
+  const long ntiles = (long)g.nt[0] * g.nt[1] * g.nt[2];
+  static_assert(sizeof(int) == 4, "tile ids are 32-bit");
+  long key[10] = {g.nt[0], g.nt[1], g.nt[2], g.glo[0], g.glo[1], g.glo[2], g.ghi[0], g.ghi[1], g.ghi[2], g.n[0] + 4096L * (g.n[1] + 4096L * g.n[2])};
+  if (ctx->tile_order && ntiles == ctx->ntiles_total && memcmp(key, ctx->tile_key, sizeof key) == 0) return 0;
+  std::vector<int> inner, outer;
+  inner.reserve(ntiles);
+  for (long t = 0; t < ntiles; t++) {
+    const int tc[3] = {(int)(t % g.nt[0]), (int)((t / g.nt[0]) % g.nt[1]), (int)(t / ((long)g.nt[0] * g.nt[1]))};
+    bool ghost = false;
+    for (int k = 0; k < g.dim; k++) {
+      const int c0 = tc[k] << g.tb[k];
+      const int h0 = std::max(c0 - g.s[k], 0), h1 = std::min(c0 + (1 << g.tb[k]) - 1 + g.s[k], g.n[k] - 1);
+      if (h0 < g.glo[k] || h1 > g.ghi[k]) ghost = true;
+    }
+    (ghost ? outer : inner).push_back((int)t);
+  }
+  if (ntiles > ctx->tile_order_cap) {
+    for (int *q : {ctx->tile_order, ctx->tile_cnt, ctx->tile_off, ctx->aorder}) if (q) cudaFree(q);
+    ctx->tile_order = nullptr;
+    CK(cudaMalloc((void **)&ctx->tile_order, sizeof(int) * (size_t)ntiles));
+    if (ctx->tile_cnt) cudaFree(ctx->tile_cnt);
+    if (ctx->tile_off) cudaFree(ctx->tile_off);
+    ctx->tile_cnt = ctx->tile_off = nullptr;
+    CK(cudaMalloc((void **)&ctx->tile_cnt, sizeof(int) * (size_t)(ntiles + 2)));
+    CK(cudaMalloc((void **)&ctx->tile_off, sizeof(int) * (size_t)(ntiles + 2)));
+    ctx->tile_order_cap = ntiles;
+  }
+  ctx->ntiles_interior = (int)inner.size();
+  ctx->ntiles_total = (int)ntiles;
+  inner.insert(inner.end(), outer.begin(), outer.end());
+  // the pair pass that reads the list is ordered after this copy on the same stream; the vector dies at return
+  CK(cudaMemcpyAsync(ctx->tile_order, inner.data(), sizeof(int) * (size_t)ntiles, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  memcpy(ctx->tile_key, key, sizeof key);
   return 0;
 }
 
@@ -468,7 +532,8 @@ int sphbvf_create(const sphbvf_config *cfg, sphbvf_ctx **out) {
   cudaMemset(ctx->w.flags, 0, sizeof(int) * 8);
   ctx->run_nsteps_user = -1;
   { const char *e = getenv("SPHBVF_NO_FUSE"); ctx->fuse = !(e && atoi(e)); }
-  { const char *e = getenv("SPHBVF_PAIR"); ctx->pair_pref = (e && e[0] == 'g') ? 1 : 0; }   // gather | tile (default)
+  { const char *e = getenv("SPHBVF_PAIR"); ctx->pair_pref = (e && e[0] == 't') ? 1 : 0; }   // tile | gather (default)
+  { const char *e = getenv("SPHBVF_HALO"); ctx->overlap_halo = !(e && e[0] == 's'); }       // serial | overlap (default)
   if (cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device) != cudaSuccess)
     ctx->smem_optin = 48 * 1024;
   *out = ctx;
@@ -478,10 +543,12 @@ int sphbvf_create(const sphbvf_config *cfg, sphbvf_ctx **out) {
 void sphbvf_destroy(sphbvf_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
+  comm_halo_join(ctx);
   cudaStreamSynchronize(ctx->st);
   ctx->drain_events();
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   comm_destroy(ctx);
+  for (int *q : {ctx->tile_order, ctx->tile_cnt, ctx->tile_off, ctx->aorder}) if (q) cudaFree(q);
   DevState &d = ctx->d;
   void *ptrs[] = {d.tag, d.type, d.mask, d.solid, d.fixed, d.slot, d.x, d.v, d.vest, d.rho, d.rhoI, d.e, d.C, d.dev,
                   d.f, d.nw, d.ddv, d.ddx, d.drho, d.phi, d.nd, d.rhoAux1, d.rhoAux2, d.Pnew, d.ddev, d.Q,
@@ -508,7 +575,6 @@ int sphbvf_set_type(sphbvf_ctx *ctx, int t, double mass, double rho0, double c0,
   co.c0[t] = c0;
   co.B[t] = c0 * c0 * rho0 / 7.0;   // pair_...transport_velocity.cpp:981
   co.G0[t] = G0;
-  co.kp[t] = (c0 * c0) / (mass * mass);   // prr_from_v
   return 0;
 }
 
@@ -776,7 +842,10 @@ int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt) {
   if (pack_valid && ctx->cfg.nranks == 1 && !ctx->d.nghost) return 0;   // records are current, nothing to refresh
   ctx->tic(K_PACK);
   if (!pack_valid) launch_pack(ctx->d, ctx->co, ctx->with_dev, ctx->st);
-  if (ctx->cfg.nranks > 1) { if ((rc = comm_forward(ctx))) return rc; }
+  if (ctx->cfg.nranks > 1) {
+    const PairFlags pf = pair_flags(ctx);   // pD (rhoI, e) travels only when the coming pair pass reads it
+    if ((rc = comm_forward(ctx, pf.filter_step || pf.random))) return rc;
+  }
   else launch_ghost_refresh(ctx->d, ctx->co, ctx->with_dev, ctx->st);
   ctx->toc();
   CKLAUNCH();
@@ -786,8 +855,21 @@ int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt) {
 int sphbvf_pair_compute(sphbvf_ctx *ctx) {
   if (!ctx->setup_done) return ctx->fail(SPHBVF_ESTATE, "pair_compute before setup");
   FLUSH();
+  int rc;
   ctx->tic(K_PAIR);
-  launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->grid, ctx->w, ctx->st);
+  if (ctx->halo_pending && ctx->tile_order && ctx->ntiles_interior > 0 && (ctx->d.list16 || ctx->aorder_valid)) {
+    // the halo of this step is still in flight on its own stream: the atoms that cannot see a ghost go first, the
+    // compute stream then waits for the unpack, and the atoms along the brick faces follow
+    const int nin = ctx->ntiles_interior, ntot = ctx->ntiles_total;
+    PairSubset in = {ctx->tile_order, nin, ctx->aorder, 0, ctx->natoms_interior};
+    PairSubset out = {ctx->tile_order + nin, ntot - nin, ctx->aorder, ctx->natoms_interior, ctx->d.nlocal};
+    launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->grid, ctx->w, &in, ctx->st);
+    if ((rc = comm_halo_join(ctx))) return rc;
+    launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->grid, ctx->w, &out, ctx->st);
+  } else {
+    if ((rc = comm_halo_join(ctx))) return rc;
+    launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->grid, ctx->w, nullptr, ctx->st);
+  }
   ctx->toc();
   CKLAUNCH();
   return 0;
@@ -804,6 +886,7 @@ int sphbvf_virial(sphbvf_ctx *ctx, double *virial6) {
   if (!ctx->setup_done) return ctx->fail(SPHBVF_ESTATE, "virial before setup");
   cudaSetDevice(ctx->cfg.device);
   FLUSH();
+  { int rcj = comm_halo_join(ctx); if (rcj) return rcj; }
   if (!ctx->d_virial) CK(cudaMalloc((void **)&ctx->d_virial, sizeof(double) * 6));
   CK(cudaMemsetAsync(ctx->d_virial, 0, sizeof(double) * 6, ctx->st));
   launch_virial(ctx->d, ctx->co, pair_flags(ctx), ctx->grid, ctx->w, ctx->d_virial, ctx->st);
@@ -894,6 +977,7 @@ void *sphbvf_stream(sphbvf_ctx *ctx) { return (void *)ctx->st; }
 
 int sphbvf_sync(sphbvf_ctx *ctx) {
   FLUSH();
+  { int rcj = comm_halo_join(ctx); if (rcj) return rcj; }
   CK(cudaStreamSynchronize(ctx->st));
   return 0;
 }

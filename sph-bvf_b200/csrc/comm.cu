@@ -86,7 +86,8 @@ int sphbvf_comm_plan(const sphbvf_config *cfg, int rank, int *peer, double *shif
 // ---- NCCL halo (implemented in comm_nccl.cu when built with NCCL) ----------------------------
 #ifndef SPHBVF_WITH_NCCL
 int comm_rebuild(sphbvf_ctx *ctx) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
-int comm_forward(sphbvf_ctx *ctx) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
+int comm_forward(sphbvf_ctx *ctx, int) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
+int comm_halo_join(sphbvf_ctx *) { return 0; }
 int comm_vote(sphbvf_ctx *ctx, int *) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
 int comm_allreduce_max(sphbvf_ctx *ctx, int *, int) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
 int comm_allreduce_max_double(sphbvf_ctx *ctx, double *) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }

@@ -62,7 +62,7 @@ NcclApi *nccl_api() {
 
 constexpr int ND = 27;       // directions (dx+1) + 3 (dy+1) + 9 (dz+1); 13 = stay
 constexpr int NDX = 32;      // stride of a rank's count vector: ND counts + [27] non-finite flag, [28] lost flag, [29] status
-constexpr int NHALO = 16;    // pA pB pC pD
+constexpr int NHALO = 16;    // the 96-byte record (12) + pD (4); pD travels only when the coming pair pass reads it
 struct DirTable {
   int peer[ND];
   int off[ND + 1];           // first slot of each direction in the send list / ghost slab
@@ -84,6 +84,8 @@ struct CommState {
   int *d_dir = nullptr;      // [nmax] migration direction of each owned atom
   int dir_cap = 0;
   int *d_keep = nullptr, *d_pos = nullptr;
+  cudaStream_t halo_st = nullptr;             // the per-step halo runs here, beside the interior of the pair pass
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
 };
 
 #define CK(call)                                                                                   \
@@ -233,37 +235,47 @@ __global__ void border_kernel(const DevState d, const BrickGeom b, const double 
 }
 
 // pack_comm / pack_border: the records the pair kernel reads, position shifted by the periodic image
-//   record: pA(4) pB(4) pC(4) pD(4) | pCs[S] | pdev[9] (with_dev) | flags tag (border)
-__global__ void halo_pack_kernel(const DevState d, const int S, const int with_dev, const int border, const int nsend,
-                                 const int *sendidx, const DirTable t, double *buf) {
+//   record: prec(12) [pD(4) if with_pd] | pCs[S] | pdev[9] (with_dev) | flags tag (border)
+// pD = {rhoI, art, C0, e} is read by the Shepard-filter steps (every 20th) and by the stochastic term only: on all
+// other steps a ghost costs 96 B instead of 128 B on the wire.
+__host__ __device__ __forceinline__ int halo_width(int S, int with_dev, int border, int with_pd) {
+  return 12 + (with_pd ? 4 : 0) + S + (with_dev ? 9 : 0) + (border ? 2 : 0);
+}
+
+__global__ void halo_pack_kernel(const DevState d, const int S, const int with_dev, const int border, const int with_pd,
+                                 const int nsend, const int *sendidx, const DirTable t, double *buf) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nsend) return;
   int code = 0;
   while (s >= t.off[code + 1]) code++;
   const int i = sendidx[s];
-  const int R = NHALO + S + (with_dev ? 9 : 0) + (border ? 2 : 0);
+  const int R = halo_width(S, with_dev, border, with_pd);
   double *r = buf + (size_t)s * R;
   const Prec P = d.prec[i];
   Rec4 A = P.A;
   // x + shift in the reference's order: one rounded add per shifted dimension
   A.x += t.shift[code][0]; A.y += t.shift[code][1]; A.z += t.shift[code][2];
-  const Rec4 B = P.B, C = P.C, D = d.pD[i];
+  const Rec4 B = P.B, C = P.C;
   r[0] = A.x; r[1] = A.y; r[2] = A.z; r[3] = A.w;
   r[4] = B.x; r[5] = B.y; r[6] = B.z; r[7] = B.w;
   r[8] = C.x; r[9] = C.y; r[10] = C.z; r[11] = C.w;
-  r[12] = D.x; r[13] = D.y; r[14] = D.z; r[15] = D.w;
-  int q = NHALO;
+  int q = 12;
+  if (with_pd) {
+    const Rec4 D = d.pD[i];
+    r[12] = D.x; r[13] = D.y; r[14] = D.z; r[15] = D.w;
+    q = 16;
+  }
   for (int k = 0; k < S; k++) r[q++] = d.pCs[(size_t)i * S + k];
   if (with_dev)
     for (int k = 0; k < 9; k++) r[q++] = d.pdev[9 * (size_t)i + k];
   if (border) { r[q++] = d.pflags[i]; r[q++] = d.tag[i]; }
 }
 
-__global__ void halo_unpack_kernel(const DevState d, const int S, const int with_dev, const int border,
+__global__ void halo_unpack_kernel(const DevState d, const int S, const int with_dev, const int border, const int with_pd,
                                    const DirTable t, const double *buf) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= d.nghost) return;
-  const int R = NHALO + S + (with_dev ? 9 : 0) + (border ? 2 : 0);
+  const int R = halo_width(S, with_dev, border, with_pd);
   const double *r = buf + (size_t)g * R;
   const int j = d.nlocal + g;
   Prec P;
@@ -271,8 +283,11 @@ __global__ void halo_unpack_kernel(const DevState d, const int S, const int with
   P.B = make_rec4(r[4], r[5], r[6], r[7]);
   P.C = make_rec4(r[8], r[9], r[10], r[11]);
   d.prec[j] = P;
-  d.pD[j] = make_rec4(r[12], r[13], r[14], r[15]);
-  int q = NHALO;
+  int q = 12;
+  if (with_pd) {
+    d.pD[j] = make_rec4(r[12], r[13], r[14], r[15]);
+    q = 16;
+  }
   for (int k = 0; k < S; k++) d.pCs[(size_t)j * S + k] = r[q++];
   if (with_dev)
     for (int k = 0; k < 9; k++) d.pdev[9 * (size_t)j + k] = r[q++];
@@ -368,7 +383,7 @@ static int exchange_counts(sphbvf_ctx *ctx, int *d_local, int *sendcnt, int *rec
 // several messages between the same two ranks pair up in the order NCCL matches them; a brick
 // that neighbours itself copies on the device.
 static int exchange_payload(sphbvf_ctx *ctx, const int *sendcnt, const int *sendoff, const int *recvcnt,
-                            const int *recvoff, int width) {
+                            const int *recvoff, int width, cudaStream_t st) {
   CommState *c = ctx->comm;
   const int me = ctx->cfg.rank;
   bool any = false;
@@ -376,7 +391,7 @@ static int exchange_payload(sphbvf_ctx *ctx, const int *sendcnt, const int *send
     if (sendcnt[dcode] && c->send.peer[dcode] == me) {
       const int rd = ND - 1 - dcode;   // arrives as "from direction -d"
       CK(cudaMemcpyAsync(c->recvbuf + (size_t)recvoff[rd] * width, c->sendbuf + (size_t)sendoff[dcode] * width,
-                         sizeof(double) * (size_t)sendcnt[dcode] * width, cudaMemcpyDeviceToDevice, ctx->st));
+                         sizeof(double) * (size_t)sendcnt[dcode] * width, cudaMemcpyDeviceToDevice, st));
     } else if (sendcnt[dcode] || (recvcnt[dcode] && c->recv.peer[dcode] != me)) any = true;
   }
   if (!any) return 0;
@@ -384,25 +399,25 @@ static int exchange_payload(sphbvf_ctx *ctx, const int *sendcnt, const int *send
   for (int dcode = 0; dcode < ND; dcode++)
     if (sendcnt[dcode] && c->send.peer[dcode] != me)
       NK(nccl_api()->Send(c->sendbuf + (size_t)sendoff[dcode] * width, (size_t)sendcnt[dcode] * width, ncclDouble,
-                  c->send.peer[dcode], c->comm, ctx->st));
+                  c->send.peer[dcode], c->comm, st));
   for (int dcode = ND - 1; dcode >= 0; dcode--)
     if (recvcnt[dcode] && c->recv.peer[dcode] != me)
       NK(nccl_api()->Recv(c->recvbuf + (size_t)recvoff[dcode] * width, (size_t)recvcnt[dcode] * width, ncclDouble,
-                  c->recv.peer[dcode], c->comm, ctx->st));
+                  c->recv.peer[dcode], c->comm, st));
   NK(nccl_api()->GroupEnd());
   return 0;
 }
 
-static int halo(sphbvf_ctx *ctx, int border) {
+static int halo(sphbvf_ctx *ctx, int border, int with_pd, cudaStream_t st) {
   CommState *c = ctx->comm;
   DevState &d = ctx->d;
   const int S = ctx->co.nspecies;
-  const int R = NHALO + S + (ctx->with_dev ? 9 : 0) + (border ? 2 : 0);
+  const int R = halo_width(S, ctx->with_dev, border, with_pd);
   int rc;
   if ((rc = ensure_buf(ctx, (size_t)std::max(c->nsend, d.nghost) * R + 64))) return rc;
   if (c->nsend) {
-    halo_pack_kernel<<<nblocks(c->nsend, 256), 256, 0, ctx->st>>>(d, S, ctx->with_dev, border, c->nsend, c->sendidx,
-                                                                   c->send, c->sendbuf);
+    halo_pack_kernel<<<nblocks(c->nsend, 256), 256, 0, st>>>(d, S, ctx->with_dev, border, with_pd, c->nsend, c->sendidx,
+                                                              c->send, c->sendbuf);
     SPHBVF_LAUNCHED(1);
   }
   int sendcnt[ND], recvcnt[ND];
@@ -410,18 +425,51 @@ static int halo(sphbvf_ctx *ctx, int border) {
     sendcnt[k] = c->send.off[k + 1] - c->send.off[k];
     recvcnt[k] = c->recv.off[k + 1] - c->recv.off[k];
   }
-  if ((rc = exchange_payload(ctx, sendcnt, c->send.off, recvcnt, c->recv.off, R))) return rc;
+  if ((rc = exchange_payload(ctx, sendcnt, c->send.off, recvcnt, c->recv.off, R, st))) return rc;
   if (d.nghost) {
-    halo_unpack_kernel<<<nblocks(d.nghost, 256), 256, 0, ctx->st>>>(d, S, ctx->with_dev, border, c->recv, c->recvbuf);
+    halo_unpack_kernel<<<nblocks(d.nghost, 256), 256, 0, st>>>(d, S, ctx->with_dev, border, with_pd, c->recv, c->recvbuf);
     SPHBVF_LAUNCHED(1);
   }
   CK(cudaGetLastError());
   return 0;
 }
 
-int comm_forward(sphbvf_ctx *ctx) {
-  if (!ctx->comm) return ctx->fail(SPHBVF_ECOMM, "sphbvf_comm_init has not been called");
-  return halo(ctx, 0);
+// Per-step halo (Comm::forward_comm).  It runs on its OWN high-priority stream, ordered after the kernel that wrote
+// the records (event on the compute stream), and only the tiles of the pair pass that can see a ghost wait for it
+// (sphbvf_pair_compute launches the interior tiles first, then joins): pack -> NVLink -> unpack overlaps the interior
+// of the pair pass instead of stretching the step.  NCCL operations of the one communicator never overlap each other:
+// everything else that uses it (rebuild, votes) joins the halo stream first (comm_halo_join).
+int comm_forward(sphbvf_ctx *ctx, int with_pd) {
+  CommState *c = ctx->comm;
+  if (!c) return ctx->fail(SPHBVF_ECOMM, "sphbvf_comm_init has not been called");
+  if (!c->halo_st) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = highest priority
+    CK(cudaStreamCreateWithPriority(&c->halo_st, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+  }
+  const bool overlap = ctx->overlap_halo != 0;
+  cudaStream_t hs = overlap ? c->halo_st : ctx->st;
+  if (overlap) {
+    CK(cudaEventRecord(c->ev_ready, ctx->st));
+    CK(cudaStreamWaitEvent(hs, c->ev_ready, 0));
+  }
+  const int rc = halo(ctx, 0, with_pd, hs);
+  if (rc) return rc;
+  if (overlap) {
+    CK(cudaEventRecord(c->ev_done, hs));
+    ctx->halo_pending = 1;
+  }
+  return 0;
+}
+
+// make the compute stream wait for a halo in flight (no host synchronisation)
+int comm_halo_join(sphbvf_ctx *ctx) {
+  if (!ctx->halo_pending) return 0;
+  ctx->halo_pending = 0;
+  CK(cudaStreamWaitEvent(ctx->st, ctx->comm->ev_done, 0));
+  return 0;
 }
 
 // max over ranks of up to 8 ints: the rebuild vote (neighbor.cpp:1997) and the per-run flags
@@ -429,6 +477,7 @@ int comm_allreduce_max(sphbvf_ctx *ctx, int *vals, int n) {
   CommState *c = ctx->comm;
   if (!c) return ctx->fail(SPHBVF_ECOMM, "sphbvf_comm_init has not been called");
   if (n > 8) return ctx->fail(SPHBVF_EINVAL, "comm_allreduce_max: n > 8");
+  { int rcj = comm_halo_join(ctx); if (rcj) return rcj; }
   int *v = c->d_counts + 2 * NDX + NDX * ctx->cfg.nranks;
   for (int k = 0; k < n; k++) c->h_counts[k] = vals[k];
   CK(cudaMemcpyAsync(v, c->h_counts, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->st));
@@ -455,6 +504,7 @@ static int comm_agree(sphbvf_ctx *ctx, int rc_local) {
 int comm_allreduce_max_double(sphbvf_ctx *ctx, double *val) {
   CommState *c = ctx->comm;
   if (!c) return ctx->fail(SPHBVF_ECOMM, "sphbvf_comm_init has not been called");
+  { int rcj = comm_halo_join(ctx); if (rcj) return rcj; }
   double *v = (double *)(c->d_counts + 2 * NDX + NDX * ctx->cfg.nranks + 8);   // 8-byte aligned scratch (NDX is even)
   double *h = (double *)(c->h_counts + 2);
   *h = *val;
@@ -506,6 +556,7 @@ int comm_rebuild(sphbvf_ctx *ctx) {
   const int S = ctx->co.nspecies;
   const BrickGeom bg = geom(ctx);
   int rc;
+  if ((rc = comm_halo_join(ctx))) return rc;
   ctx->tic(K_NEIGH);
   CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * 8, st));
 
@@ -530,7 +581,7 @@ int comm_rebuild(sphbvf_ctx *ctx) {
   if (nleave || narrive) {
     const int NM = 26 + S;
     const int nstay = d.nlocal - nleave;
-    if ((rc = exchange_payload(ctx, sendcnt, sendoff, recvcnt, recvoff, NM))) return rc;
+    if ((rc = exchange_payload(ctx, sendcnt, sendoff, recvcnt, recvoff, NM, st))) return rc;
     d.nlocal = nstay;
     if (narrive) {
       unpack_arrivals_kernel<<<nblocks(narrive, 256), 256, 0, st>>>(d, S, nstay, narrive, c->recvbuf);
@@ -570,7 +621,7 @@ int comm_rebuild(sphbvf_ctx *ctx) {
       if ((rc2 = ctx_ensure_capacity(ctx, d.nmax, d.nlocal + nghost + nghost / 4 + 1024))) return rc2;
     }
     const int S2 = ctx->co.nspecies;
-    const int R = NHALO + S2 + (ctx->with_dev ? 9 : 0) + 2;
+    const int R = halo_width(S2, ctx->with_dev, 1, 1);
     return ensure_buf(ctx, (size_t)std::max(c->nsend, nghost) * R + 64);
   }();
   if ((rc = comm_agree(ctx, rc))) return rc;
@@ -581,7 +632,7 @@ int comm_rebuild(sphbvf_ctx *ctx) {
   }
   CK(cudaMemcpyAsync(d.ptag, d.tag, sizeof(int) * (size_t)d.nlocal, cudaMemcpyDeviceToDevice, st));
   launch_pack(d, ctx->co, ctx->with_dev, st);
-  if ((rc = halo(ctx, 1))) return rc;
+  if ((rc = halo(ctx, 1, 1, st))) return rc;
 
   rc = rebuild_finish(ctx);
   if ((rc = comm_agree(ctx, rc))) return rc;
@@ -592,6 +643,12 @@ int comm_rebuild(sphbvf_ctx *ctx) {
 void comm_destroy(sphbvf_ctx *ctx) {
   CommState *c = ctx->comm;
   if (!c) return;
+  if (c->halo_st) {
+    cudaStreamSynchronize(c->halo_st);
+    cudaStreamDestroy(c->halo_st);
+    cudaEventDestroy(c->ev_ready);
+    cudaEventDestroy(c->ev_done);
+  }
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
   for (void *p : {(void *)c->sendidx, (void *)c->sendbuf, (void *)c->recvbuf, (void *)c->d_counts, (void *)c->d_dir,
                   (void *)c->d_keep, (void *)c->d_pos})

@@ -34,9 +34,18 @@ struct sphbvf_ctx {
   int fuse = 1, final_pending = 0, pack_valid = 0;
   double pend_dt = 0.0;
   long pend_step = 0;
-  int pair_pref = 0;           // 0: tile form when it fits (default), 1: gather form (SPHBVF_PAIR=gather)
+  int pair_pref = 0;           // 0: gather form (default), 1: tile form when it fits (SPHBVF_PAIR=tile)
   int smem_optin = 0;          // cudaDevAttrMaxSharedMemoryPerBlockOptin of the device
   int expanded_valid = 0;      // d.neigh holds the expansion of the current tile-form list (sphbvf_get_pairs)
+  int overlap_halo = 1;        // multi-rank: per-step halo on its own stream beside the interior tiles (SPHBVF_HALO=serial: 0)
+  int halo_pending = 0;        // a halo is in flight on the halo stream; ghost readers join it first
+  int *tile_order = nullptr;   // [ntiles] tiles that cannot see a ghost first, then the others
+  int *tile_cnt = nullptr, *tile_off = nullptr;   // [ntiles + 1] scratch of the atom order
+  int *aorder = nullptr;       // [nmax] owned atoms in tile_order (gather form: the split pair pass indexes through it)
+  int aorder_cap = 0, aorder_valid = 0, natoms_interior = 0;
+  int ntiles_interior = 0, ntiles_total = 0;
+  long tile_order_cap = 0;
+  long tile_key[10] = {};
   int open_fam = -1;           // kernel family of the open tic()
   long launch_mark = 0;
   int random_set = 0;
@@ -72,7 +81,8 @@ int flush_final(sphbvf_ctx *ctx);        // launch a final_integrate that sphbvf
 
 // comm.cu / comm_nccl.cu: brick decomposition over NCCL (one rank per GPU)
 int comm_rebuild(sphbvf_ctx *ctx);        // pbc + migration + sort + borders + list
-int comm_forward(sphbvf_ctx *ctx);        // per-step halo of the packed records
+int comm_forward(sphbvf_ctx *ctx, int with_pd);   // per-step halo of the packed records (own stream when overlap_halo)
+int comm_halo_join(sphbvf_ctx *ctx);      // compute stream waits for a halo in flight
 int comm_vote(sphbvf_ctx *ctx, int *flag); // rebuild vote: max over ranks
 int comm_allreduce_max(sphbvf_ctx *ctx, int *vals, int n);   // n <= 8
 int comm_allreduce_max_double(sphbvf_ctx *ctx, double *val);

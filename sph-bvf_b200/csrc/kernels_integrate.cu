@@ -46,24 +46,24 @@ __device__ __forceinline__ int ldi(const int *p) {
 }
 
 // pack: primary state -> pair input records.  Holds every per-particle division of the pair pass:
-// V = m/rho, P/rho^2 = kp V (m - rho0 V) (the Tait law P = c0^2 (rho - rho0) of pair_...transport_velocity.cpp:298-299
-// written in terms of V, prr_from_v: the tile-staged pair kernel recomputes it from V with the same operations),
-// u = rho (vest - v), and the scalar artificial stress of a stress-free solid (:454-461 with dev = 0).  Shared by
-// pack_kernel and the fused integrator so both produce the same bits.
+// V = m/rho, P/rho^2 with P = 7 B (rho/rho0 - 1) (pair_...transport_velocity.cpp:298-299: evaluated exactly like the
+// reference, rho/rho0 - 1 first -- in a nearly quiescent fluid P is a difference of almost equal numbers and the flow
+// is driven by it, so any reformulation through V = m/rho costs ten digits: measured, 2.5e-10 on the heated cavity),
+// and the scalar artificial stress of a stress-free solid (:454-461 with dev = 0).  Shared by pack_kernel and the
+// fused integrator so both produce the same bits.
 __device__ __forceinline__ void pack_atom(const DevState &d, const Coeffs &co, const int i, const int t, const int solid,
                                           const int fixed, const double *x, const double *v, const double *vest,
                                           const double rho, const double rhoI, const double e, const int with_dev) {
   const double irho = 1.0 / rho;
-  const double V = co.mass[t] * irho;
-  const double Prr = prr_from_v(co.kp[t], co.rho0[t], co.mass[t], V);
+  const double P = 7.0 * co.B[t] * (rho / co.rho0[t] - 1.0);
+  const double Prr = P * irho * irho;
   Prec r;
-  r.A = make_rec4(x[0], x[1], x[2], V);
-  r.B = make_rec4(vest[0], vest[1], vest[2], rho * (vest[0] - v[0]));
-  r.C = make_rec4(rho * (vest[1] - v[1]), rho * (vest[2] - v[2]), rho, Prr);
+  r.A = make_rec4(x[0], x[1], x[2], rho);
+  r.B = make_rec4(vest[0], vest[1], vest[2], co.mass[t] * irho);
+  r.C = make_rec4(vest[0] - v[0], vest[1] - v[1], vest[2] - v[2], Prr);
   d.prec[i] = r;
   double art = 0.0;
   if (solid) {
-    const double P = 7.0 * co.B[t] * (rho / co.rho0[t] - 1.0);
     const double c_art = co.variant == SPHBVF_FSI ? 0.1 : 0.35;
     const double Ps = co.variant == SPHBVF_MECHANICS ? fabs(P) : P;
     const double ts = -Ps;

@@ -588,7 +588,7 @@ void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const
     }
   if (!d.nlocal) return;
   const char *env = getenv("SPHBVF_LIST_BUILD");   // read per rebuild so that tests can compare both builders
-  const bool per_thread = env && env[0] == 't' && !d.list16;
+  const bool per_thread = env && env[0] == 't' && env[1] == 'h' && !d.list16;
   if (!per_thread && tile_form_possible(g)) {
     const long ntiles = (long)g.nt[0] * g.nt[1] * g.nt[2];
     constexpr int smem = TB_CH * (int)sizeof(Cand);
@@ -614,6 +614,38 @@ void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const
   const int nb = nblocks(d.nlocal, 128);
   if (uniform) build_list_kernel<true><<<nb, 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
   else build_list_kernel<false><<<nb, 128, 0, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags);
+  SPHBVF_LAUNCHED(1);
+}
+
+__global__ void tile_counts_kernel(const int *__restrict__ tile_order, const int ntiles, const int bits,
+                                   const int *__restrict__ cell_start, int *cnt) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q > ntiles) return;
+  if (q == ntiles) { cnt[q] = 0; return; }
+  const long t = tile_order[q];
+  cnt[q] = cell_start[(t + 1) << bits] - cell_start[t << bits];
+}
+
+__global__ void atom_order_kernel(const int *__restrict__ tile_order, const int ntiles, const int bits,
+                                  const int *__restrict__ cell_start, const int *__restrict__ off, int *aorder,
+                                  const int n_first, int *flags) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // one warp per tile
+  if (q >= ntiles) return;
+  const long t = tile_order[q];
+  const int first = cell_start[t << bits], n = cell_start[(t + 1) << bits] - first, o = off[q];
+  for (int k = lane; k < n; k += 32) aorder[o + k] = first + k;
+  if (lane == 0 && q == n_first - 1) flags[5] = o + n;
+  if (lane == 0 && q == 0 && n_first == 0) flags[5] = 0;
+}
+
+void launch_atom_order(const Grid &g, const NeighWork &w, const int *tile_order, int ntiles, int n_first, int *cnt, int *off,
+                       int *aorder, cudaStream_t st) {
+  if (ntiles <= 0) return;
+  const int bits = g.tb[0] + g.tb[1] + g.tb[2];
+  tile_counts_kernel<<<nblocks(ntiles + 1, 256), 256, 0, st>>>(tile_order, ntiles, bits, w.cell_start, cnt);
+  SPHBVF_LAUNCHED(1);
+  exclusive_scan(cnt, off, ntiles + 1, w.scan_tmp, st);
+  atom_order_kernel<<<nblocks(ntiles, 8), 256, 0, st>>>(tile_order, ntiles, bits, w.cell_start, off, aorder, n_first, w.flags);
   SPHBVF_LAUNCHED(1);
 }
 

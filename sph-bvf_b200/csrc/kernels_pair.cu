@@ -14,21 +14,23 @@
 //
 // Two traversals share ONE arithmetic body (PairAcc::visit), so they differ only in summation order:
 //
-//  * pair_tile_kernel (tile form, default): one CTA per tile of the cell grid (4x4x4 cells, ~145 atoms).  The
-//    records of every candidate of the tile (the atoms of the <= 8x8x8 cells within stencil reach, ~1160) are
-//    staged ONCE in shared memory with cp.async (80 B per candidate as five 16-byte granule arrays, bank =
-//    slot mod 8), the Verlet list holds 16-bit slot numbers, and EIGHT lanes share one atom: at every step they
-//    take eight consecutive entries of its sorted list -- mostly consecutive slots, i.e. conflict-free LDS.128 --
-//    and their partial sums are combined once per atom by a halving butterfly.  No L2 round trip remains inside
-//    the neighbour loop (the gather form's limiter: 16 % L1 misses put a ~600-cycle L2 latency on nearly every
-//    warp-visit), and the list costs 2 B instead of 4 B per neighbour.
+//  * pair_kernel (gather form, default): one thread per owned atom, 192-thread CTAs, 96-byte records gathered
+//    through L1 with a hand software pipeline (records of neighbour k+1 in flight while k is evaluated, list entries
+//    through a cp.async ring): 5.6 ms per pass at 8 M atoms.
 //
-//  * pair_kernel (gather form): one thread per owned atom, 192-thread CTAs, 96-byte records gathered through L1
-//    with a hand software pipeline (records of neighbour k+1 in flight while k is evaluated, list entries through a
-//    cp.async ring).  Used when a tile's candidates do not fit (dense cells, > 4095 candidates, exotic stencils),
-//    with SPHBVF_PAIR=gather, and as the cross-check of the tile form in the tests.
+//  * pair_tile_kernel (tile form, SPHBVF_PAIR=tile): the design BASELINE.json's north star names -- one CTA per tile
+//    of the cell grid (4x4x4 cells, ~145 atoms); the records of every candidate of the tile (the atoms of the
+//    <= 8x8x8 cells within stencil reach, ~1160) are staged ONCE in shared memory with cp.async (six 16-byte granule
+//    arrays, bank group = slot mod 8), the Verlet list holds 16-bit slot numbers (2 B instead of 4 B per neighbour),
+//    and EIGHT lanes share one atom: at every step they take eight consecutive entries of its sorted list and their
+//    partial sums are combined once per atom by a halving butterfly.  No L2 round trip remains inside the neighbour
+//    loop.  Built, bit-checked against the gather form and measured (profiles/r02a_*): 8.1 ms per pass with 80-byte
+//    records at two CTAs per SM -- it executes 1.7 x the instructions of the gather form (staging 16 %, per-atom
+//    prologue / butterfly / stores 21 %), the shared-memory gathers cost as many data-pipe wavefronts as the L1
+//    gathers they replace (2.5 lanes of a quarter-warp collide on a bank group: runs of consecutive slots are only
+//    ~4 long), and with 16 warps per SM issue stays at 50 %.  Kept selectable and tested; DESIGN.md section 3.
 //
-// Common to both: every per-particle division lives in the pack kernel (V = m/rho, P/rho^2, u = rho (vest - v)),
+// Common to both: every per-particle division lives in the pack kernel (V = m/rho, P/rho^2),
 // sqrt is a branch-free Goldschmidt iteration on MUFU.RSQ64H (7 FP64 ops, < 1 ulp), per-type-pair coefficients are
 // kernel-argument constants when every type pair shares them (all cavity decks and the synthetic lattice) and
 // rows of a small shared-memory table otherwise.
@@ -64,8 +66,7 @@ struct __align__(16) PairRow {
 
 // per type: what the body needs about atom j's type beyond the pair row
 struct __align__(16) TypeRow {
-  double imass, mass, rho0, kp;    // 1/m, m, rho0, c0^2/m^2 (prr_from_v)
-  double c0, G0, pad0, pad1;
+  double imass, c0, G0, pad;    // 1/m, c0, G0
 };
 
 struct PairTables {
@@ -83,13 +84,8 @@ static bool make_tables(const Coeffs &co, PairTables &t) {
   bool uniform = true;
   for (int i = 1; i <= co.ntypes; i++) {
     t.type[i].imass = 1.0 / co.mass[i];
-    t.type[i].mass = co.mass[i];
-    t.type[i].rho0 = co.rho0[i];
-    t.type[i].kp = co.kp[i];
     t.type[i].c0 = co.c0[i];
     t.type[i].G0 = co.G0[i];
-    // the constant-coefficient path also takes the per-type constants of atom j from type 1
-    if (co.mass[i] != co.mass[1] || co.rho0[i] != co.rho0[1] || co.c0[i] != co.c0[1]) uniform = false;
     for (int j = 1; j <= co.ntypes; j++) {
       auto coef = [&](double h, double &cwfd, double &cwf) {
         double ih = 1.0 / h, ihsq = ih * ih;
@@ -188,7 +184,7 @@ struct PairConsts {
 template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM>
 struct PairAcc {
   // atom i
-  double xi, yi, zi, Vi, vxi, vyi, vzi, uxi, uyi, uzi, rhoi, Prri;
+  double xi, yi, zi, rhoi, vxi, vyi, vzi, Vi, wxi, wyi, wzi, Prri;   // record: A = {x,y,z,rho} B = {vest,V} C = {w,P/rho^2}
   double Vi2, c0i, Pi, irhoi, G0i, ei, arti;
   int ti, tagi;
   bool si;
@@ -204,9 +200,9 @@ struct PairAcc {
                                        const int i, const int fl, const Rec4 &A, const Rec4 &B, const Rec4 &C) {
     ti = fl & 7;
     si = SOLIDS && ((fl >> 4) & 1);
-    xi = A.x; yi = A.y; zi = A.z; Vi = A.w;
-    vxi = B.x; vyi = B.y; vzi = B.z; uxi = B.w;
-    uyi = C.x; uzi = C.y; rhoi = C.z; Prri = C.w;
+    xi = A.x; yi = A.y; zi = A.z; rhoi = A.w;
+    vxi = B.x; vyi = B.y; vzi = B.z; Vi = B.w;
+    wxi = C.x; wyi = C.y; wzi = C.z; Prri = C.w;
     Vi2 = Vi * Vi;
     c0i = co.c0[ti];
     Pi = Prri * rhoi * rhoi;
@@ -237,7 +233,7 @@ struct PairAcc {
     fx = fy = fz = drho = nd = rA1 = rA2 = phi = 0.0;
     ddvx = ddvy = ddvz = nwx = nwy = nwz = 0.0;
     ddxx = ddxy = ddxz = 0.0;
-    spi = 0.0;   // sum_j s_ij q_i: the i-side transport term is vest_i times this
+    spi = 0.0;   // sum_j s_ij rho_i a_i: the i-side transport term is vest_i times this
     if (SOLIDS == 2)
 #pragma unroll
       for (int k = 0; k < 9; k++) ddev[k] = 0.0;
@@ -246,14 +242,13 @@ struct PairAcc {
       for (int k = 0; k < MAXS; k++) Qs[k] = 0.0;
   }
 
-  // HAVE_RP: rhoj and Prrj come with the record; otherwise (80-byte staged records) P/rho^2 is recomputed from V
-  // with the pack kernel's own operations (same bits) and rho_j, needed by the solid-i viscosity only, is m_j / V_j
-  template <bool HAVE_RP>
+  // one neighbour, handed over as the fields of its record; `j` (its global index) is only used by the
+  // instantiations that gather extras
   __device__ __forceinline__ void visit(const DevState &d, const Coeffs &co, const PairTables &tb, const PairConsts &pc,
                                         const int tj, const bool sj_in, const int j, const double xj, const double yj,
-                                        const double zj, const double Vj, const double vxj, const double vyj,
-                                        const double vzj, const double uxj, const double uyj, const double uzj,
-                                        double rhoj, double Prrj, const double rhoIj) {
+                                        const double zj, const double rhoj, const double vxj, const double vyj,
+                                        const double vzj, const double Vj, const double wxj, const double wyj,
+                                        const double wzj, const double Prrj, const double rhoIj) {
     const bool sj = SOLIDS && sj_in;
     const double delx = xi - xj, dely = yi - yj, delz = zi - zj;
     const double rsq = delx * delx + dely * dely + delz * delz;
@@ -268,8 +263,6 @@ struct PairAcc {
     if (!(rsq < cutsq)) return;
     const double iwdelta = UNIFORM ? tb.row[MAXT + 1].iwdelta : myrow[tj].iwdelta;
     const double h2eps = UNIFORM ? tb.row[MAXT + 1].h2eps : myrow[tj].h2eps;
-    const TypeRow &tyj = tb.type[UNIFORM ? 1 : tj];
-    if (!HAVE_RP) Prrj = prr_from_v(tyj.kp, tyj.rho0, tyj.mass, Vj);
 
     const double r = fast_sqrt(rsq);
     const double t = h - r, t2 = t * t;
@@ -278,11 +271,9 @@ struct PairAcc {
     const double Vj2 = Vj * Vj;
     const double velx = vxi - vxj, vely = vyi - vyj, velz = vzi - vzj;
     const double dvr = delx * velx + dely * vely + delz * velz;
-    // q = rho (v - vt) . del, straight from the stored u = rho (vest - v); a = (v - vt) . del = q / rho = q V / m
-    const double qi = uxi * delx + uyi * dely + uzi * delz;
-    const double qj = uxj * delx + uyj * dely + uzj * delz;
-    const double irhoj = Vj * tyj.imass;
-    const double aj = qj * irhoj;
+    const double ai = wxi * delx + wyi * dely + wzi * delz;   // (v_i - vt_i) . del
+    const double aj = wxj * delx + wyj * dely + wzj * delz;
+    const double qi = rhoi * ai, qj = rhoj * aj;
     const double S2 = Vi2 + Vj2;
     const double S2w = S2 * wfd;
 
@@ -316,6 +307,7 @@ struct PairAcc {
 
     double devj[9];
     if (SOLIDS == 2) {
+      const double irhoj = Vj * tb.type[tj].imass;
       if (si || sj) {
 #pragma unroll
         for (int k = 0; k < 9; k++) devj[k] = sj ? d.pdev[9 * (size_t)j + k] : 0.0;
@@ -338,10 +330,10 @@ struct PairAcc {
       }
       // ---- Jaumann rate for solid i (:435-451)
       if (si) {
-        double G0j = tyj.G0;
+        double G0j = tb.type[tj].G0;
         double geff;
         if (VARIANT == SPHBVF_FSI && SPECIES) {
-          G0j = tyj.G0 * (1.0 - 0.99 * d.pCs[(size_t)j * co.nspecies]);
+          G0j = tb.type[tj].G0 * (1.0 - 0.99 * d.pCs[(size_t)j * co.nspecies]);
           geff = (2.0 * G0i * G0j) / (G0i + G0j + 1e-12);
         } else geff = tb.geff[ti][tj];
         const double hw = -0.5 * Vj * wfd;   // 0.5 * Vj * wfd * (v_j - v_i) = hw * vel
@@ -370,7 +362,7 @@ struct PairAcc {
     // ---- momentum (:497-529)
     if (!si) {
       // chained FMAs into the accumulators (4 per component instead of 7 separately rounded ops);
-      // the i-side transport term s q_i vest_i has a per-atom constant vector: summed as a scalar
+      // the i-side transport term s rho_i a_i vest_i has a per-atom constant vector: summed as a scalar
       const double fvisc = S2w * eta;
       const double s = -0.5 * S2w;
       const double pj_ = s * qj;
@@ -417,15 +409,15 @@ struct PairAcc {
     } else {
       double fviscs = 0.;
       if (dvr < 0.) {
-        if (!HAVE_RP) rhoj = tyj.mass * fast_rcp(Vj);
         const double mu = h * dvr * fast_rcp(rsq + h2eps);
-        fviscs = mmw * (-(c0i + tyj.c0) * mu + 2.0 * mu * mu) * fast_rcp(rhoi + rhoj);
+        fviscs = mmw * (-(c0i + tb.type[tj].c0) * mu + 2.0 * mu * mu) * fast_rcp(rhoi + rhoj);
       }
       const double cc = -(fpair + fviscs);
       fx += cc * delx + fartx;
       fy += cc * dely + farty;
       fz += cc * delz + fartz;
       if (SOLIDS == 2) {
+        const double irhoj = Vj * tb.type[tj].imass;
         const double ii = irhoi * irhoi, jj = irhoj * irhoj;
         fx += mmw * (delx * (devi[0] * ii + devj[0] * jj) + dely * (devi[3] * ii + devj[3] * jj) + delz * (devi[6] * ii + devj[6] * jj));
         fy += mmw * (delx * (devi[1] * ii + devj[1] * jj) + dely * (devi[4] * ii + devj[4] * jj) + delz * (devi[7] * ii + devj[7] * jj));
@@ -455,7 +447,7 @@ struct PairAcc {
       if (r < hc) {
         const double tc = hc - r;
         const double wfdc = tb.cwfdc[ti][tj] * tc * tc;
-        const double ai = qi * irhoi;
+        const double irhoj = Vj * tb.type[tj].imass;
         const double q0 = tb.mred2[ti][tj] * (irhoi + irhoj) * rsq * wfdc / (rsq + tb.hc2eps[ti][tj]);
         for (int k = 0; k < co.nspecies; k++) {
           const double Cjk = d.pCs[(size_t)j * co.nspecies + k];
@@ -494,15 +486,18 @@ __device__ __forceinline__ void cp_async4(int *smem_dst, const int *gsrc) {
 template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL = false>
 __global__ void __launch_bounds__(PAIR_T, PAIR_MINB)
 pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
-            const PairConsts pc, double *virial_out = nullptr) {
+            const PairConsts pc, const int *__restrict__ aorder, const int a0, const int a1, double *virial_out = nullptr) {
   __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
   __shared__ int ring[RING][PAIR_T];
   if (!UNIFORM) {
     for (int q = threadIdx.x; q < MAXT * MAXT; q += blockDim.x) srow[q] = tb.row[q];
     __syncthreads();
   }
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.nlocal) return;
+  // atoms [a0, a1) of the launch, through the atom order when the pass is split (interior of the brick while the
+  // halo is in flight, then the atoms that can see a ghost): consecutive positions stay consecutive atoms of a tile
+  const int p = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a1) return;
+  const int i = aorder ? aorder[p] : p;
 
   PairAcc<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM> acc;
   acc.init(d, co, tb, srow, i, d.pflags[i], d.prec[i].A, d.prec[i].B, d.prec[i].C);
@@ -513,7 +508,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     const int tj = (ent >> NEIGH_JBITS) & 7;
     const bool sj = (ent >> 30) & 1;
     if (!VIRIAL) {
-      acc.template visit<true>(d, co, tb, pc, tj, sj, j, Aj.x, Aj.y, Aj.z, Aj.w, Bj.x, Bj.y, Bj.z, Bj.w, Cj.x, Cj.y, Cj.z, Cj.w, rhoIj);
+      acc.visit(d, co, tb, pc, tj, sj, j, Aj.x, Aj.y, Aj.z, Aj.w, Bj.x, Bj.y, Bj.z, Bj.w, Cj.x, Cj.y, Cj.z, Cj.w, rhoIj);
       return;
     }
     const int g = j - d.nlocal;
@@ -522,7 +517,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     if (sx == 0.0 && sy == 0.0 && sz == 0.0) return;
     double f0x, f0y, f0z, f1x, f1y, f1z;
     acc.force_now(f0x, f0y, f0z);
-    acc.template visit<true>(d, co, tb, pc, tj, sj, j, Aj.x, Aj.y, Aj.z, Aj.w, Bj.x, Bj.y, Bj.z, Bj.w, Cj.x, Cj.y, Cj.z, Cj.w, rhoIj);
+    acc.visit(d, co, tb, pc, tj, sj, j, Aj.x, Aj.y, Aj.z, Aj.w, Bj.x, Bj.y, Bj.z, Bj.w, Cj.x, Cj.y, Cj.z, Cj.w, rhoIj);
     acc.force_now(f1x, f1y, f1z);
     const double Fx = f1x - f0x, Fy = f1y - f0y, Fz = f1z - f0z;
     vir[0] -= 0.5 * sx * Fx; vir[1] -= 0.5 * sy * Fy; vir[2] -= 0.5 * sz * Fz;
@@ -662,19 +657,15 @@ __device__ __forceinline__ void octet_reduce16(double (&v)[16], const int lane) 
   }
 }
 
-// NG = 16-byte granules staged per candidate: 5 (80 B) in the hot instantiations, 6 when the body reads rho_j
-template <int VARIANT, int SOLIDS>
-struct TileGranules { static constexpr int value = (VARIANT == SPHBVF_FSI || SOLIDS == 2) ? 6 : PREC_GRANULES_HOT; };
-
-size_t pair_tile_smem(int cap, int granules, bool index_map) { return (size_t)cap * (granules * 16 + (index_map ? 4 : 0)); }
+size_t pair_tile_smem(int cap, bool index_map) { return (size_t)cap * (PREC_GRANULES * 16 + (index_map ? 4 : 0)); }
 
 template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL = false>
 __global__ void __launch_bounds__(PT_T, (SOLIDS == 2 || SPECIES || RANDOM) ? 1 : PT_MINB)   // the heavy instantiations get 255 registers
 pair_tile_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_constant__ Coeffs co,
                  const __grid_constant__ PairTables tb, const int *__restrict__ cell_start,
-                 const int *__restrict__ gcell_start, const int *__restrict__ gorder, const PairConsts pc,
-                 double *virial_out = nullptr) {
-  constexpr int NG = TileGranules<VARIANT, SOLIDS>::value;
+                 const int *__restrict__ gcell_start, const int *__restrict__ gorder, const int *__restrict__ tile_list,
+                 const PairConsts pc, double *virial_out = nullptr) {
+  constexpr int NG = PREC_GRANULES;
   constexpr bool NEEDJ = NeedsJ<SPECIES, SOLIDS, FILTER, RANDOM, VIRIAL>::value;
   extern __shared__ __align__(16) unsigned char pt_smem[];
   __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
@@ -683,7 +674,8 @@ pair_tile_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_
   __shared__ int next_group;
 
   TileGeom t;
-  if (!tile_geometry(g, blockIdx.x, cell_start, t)) return;   // no owned atom in this tile (whole CTA)
+  // tile_list: the tiles of this launch (interior tiles while the halo is in flight, then the ones that see ghosts)
+  if (!tile_geometry(g, tile_list ? tile_list[blockIdx.x] : blockIdx.x, cell_start, t)) return;   // no owned atom (whole CTA)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cap = d.tile_cap;
   double2 *rec = reinterpret_cast<double2 *>(pt_smem);        // rec[gr * cap + slot], cap a multiple of 8: bank group = slot mod 8
@@ -725,40 +717,45 @@ pair_tile_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_
     nnmax = max(nnmax, __shfl_xor_sync(0xffffffffu, nnmax, 8));
     nnmax = max(nnmax, __shfl_xor_sync(0xffffffffu, nnmax, 16));
     const unsigned short *row = d.neigh16 + (size_t)i * d.pitch16 + sub;   // entry k of my lane at step s: k = 8 s + sub
-    // entries of the first block of 8 steps (64 entries of the row), requested with the atom's own record
-    unsigned e_cur[8], e_nxt[8];
+    // The entries of a block of 8 steps (64 entries of the row) travel as eight 16-bit loads packed into two 64-bit
+    // registers; the NEXT block is requested before the current one is evaluated (the list is the only DRAM stream
+    // of the loop), and a step shifts its entry out -- no register array, so the visit loop stays ONE copy of the
+    // body in the instruction cache (unrolled eight times it was 77 KB of code).
+    auto load_block = [&](const int sb, unsigned long long &lo, unsigned long long &hi) {
+      unsigned e[8];
 #pragma unroll
-    for (int q = 0; q < 8; q++) e_cur[q] = (8 * q + sub < nn) ? row[8 * q] : 0u;
+      for (int q = 0; q < 8; q++) e[q] = (8 * (sb + q) + sub < nn) ? row[8 * (sb + q)] : 0u;
+      lo = (unsigned long long)e[0] | (unsigned long long)e[1] << 16 | (unsigned long long)e[2] << 32 | (unsigned long long)e[3] << 48;
+      hi = (unsigned long long)e[4] | (unsigned long long)e[5] << 16 | (unsigned long long)e[6] << 32 | (unsigned long long)e[7] << 48;
+    };
+    unsigned long long cur_lo, cur_hi, nxt_lo, nxt_hi;
+    load_block(0, cur_lo, cur_hi);
 
     PairAcc<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM> acc;
     acc.init(d, co, tb, srow, i, d.pflags[i], d.prec[i].A, d.prec[i].B, d.prec[i].C);
     double vir[6] = {0, 0, 0, 0, 0, 0};
 
-    for (int s0 = 0; 8 * s0 < nnmax; s0 += 8) {
-      // the entries of the NEXT block of 8 steps are requested before this block is evaluated
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const int k = 8 * (s0 + 8 + q) + sub;
-        e_nxt[q] = k < nn ? row[8 * (s0 + 8 + q)] : 0u;
-      }
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const int k = 8 * (s0 + q) + sub;
-        if (8 * (s0 + q) >= nnmax) break;   // warp-uniform
-        const unsigned e = e_cur[q];
+    const int nsteps = (nnmax + 7) >> 3;   // warp-uniform
+    for (int s0 = 0; s0 < nsteps; s0 += 8) {
+      load_block(s0 + 8, nxt_lo, nxt_hi);
+      const int send = min(s0 + 8, nsteps);
+#pragma unroll 1
+      for (int st = s0; st < send; st++) {
+        const unsigned e = (unsigned)cur_lo & 0xffffu;
+        cur_lo = (cur_lo >> 16) | (cur_hi << 48);
+        cur_hi >>= 16;
+        const int k = 8 * st + sub;
         const int slot = e & TILE_SLOT_MASK;
+        // granules of the record: {x, y} {z, rho} {vest.x, vest.y} {vest.z, V} {w.x, w.y} {w.z, P/rho^2}
         const double2 g0 = rec[slot], g1 = rec[cap + slot], g2 = rec[2 * cap + slot], g3 = rec[3 * cap + slot],
-                      g4 = rec[4 * cap + slot];
-        double rhoj = 0.0, Prrj = 0.0;
-        if (NG == 6) { const double2 g5 = rec[5 * cap + slot]; rhoj = g5.x; Prrj = g5.y; }
+                      g4 = rec[4 * cap + slot], g5 = rec[5 * cap + slot];
         if (k < nn) {
           const int tj = (e >> TILE_SLOT_BITS) & 7;
           const bool sj = (e >> 15) & 1;
           const int j = NEEDJ ? gidx[slot] : 0;
           const double rhoIj = FILTER ? d.pD[j].x : 0.0;
           if (!VIRIAL) {
-            acc.template visit<NG == 6>(d, co, tb, pc, tj, sj, j, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y, g4.x, g4.y,
-                                        rhoj, Prrj, rhoIj);
+            acc.visit(d, co, tb, pc, tj, sj, j, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y, g4.x, g4.y, g5.x, g5.y, rhoIj);
           } else {
             const int gh = j - d.nlocal;
             if (gh >= 0) {
@@ -766,8 +763,7 @@ pair_tile_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_
               if (sx != 0.0 || sy != 0.0 || sz != 0.0) {
                 double f0x, f0y, f0z, f1x, f1y, f1z;
                 acc.force_now(f0x, f0y, f0z);
-                acc.template visit<NG == 6>(d, co, tb, pc, tj, sj, j, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y, g4.x,
-                                            g4.y, rhoj, Prrj, rhoIj);
+                acc.visit(d, co, tb, pc, tj, sj, j, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y, g4.x, g4.y, g5.x, g5.y, rhoIj);
                 acc.force_now(f1x, f1y, f1z);
                 const double Fx = f1x - f0x, Fy = f1y - f0y, Fz = f1z - f0z;
                 vir[0] -= 0.5 * sx * Fx; vir[1] -= 0.5 * sy * Fy; vir[2] -= 0.5 * sz * Fz;
@@ -777,8 +773,8 @@ pair_tile_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_
           }
         }
       }
-#pragma unroll
-      for (int q = 0; q < 8; q++) e_cur[q] = e_nxt[q];
+      cur_lo = nxt_lo;
+      cur_hi = nxt_hi;
     }
 
     if (VIRIAL) {
@@ -839,13 +835,17 @@ pair_tile_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_
 struct TileArgs {
   const Grid *g;
   const NeighWork *w;
+  const int *tile_list;   // tile form: nullptr = every tile of the grid
+  int ntiles;
+  const int *aorder;      // gather form: positions [a0, a1) of this atom order (nullptr: atoms a0 .. a1)
+  int a0, a1;
 };
 
 template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL>
 static void launch_one(const DevState &d, const Coeffs &co, const PairTables &tb, const PairConsts &pc, const TileArgs &ta,
                        double *vout, cudaStream_t st) {
   if (d.list16) {
-    const size_t smem = pair_tile_smem(d.tile_cap, TileGranules<VARIANT, SOLIDS>::value, NeedsJ<SPECIES, SOLIDS, FILTER, RANDOM, VIRIAL>::value);
+    const size_t smem = pair_tile_smem(d.tile_cap, NeedsJ<SPECIES, SOLIDS, FILTER, RANDOM, VIRIAL>::value);
     auto kern = pair_tile_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL>;
     // opt-in to > 48 KB of dynamic shared memory: per function and per device; repeated only when the size grows
     static size_t opted[64] = {};
@@ -857,11 +857,12 @@ static void launch_one(const DevState &d, const Coeffs &co, const PairTables &tb
       cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (dev >= 0 && dev < 64) opted[dev] = smem;
     }
-    const long ntiles = (long)ta.g->nt[0] * ta.g->nt[1] * ta.g->nt[2];
-    kern<<<(int)ntiles, PT_T, smem, st>>>(d, *ta.g, co, tb, ta.w->cell_start, ta.w->gcell_start, ta.w->gorder, pc, vout);
+    if (ta.ntiles <= 0) return;
+    kern<<<ta.ntiles, PT_T, smem, st>>>(d, *ta.g, co, tb, ta.w->cell_start, ta.w->gcell_start, ta.w->gorder, ta.tile_list, pc, vout);
   } else {
-    const int blocks = (d.nlocal + PAIR_T - 1) / PAIR_T;
-    pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<blocks, PAIR_T, 0, st>>>(d, co, tb, pc, vout);
+    if (ta.a1 <= ta.a0) return;
+    const int blocks = (ta.a1 - ta.a0 + PAIR_T - 1) / PAIR_T;
+    pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<blocks, PAIR_T, 0, st>>>(d, co, tb, pc, ta.aorder, ta.a0, ta.a1, vout);
   }
   SPHBVF_LAUNCHED(1);
 }
@@ -941,6 +942,11 @@ static PairConsts consts_of(const PairFlags &pf) {
 }
 
 // Pair::virial_fdotr_compute for the gather formulation; out[6] must be zeroed by the caller
+static TileArgs all_atoms(const DevState &d, const Grid &g, const NeighWork &w) {
+  TileArgs ta = {&g, &w, nullptr, (int)((long)g.nt[0] * g.nt[1] * g.nt[2]), nullptr, 0, d.nlocal};
+  return ta;
+}
+
 void launch_virial(const DevState &d, const Coeffs &co, const PairFlags &pf, const Grid &g, const NeighWork &w, double *out,
                    cudaStream_t st) {
   if (!d.nlocal) return;
@@ -953,7 +959,7 @@ void launch_virial(const DevState &d, const Coeffs &co, const PairFlags &pf, con
   PairConsts pc = consts_of(pf);
   pc.rand_pref = 0.0;
   pc.seed = 0ULL;
-  const TileArgs ta = {&g, &w};
+  const TileArgs ta = all_atoms(d, g, w);
   const bool sp = co.nspecies > 0;
   switch (co.variant) {
     case SPHBVF_TV: sp ? launch_virial_solids<SPHBVF_TV, true>(d, co, tb, pf, pc, ta, out, st) : launch_virial_solids<SPHBVF_TV, false>(d, co, tb, pf, pc, ta, out, st); break;
@@ -963,11 +969,17 @@ void launch_virial(const DevState &d, const Coeffs &co, const PairFlags &pf, con
 #endif
 }
 
-void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, const Grid &g, const NeighWork &w, cudaStream_t st) {
+// part: the subset of the owned atoms to process (nullptr: all of them)
+void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, const Grid &g, const NeighWork &w,
+                 const PairSubset *part, cudaStream_t st) {
   PairTables tb;
   const bool uniform = make_tables(co, tb);
   const PairConsts pc = consts_of(pf);
-  const TileArgs ta = {&g, &w};
+  TileArgs ta = all_atoms(d, g, w);
+  if (part) {
+    ta.tile_list = part->tile_list; ta.ntiles = part->ntiles;
+    ta.aorder = part->aorder; ta.a0 = part->a0; ta.a1 = part->a1;
+  }
 #ifdef SPHBVF_HOT_ONLY   // tuning builds (tools/build_variant.sh): only the benchmark's instantiations, seconds to compile
   (void)uniform;
   if (d.nlocal) launch_filter<SPHBVF_TV, false, 1, true>(d, co, tb, pf, pc, ta, st);

@@ -5,19 +5,17 @@
 //     x v vest [n][3] | rho rhoI e [n] | C [n][S] | dev [n][9] | tag type mask solid fixed slot [n]
 //   pair outputs, owned atoms (written once per step by the pair kernel, no atomics, no memset):
 //     f nw ddv ddx [n][3] | drho phi nd rhoAux1 rhoAux2 Pnew [n] | ddev [n][9] | Q [n][S]
-//   packed pair inputs, owned + ghost atoms: one 96-byte record of six 16-byte granules per atom (Prec)
-//     {x, y} {z, V} {vest.x, vest.y} {vest.z, u.x} {u.y, u.z} {rho, P/rho^2}
-//     with V = m/rho and u = rho (vest - v) (density times momentum-minus-transport velocity).  The first
-//     FIVE granules (80 B) are all the hot pair pass needs: P/rho^2 = kp V (m - rho0 V) is recomputed from V
-//     with the very operations the pack kernel used, so the tile-staged kernel stages 80 B per candidate;
-//     pD = {rhoI, art, C0, e} is only read on Shepard-filter steps / by the stochastic term;
-//     pCs [nall][S], pdev [nall][9].
+//   packed pair inputs, owned + ghost atoms: one 96-byte record (three 32-byte aligned quarters, six 16-byte
+//   granules) per atom, so a neighbour visit is three 256-bit loads that touch one or two cache lines:
+//     A = {x, y, z, rho}   B = {vest.x, vest.y, vest.z, V = m/rho}   C = {w.x, w.y, w.z, P/rho^2}
+//     with w = vest - v (momentum minus transport velocity); pD = {rhoI, art, C0, e} is only read on
+//     Shepard-filter steps and by the stochastic term; pCs [nall][S], pdev [nall][9].
 //   neighbour structure: full (both directions) Verlet list of the owned atoms, frozen between
 //   rebuilds exactly like the reference's list, in one of two encodings chosen at every rebuild:
-//     list16 = 1 (tile form): 16-bit entries = slot of j among the staged candidates of i's tile
+//     list16 = 1 (tile form, SPHBVF_PAIR=tile): 16-bit entries = slot of j among the staged candidates of i's tile
 //       (12 bits) | type_j (3 bits) | solid_tag_j (1 bit), row-major neigh16[i * pitch16 + k]: 2 B per
 //       neighbour, consumed by pair_tile_kernel (one CTA per tile, candidates staged in shared memory);
-//     list16 = 0 (gather form): 32-bit entries j (27 bits) | type_j (3) | solid_tag_j (1), stored
+//     list16 = 0 (gather form, default): 32-bit entries j (27 bits) | type_j (3) | solid_tag_j (1), stored
 //       TRANSPOSED neigh[k * stride + i] so that the 32 lanes of a warp read 128 contiguous bytes per k,
 //       consumed by pair_kernel (one thread per atom, records gathered through L1).
 #pragma once
@@ -42,14 +40,7 @@ struct Coeffs {
   double eta[MAXT][MAXT], cut[MAXT][MAXT], cutsq[MAXT][MAXT], cutc[MAXT][MAXT];
   double cutneighsq[MAXT][MAXT];
   double kappa[MAXT][MAXT][MAXS];
-  double kp[MAXT];   // c0^2 / m^2: P/rho^2 = kp V (m - rho0 V) with V = m/rho  (P = c0^2 (rho - rho0), pair_...:298-299)
 };
-
-// P/rho^2 from V = m/rho.  ONE definition for the pack kernel and for the tile-staged pair kernel, which recomputes
-// the value instead of staging it: same operations, same bits.
-__host__ __device__ __forceinline__ double prr_from_v(double kp, double rho0, double mass, double V) {
-  return kp * V * fma(-rho0, V, mass);
-}
 
 // 32-byte aligned record: one LDG.E.ENL2.256 per gather on sm_100a
 struct __align__(32) Rec4 {
@@ -62,11 +53,11 @@ __host__ __device__ __forceinline__ Rec4 make_rec4(double x, double y, double z,
 }
 
 // the record the pair kernels read for every neighbour: 96 bytes, 32-byte aligned (1.33 particles per 128-byte
-// line, no padding); as three Rec4:  A = {x, y, z, V}   B = {vest.x, vest.y, vest.z, u.x}   C = {u.y, u.z, rho, P/rho^2}
+// line, no padding):  A = {x, y, z, rho}   B = {vest.x, vest.y, vest.z, V}   C = {w.x, w.y, w.z, P/rho^2}
 struct __align__(32) Prec {
   Rec4 A, B, C;
 };
-constexpr int PREC_GRANULES_HOT = 5;   // 16-byte granules of a record the hot pair pass needs (no rho, no P/rho^2)
+constexpr int PREC_GRANULES = 6;   // 16-byte granules per record
 
 // cell grid used for sorting and for the list build (covers sub-box + ghost shell).
 // Cells are numbered TILE-major: the grid is cut into tiles of 2^tb[0] x 2^tb[1] x 2^tb[2] cells
@@ -193,12 +184,21 @@ struct PairFlags {
   unsigned long long seed;
   long ntimestep;
 };
-void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, const Grid &g, const NeighWork &w, cudaStream_t st);
+// part of the owned atoms a pair launch covers (the overlapped halo runs the interior first): tile form -> a list of
+// tiles; gather form -> positions [a0, a1) of an atom order (nullptr: the atoms themselves)
+struct PairSubset {
+  const int *tile_list;
+  int ntiles;
+  const int *aorder;
+  int a0, a1;
+};
+void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, const Grid &g, const NeighWork &w,
+                 const PairSubset *part, cudaStream_t st);
 void launch_virial(const DevState &d, const Coeffs &co, const PairFlags &pf, const Grid &g, const NeighWork &w, double *out6,
                    cudaStream_t st);
-// dynamic shared memory pair_tile_kernel needs for `cap` staged slots: `granules` x 16 B per record (5 hot, 6 when the
-// body reads rho_j) and 4 B per slot for the slot -> global index map of the instantiations that gather extras
-size_t pair_tile_smem(int cap, int granules, bool index_map);
+// dynamic shared memory pair_tile_kernel needs for `cap` staged slots: 96 B per record and 4 B per slot for the
+// slot -> global index map of the instantiations that gather extras (species, deviatoric tensors, rhoI, noise)
+size_t pair_tile_smem(int cap, bool index_map);
 
 // kernels_neigh.cu
 struct NeighWork {      // scratch owned by the context
@@ -228,6 +228,10 @@ void launch_fill_images(const DevState &d, const Box &b, double cutghost, const 
 void launch_bin_ghosts(const DevState &d, const Grid &g, const NeighWork &w, cudaStream_t st);
 void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const NeighWork &w, cudaStream_t st);
 bool tile_form_possible(const Grid &g);   // the halo of a tile fits the tile kernels' tables
+// owned atoms in the order of `tile_order` (a permutation of the tiles): aorder[p] = atom index; flags[5] = number of
+// atoms in the first `n_first` tiles.  cnt / off: scratch of ntiles + 1 ints each.
+void launch_atom_order(const Grid &g, const NeighWork &w, const int *tile_order, int ntiles, int n_first, int *cnt, int *off,
+                       int *aorder, cudaStream_t st);
 // tile form -> gather form (d.neigh, transposed 32-bit entries) for sphbvf_get_pairs and cross-checks
 void launch_expand_list(const DevState &d, const Grid &g, const NeighWork &w, cudaStream_t st);
 void launch_copy_xhold(const DevState &d, cudaStream_t st);
