@@ -378,13 +378,21 @@ int rebuild_finish(sphbvf_ctx *ctx) {
 }
 
 // Tiles in the order the overlapped pair pass wants them: first the tiles whose halo box holds no cell that can
-// contain a ghost (they can run while the per-step halo is still on the wire), then the ones along the brick faces.
-// A function of the cell grid only, so it is rebuilt when the grid changes, not at every rebuild.
+// contain a ghost (they can run while the per-step halo is still on the wire), then the ones along the brick faces
+// that have a neighbour.  A function of the cell grid and the halo plan only, so it is rebuilt when those change.
 int make_tile_order(sphbvf_ctx *ctx) {
   const Grid &g = ctx->grid;
   const long ntiles = (long)g.nt[0] * g.nt[1] * g.nt[2];
   static_assert(sizeof(int) == 4, "tile ids are 32-bit");
-  long key[10] = {g.nt[0], g.nt[1], g.nt[2], g.glo[0], g.glo[1], g.glo[2], g.ghi[0], g.ghi[1], g.ghi[2], g.n[0] + 4096L * (g.n[1] + 4096L * g.n[2])};
+  int peer[3][2];
+  long peermask = 0;
+  for (int k = 0; k < 3; k++)
+    for (int sd = 0; sd < 2; sd++) {
+      peer[k][sd] = comm_face_has_peer(ctx, k, sd);
+      peermask = 2 * peermask + peer[k][sd];
+    }
+  long key[11] = {g.nt[0], g.nt[1], g.nt[2], g.glo[0], g.glo[1], g.glo[2], g.ghi[0], g.ghi[1], g.ghi[2],
+                  g.n[0] + 4096L * (g.n[1] + 4096L * g.n[2]), peermask};
   if (ctx->tile_order && ntiles == ctx->ntiles_total && memcmp(key, ctx->tile_key, sizeof key) == 0) return 0;
   std::vector<int> inner, outer;
   inner.reserve(ntiles);
@@ -394,7 +402,8 @@ int make_tile_order(sphbvf_ctx *ctx) {
     for (int k = 0; k < g.dim; k++) {
       const int c0 = tc[k] << g.tb[k];
       const int h0 = std::max(c0 - g.s[k], 0), h1 = std::min(c0 + (1 << g.tb[k]) - 1 + g.s[k], g.n[k] - 1);
-      if (h0 < g.glo[k] || h1 > g.ghi[k]) ghost = true;
+      // cells below glo / above ghi may hold ghosts, if a neighbour brick (or this brick's own periodic image) sends any
+      if ((h0 < g.glo[k] && peer[k][0]) || (h1 > g.ghi[k] && peer[k][1])) ghost = true;
     }
     (ghost ? outer : inner).push_back((int)t);
   }
@@ -864,8 +873,11 @@ int sphbvf_pair_compute(sphbvf_ctx *ctx) {
     PairSubset in = {ctx->tile_order, nin, ctx->aorder, 0, ctx->natoms_interior};
     PairSubset out = {ctx->tile_order + nin, ntot - nin, ctx->aorder, ctx->natoms_interior, ctx->d.nlocal};
     launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->grid, ctx->w, &in, ctx->st);
+    // the face atoms run on the halo stream, right behind the unpack: they fill the tail of the interior launch instead
+    // of waiting for it; the compute stream then waits for both
+    launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->grid, ctx->w, &out, comm_halo_stream(ctx));
+    if ((rc = comm_halo_mark(ctx))) return rc;
     if ((rc = comm_halo_join(ctx))) return rc;
-    launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->grid, ctx->w, &out, ctx->st);
   } else {
     if ((rc = comm_halo_join(ctx))) return rc;
     launch_pair(ctx->d, ctx->co, pair_flags(ctx), ctx->grid, ctx->w, nullptr, ctx->st);

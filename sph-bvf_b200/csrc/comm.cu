@@ -88,6 +88,9 @@ int sphbvf_comm_plan(const sphbvf_config *cfg, int rank, int *peer, double *shif
 int comm_rebuild(sphbvf_ctx *ctx) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
 int comm_forward(sphbvf_ctx *ctx, int) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
 int comm_halo_join(sphbvf_ctx *) { return 0; }
+cudaStream_t comm_halo_stream(sphbvf_ctx *) { return nullptr; }
+int comm_halo_mark(sphbvf_ctx *) { return 0; }
+int comm_face_has_peer(const sphbvf_ctx *, int, int) { return 0; }
 int comm_vote(sphbvf_ctx *ctx, int *) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
 int comm_allreduce_max(sphbvf_ctx *ctx, int *, int) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }
 int comm_allreduce_max_double(sphbvf_ctx *ctx, double *) { return ctx->fail(SPHBVF_ECOMM, "library built without NCCL"); }

@@ -464,6 +464,20 @@ int comm_forward(sphbvf_ctx *ctx, int with_pd) {
   return 0;
 }
 
+// the stream the halo in flight runs on, and a way to extend what comm_halo_join waits for: the pair pass queues
+// the atoms along the brick faces behind the unpack on this stream, beside the interior's tail on the compute stream
+cudaStream_t comm_halo_stream(sphbvf_ctx *ctx) { return ctx->comm ? ctx->comm->halo_st : nullptr; }
+int comm_halo_mark(sphbvf_ctx *ctx) {
+  CK(cudaEventRecord(ctx->comm->ev_done, ctx->comm->halo_st));
+  return 0;
+}
+// can ghosts arrive through the face of this brick in dimension k (side 0: low, 1: high)?
+int comm_face_has_peer(const sphbvf_ctx *ctx, int k, int side) {
+  if (!ctx->comm) return 0;
+  static const int step[3] = {1, 3, 9};
+  return ctx->comm->recv.peer[13 + (side ? step[k] : -step[k])] >= 0;
+}
+
 // make the compute stream wait for a halo in flight (no host synchronisation)
 int comm_halo_join(sphbvf_ctx *ctx) {
   if (!ctx->halo_pending) return 0;

@@ -45,7 +45,7 @@ struct sphbvf_ctx {
   int aorder_cap = 0, aorder_valid = 0, natoms_interior = 0;
   int ntiles_interior = 0, ntiles_total = 0;
   long tile_order_cap = 0;
-  long tile_key[10] = {};
+  long tile_key[11] = {};
   int open_fam = -1;           // kernel family of the open tic()
   long launch_mark = 0;
   int random_set = 0;
@@ -83,6 +83,9 @@ int flush_final(sphbvf_ctx *ctx);        // launch a final_integrate that sphbvf
 int comm_rebuild(sphbvf_ctx *ctx);        // pbc + migration + sort + borders + list
 int comm_forward(sphbvf_ctx *ctx, int with_pd);   // per-step halo of the packed records (own stream when overlap_halo)
 int comm_halo_join(sphbvf_ctx *ctx);      // compute stream waits for a halo in flight
+cudaStream_t comm_halo_stream(sphbvf_ctx *ctx);
+int comm_halo_mark(sphbvf_ctx *ctx);      // comm_halo_join also waits for what was queued on the halo stream since
+int comm_face_has_peer(const sphbvf_ctx *ctx, int k, int side);   // ghosts can arrive through that face of the brick
 int comm_vote(sphbvf_ctx *ctx, int *flag); // rebuild vote: max over ranks
 int comm_allreduce_max(sphbvf_ctx *ctx, int *vals, int n);   // n <= 8
 int comm_allreduce_max_double(sphbvf_ctx *ctx, double *val);
