@@ -465,7 +465,7 @@ static int rebuild(sphbvf_ctx *ctx) {
 static PairFlags pair_flags(const sphbvf_ctx *ctx) {
   PairFlags pf;
   const int var = ctx->co.variant;
-  pf.filter_step = var == SPHBVF_FSI ? 0 : (ctx->ntimestep % 20) == 0;
+  pf.filter_step = shepard_filter_step(var, ctx->ntimestep);
   pf.with_dev = ctx->with_dev;
   pf.any_solid = ctx->any_solid;
   // density diffusion of the fsi pair style: amplDamp = 0.1 while ntimestep*dt <= dt*nsteps
@@ -477,6 +477,23 @@ static PairFlags pair_flags(const sphbvf_ctx *ctx) {
   pf.seed = ctx->seed;
   pf.ntimestep = ctx->ntimestep;
   return pf;
+}
+
+// any_solid / with_dev / e_nonzero select the pair-kernel instantiation and the halo record width.  They are derived
+// from the DEVICE state (a reduction over the owned atoms), so that fields changed through sphbvf_upload after
+// sphbvf_set_atoms count: set_atoms(e = NULL) followed by upload(E != 0) must switch the stochastic term on.
+static int derive_flags(sphbvf_ctx *ctx) {
+  int *out = ctx->w.flags + 5;   // flags[5..7]: scratch between rebuilds
+  CK(cudaMemsetAsync(out, 0, sizeof(int) * 3, ctx->st));
+  launch_derive_flags(ctx->d, ctx->co, out, ctx->st);
+  CKLAUNCH();
+  int rc;
+  if ((rc = fetch_flags(ctx))) return rc;
+  ctx->any_solid = ctx->h_flags[5];
+  ctx->with_dev = ctx->h_flags[6];
+  ctx->e_nonzero = ctx->h_flags[7];
+  ctx->flags_dirty = 0;
+  return 0;
 }
 
 template <typename T>
@@ -764,6 +781,7 @@ int sphbvf_setup(sphbvf_ctx *ctx) {
   // Identical whenever the initial momentum velocity of atoms near a periodic face is zero (all
   // shipped decks) or the run was preceded by a `run 0`.
   launch_setup_pre_force(ctx->d, ctx->cfg.integrate_groupbit, ctx->st);
+  if ((rc = derive_flags(ctx))) return rc;
   if (ctx->cfg.nranks > 1) {
     // kernel specialisation and halo record width must agree on every brick
     int v[3] = {ctx->any_solid, ctx->with_dev, ctx->e_nonzero};
@@ -785,6 +803,7 @@ int sphbvf_setup_neighbors(sphbvf_ctx *ctx) {
   cudaSetDevice(ctx->cfg.device);
   int rc;
   FLUSH();
+  if ((rc = derive_flags(ctx))) return rc;
   if (ctx->cfg.nranks > 1) {
     int v[3] = {ctx->any_solid, ctx->with_dev, ctx->e_nonzero};
     if ((rc = comm_allreduce_max(ctx, v, 3))) return rc;
@@ -832,6 +851,19 @@ int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt) {
   FLUSH();
   const int pack_valid = ctx->pack_valid;
   ctx->pack_valid = 0;
+  // e / dev / type / solid_tag were uploaded since the last step: the kernel specialisation follows the new state
+  // (all ranks agree), and new types or solid tags sit in the packed list entries, so the list is rebuilt now
+  // (multi-rank: such an upload is a collective act of the host code, every rank sees it in the same step)
+  int force_rebuild = 0;
+  if (ctx->flags_dirty) {
+    force_rebuild = (ctx->flags_dirty & 2) != 0;
+    if ((rc = derive_flags(ctx))) return rc;
+    if (ctx->cfg.nranks > 1) {
+      int v[3] = {ctx->any_solid, ctx->with_dev, ctx->e_nonzero};
+      if ((rc = comm_allreduce_max(ctx, v, 3))) return rc;
+      ctx->any_solid = v[0]; ctx->with_dev = v[1]; ctx->e_nonzero = v[2];
+    }
+  }
   // Neighbor::decide (neighbor.cpp:1922-1937)
   ctx->ago++;
   if (ctx->ago >= ctx->cfg.neigh_delay && ctx->ago % ctx->cfg.neigh_every == 0) {
@@ -845,6 +877,7 @@ int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt) {
       if (flag && ctx->ago == std::max(ctx->cfg.neigh_every, ctx->cfg.neigh_delay)) ctx->ndanger++;
     }
   }
+  if (force_rebuild) flag = 1;
   if (rebuilt) *rebuilt = flag;
   if (flag) return ctx->cfg.nranks > 1 ? comm_rebuild(ctx) : rebuild(ctx);
   // Comm::forward_comm (comm_brick.cpp:460-520): refresh the packed records of owned atoms and ghosts
@@ -1091,10 +1124,17 @@ int sphbvf_download_local(sphbvf_ctx *ctx, int field, void *host, int cap_rows) 
   return 0;
 }
 
+// fields that decide the kernel specialisation (and, for type / solid_tag, the packed list entries)
+static void note_upload(sphbvf_ctx *ctx, int field) {
+  if (field == SPHBVF_F_E || field == SPHBVF_F_DEV) ctx->flags_dirty |= 1;
+  if (field == SPHBVF_F_TYPE || field == SPHBVF_F_SOLID_TAG || field == SPHBVF_F_FIXED_TAG) ctx->flags_dirty |= 3;   // + rebuild
+}
+
 int sphbvf_upload_local(sphbvf_ctx *ctx, int field, const void *host, int nrows) {
   void *p;
   int nc, is_int;
   if (!field_info(ctx, field, &p, &nc, &is_int)) return ctx->fail(SPHBVF_EINVAL, "unknown field %d", field);
+  note_upload(ctx, field);
   const int n = ctx->d.nlocal;
   if (nrows != n) return ctx->fail(SPHBVF_EINVAL, "upload_local: %d rows given, %d atoms owned", nrows, n);
   if (!n || !nc) return 0;
@@ -1111,6 +1151,7 @@ int sphbvf_upload(sphbvf_ctx *ctx, int field, const void *host) {
   int nc, is_int, rc;
   if (!field_info(ctx, field, &p, &nc, &is_int)) return ctx->fail(SPHBVF_EINVAL, "unknown field %d", field);
   if (ctx->migrated) return ctx->fail(SPHBVF_ESTATE, "atoms migrated between ranks: upload by slot is undefined");
+  note_upload(ctx, field);
   FLUSH();
   ctx->pack_valid = 0;
   const int n = ctx->d.nlocal;

@@ -34,6 +34,7 @@ struct sphbvf_ctx {
   int fuse = 1, final_pending = 0, pack_valid = 0;
   double pend_dt = 0.0;
   long pend_step = 0;
+  int flags_dirty = 0;         // bit 0: e / dev uploaded, bit 1: type / solid_tag / fixed_tag uploaded since the flags were derived
   int pair_pref = 0;           // 0: gather form (default), 1: tile form when it fits (SPHBVF_PAIR=tile)
   int smem_optin = 0;          // cudaDevAttrMaxSharedMemoryPerBlockOptin of the device
   int expanded_valid = 0;      // d.neigh holds the expansion of the current tile-form list (sphbvf_get_pairs)

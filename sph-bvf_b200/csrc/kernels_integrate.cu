@@ -102,8 +102,7 @@ integrate_kernel(const DevState d, const __grid_constant__ Coeffs co, const Inte
   if (i >= d.nlocal) return;
   const size_t i3 = 3 * (size_t)i;
   constexpr bool FIN = MODE != 0, INI = MODE != 1;
-  // freqFilter 20 (TV :287, mechanics :311); fsi: 1e16 -> INT_MAX, never fires (..._fsi.cpp:304)
-  const bool filter = FIN && (VARIANT == SPHBVF_FSI ? (a.step_final % 2147483647L) == 0 : (a.step_final % 20) == 0);
+  const bool filter = FIN && shepard_filter_step(VARIANT, a.step_final);
   // one batch of loads, none of them behind a branch on loaded data (ldv/ldi are volatile: the compiler may
   // neither sink them into the branches that use them nor split the batch)
   const int mask = ldi(d.mask + i), type = ldi(d.type + i), solid = ldi(d.solid + i), fixed = ldi(d.fixed + i);
@@ -367,6 +366,23 @@ __global__ void max_vsq_kernel(const DevState d, const int groupbit, unsigned lo
 void launch_max_vsq(const DevState &d, int groupbit, unsigned long long *out, cudaStream_t st) {
   if (!d.nlocal) return;
   max_vsq_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, groupbit, out);
+  SPHBVF_LAUNCHED(1);
+}
+
+__global__ void derive_flags_kernel(const DevState d, const __grid_constant__ Coeffs co, int *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.nlocal) return;
+  const bool solid = d.solid[i] != 0;
+  bool dev = solid && co.G0[d.type[i]] != 0.0;
+  for (int k = 0; k < 9 && !dev; k++) dev = d.dev[9 * (size_t)i + k] != 0.0;
+  if (solid && !out[0]) out[0] = 1;
+  if (dev && !out[1]) out[1] = 1;
+  if (d.e[i] != 0.0 && !out[2]) out[2] = 1;
+}
+
+void launch_derive_flags(const DevState &d, const Coeffs &co, int *out, cudaStream_t st) {
+  if (!d.nlocal) return;
+  derive_flags_kernel<<<nblocks(d.nlocal, 256), 256, 0, st>>>(d, co, out);
   SPHBVF_LAUNCHED(1);
 }
 

@@ -98,6 +98,13 @@ struct Box {
   int dim;
 };
 
+// Shepard filter of the density (fix_...transport_velocity.cpp:287, ..._mechanics.cpp:311: every 20 steps; the fsi fix
+// has freqFilter = 1e16 -> INT_MAX, ..._fsi.cpp:304): ONE predicate for the integrator that consumes rhoAux1/2 and
+// for the pair pass that has to compute the numerator on exactly those steps
+__host__ __device__ __forceinline__ bool shepard_filter_step(int variant, long step) {
+  return variant == SPHBVF_FSI ? (step % 2147483647L) == 0 : (step % 20) == 0;
+}
+
 enum FixKind { FIX_BUOYANCY = 0, FIX_FORCING = 1, FIX_BUFFER = 2, FIX_SETFORCE = 3, FIX_CHEMRXN = 4 };
 struct FixDesc {
   int kind, groupbit;
@@ -163,6 +170,9 @@ void launch_final_integrate(const DevState &d, const Coeffs &co, double dt, long
 void launch_final_initial(const DevState &d, const Coeffs &co, double dt_final, long step_final, double dt_init,
                           long step_init, int groupbit, int do_pack, int with_dev, cudaStream_t st);
 void launch_max_vsq(const DevState &d, int groupbit, unsigned long long *out, cudaStream_t st);
+// out[0] = some atom has solid_tag, out[1] = some solid can carry deviatoric stress (G0 of its type != 0) or some
+// dev != 0, out[2] = some e != 0: what selects the pair-kernel instantiation.  out must be zeroed by the caller.
+void launch_derive_flags(const DevState &d, const Coeffs &co, int *out, cudaStream_t st);
 void launch_ke_tensor(const DevState &d, const Coeffs &co, int groupbit, double *scratch, double *out6, cudaStream_t st);
 void launch_fix(const DevState &d, const Coeffs &co, const FixDesc &fx, int hook, long ntimestep,
                 cudaStream_t st);   // hook: 0 post_integrate, 1 post_force, 2 end_of_step

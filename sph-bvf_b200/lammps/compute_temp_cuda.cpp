@@ -17,7 +17,7 @@ ComputeTempCuda::ComputeTempCuda(LAMMPS *lmp, int narg, char **arg) : ComputeTem
 bool ComputeTempCuda::device_sums(double *ke6)
 {
   SphbvfLmp *engine = SphbvfLmp::peek();
-  if (!engine || !engine->active() || engine->host_is_current()) return false;
+  if (!engine || !engine->active() || engine->host_has(SphbvfLmp::HF_V)) return false;
   engine->ke_tensor(groupbit, ke6);
   engine->count_device_thermo();
   return true;

@@ -121,7 +121,7 @@ void FixSsaTsdpdBvfCuda::setup_pre_force(int)
 void FixSsaTsdpdBvfCuda::setup(int)
 {
   engine->call(sphbvf_setup_post_force);
-  if (engine->output_needs_host(true)) engine->to_host();   // output of step 0 (Verlet::setup -> output->setup)
+  engine->fetch(engine->output_fields(true));   // output of step 0 (Verlet::setup -> output->setup)
 }
 
 /* ---------------------------------------------------------------------- */
@@ -146,7 +146,7 @@ void FixSsaTsdpdBvfCuda::final_integrate()
 void FixSsaTsdpdBvfCuda::end_of_step()
 {
   engine->call(sphbvf_end_of_step);
-  if (update->ntimestep == output->next && engine->output_needs_host()) engine->to_host();
+  if (update->ntimestep == output->next) engine->fetch(engine->output_fields());
 }
 
 void FixSsaTsdpdBvfCuda::post_run() { engine->stop(); }

@@ -8,6 +8,7 @@
 #include <string.h>
 #include <condition_variable>
 #include <mutex>
+#include <string>
 #include <thread>
 #include "sphbvf_lmp.h"
 #include "atom.h"
@@ -18,6 +19,8 @@
 #include "lammps.h"
 #include "memory.h"
 #include "compute.h"
+#include "dump.h"
+#include "dump_custom.h"
 #include "fix.h"
 #include "modify.h"
 #include "neighbor.h"
@@ -119,9 +122,10 @@ SphbvfLmp::SphbvfLmp(LAMMPS *lmp) : Pointers(lmp)
   integrate_groupbit = 1;
   nfixdesc = 0;
   ctx = NULL;
-  host_current = 1;
+  host_mask = HF_ALL;
   nlocal_uploaded = 0;
   ndownloads = ndevice_thermo = nskipped = 0;
+  nbytes_down = 0;
   nranks = 1;
   workers = NULL;
 }
@@ -378,7 +382,9 @@ void SphbvfLmp::start()
     });
   }
   nlocal_uploaded = n;
-  host_current = 0;
+  host_mask = 0;
+  ndownloads = ndevice_thermo = nskipped = 0;
+  nbytes_down = 0;
   // the host copy is stale from now on: LAMMPS must not reorder it behind the device's back
   atom->sortfreq = 0;
   if (nranks > 1 && comm->me == 0) {
@@ -391,44 +397,68 @@ void SphbvfLmp::start()
 
 /* ---------------------------------------------------------------------- */
 
-void SphbvfLmp::to_host()
+namespace {
+struct HostFieldDesc { unsigned bit; int id, ncols; };
+}
+
+/* the host array of one field (NULL: not owned by this atom style / variant / species count) */
+
+static double *host_array(Atom *atom, unsigned bit)
 {
-  if (!ctx || host_current) return;
+  switch (bit) {
+    case SphbvfLmp::HF_X: return &atom->x[0][0];
+    case SphbvfLmp::HF_V: return &atom->v[0][0];
+    case SphbvfLmp::HF_VEST: return &atom->vest[0][0];
+    case SphbvfLmp::HF_F: return &atom->f[0][0];
+    case SphbvfLmp::HF_RHO: return atom->rho;
+    case SphbvfLmp::HF_RHOI: return atom->rhoI;
+    case SphbvfLmp::HF_DRHO: return atom->drho;
+    case SphbvfLmp::HF_PHI: return atom->phi;
+    case SphbvfLmp::HF_ND: return atom->number_density;
+    case SphbvfLmp::HF_NW: return &atom->nw[0][0];
+    case SphbvfLmp::HF_DDV: return &atom->ddv[0][0];
+    case SphbvfLmp::HF_RAUX1: return atom->rhoAux1;
+    case SphbvfLmp::HF_RAUX2: return atom->rhoAux2;
+    case SphbvfLmp::HF_DEV: return &atom->deviatoricTensor[0][0][0];
+    case SphbvfLmp::HF_DDEV: return &atom->ddeviatoricTensor[0][0][0];
+    case SphbvfLmp::HF_DDX: return &atom->ddx[0][0];
+    case SphbvfLmp::HF_PNEW: return atom->Pnew;
+    case SphbvfLmp::HF_C: return &atom->C[0][0];
+    case SphbvfLmp::HF_Q: return &atom->Q[0][0];
+  }
+  return NULL;
+}
+
+void SphbvfLmp::fetch(unsigned want)
+{
+  if (!ctx) return;
   const int n = atom->nlocal, S = atom->num_sdpd_species;
+  // fields this run does not have: they count as current (nothing to copy)
+  unsigned absent = 0;
+  if (variant == SPHBVF_TV) absent |= HF_DDX | HF_PNEW;
+  if (!S) absent |= HF_C | HF_Q;
+  host_mask |= absent;
+  unsigned need = want & HF_ALL & ~host_mask;
+  if (!need) return;
   if (n != nlocal_uploaded) error->one(FLERR, "Atom count changed during a /cuda run");
-  if (nranks > 1) {
-    to_host_multi();
-    host_current = 1;
-    ndownloads++;
-    return;
-  }
   if (n) {
-    check(sphbvf_download(ctx, SPHBVF_F_X, &atom->x[0][0]));
-    check(sphbvf_download(ctx, SPHBVF_F_V, &atom->v[0][0]));
-    check(sphbvf_download(ctx, SPHBVF_F_VEST, &atom->vest[0][0]));
-    check(sphbvf_download(ctx, SPHBVF_F_F, &atom->f[0][0]));
-    check(sphbvf_download(ctx, SPHBVF_F_RHO, atom->rho));
-    check(sphbvf_download(ctx, SPHBVF_F_RHOI, atom->rhoI));
-    check(sphbvf_download(ctx, SPHBVF_F_DRHO, atom->drho));
-    check(sphbvf_download(ctx, SPHBVF_F_PHI, atom->phi));
-    check(sphbvf_download(ctx, SPHBVF_F_NUMBER_DENSITY, atom->number_density));
-    check(sphbvf_download(ctx, SPHBVF_F_NW, &atom->nw[0][0]));
-    check(sphbvf_download(ctx, SPHBVF_F_DDV, &atom->ddv[0][0]));
-    check(sphbvf_download(ctx, SPHBVF_F_RHOAUX1, atom->rhoAux1));
-    check(sphbvf_download(ctx, SPHBVF_F_RHOAUX2, atom->rhoAux2));
-    check(sphbvf_download(ctx, SPHBVF_F_DEV, &atom->deviatoricTensor[0][0][0]));
-    check(sphbvf_download(ctx, SPHBVF_F_DDEV, &atom->ddeviatoricTensor[0][0][0]));
-    if (variant != SPHBVF_TV) {
-      check(sphbvf_download(ctx, SPHBVF_F_DDX, &atom->ddx[0][0]));
-      check(sphbvf_download(ctx, SPHBVF_F_PNEW, atom->Pnew));
-    }
-    if (S) {
-      check(sphbvf_download(ctx, SPHBVF_F_C, &atom->C[0][0]));
-      check(sphbvf_download(ctx, SPHBVF_F_Q, &atom->Q[0][0]));
+    if (nranks > 1) fetch_multi(need);
+    else {
+      static const HostFieldDesc tab[] = {
+        {HF_X, SPHBVF_F_X, 3}, {HF_V, SPHBVF_F_V, 3}, {HF_VEST, SPHBVF_F_VEST, 3}, {HF_F, SPHBVF_F_F, 3}, {HF_RHO, SPHBVF_F_RHO, 1},
+        {HF_RHOI, SPHBVF_F_RHOI, 1}, {HF_DRHO, SPHBVF_F_DRHO, 1}, {HF_PHI, SPHBVF_F_PHI, 1}, {HF_ND, SPHBVF_F_NUMBER_DENSITY, 1},
+        {HF_NW, SPHBVF_F_NW, 3}, {HF_DDV, SPHBVF_F_DDV, 3}, {HF_RAUX1, SPHBVF_F_RHOAUX1, 1}, {HF_RAUX2, SPHBVF_F_RHOAUX2, 1},
+        {HF_DEV, SPHBVF_F_DEV, 9}, {HF_DDEV, SPHBVF_F_DDEV, 9}, {HF_DDX, SPHBVF_F_DDX, 3}, {HF_PNEW, SPHBVF_F_PNEW, 1},
+        {HF_C, SPHBVF_F_C, -1}, {HF_Q, SPHBVF_F_Q, -1}};
+      for (size_t q = 0; q < sizeof tab / sizeof tab[0]; q++) {
+        if (!(need & tab[q].bit)) continue;
+        check(sphbvf_download(ctx, tab[q].id, host_array(atom, tab[q].bit)));
+        nbytes_down += (bigint)8 * n * (tab[q].ncols < 0 ? S : tab[q].ncols);
+      }
     }
   }
-  host_current = 1;
-  ndownloads++;
+  host_mask |= need;
+  if (need == (HF_ALL & ~absent) || want == HF_ALL) ndownloads++;
 }
 
 /* ----------------------------------------------------------------------
@@ -436,34 +466,19 @@ void SphbvfLmp::to_host()
    with their tags and the rows are scattered into the host arrays by tag
 ------------------------------------------------------------------------- */
 
-void SphbvfLmp::to_host_multi()
+void SphbvfLmp::fetch_multi(unsigned need)
 {
   const int S = atom->num_sdpd_species;
   struct Field { int id, ncols; double *host; };
+  static const HostFieldDesc tab[] = {
+    {HF_X, SPHBVF_F_X, 3}, {HF_V, SPHBVF_F_V, 3}, {HF_VEST, SPHBVF_F_VEST, 3}, {HF_F, SPHBVF_F_F, 3}, {HF_RHO, SPHBVF_F_RHO, 1},
+    {HF_RHOI, SPHBVF_F_RHOI, 1}, {HF_DRHO, SPHBVF_F_DRHO, 1}, {HF_PHI, SPHBVF_F_PHI, 1}, {HF_ND, SPHBVF_F_NUMBER_DENSITY, 1},
+    {HF_NW, SPHBVF_F_NW, 3}, {HF_DDV, SPHBVF_F_DDV, 3}, {HF_RAUX1, SPHBVF_F_RHOAUX1, 1}, {HF_RAUX2, SPHBVF_F_RHOAUX2, 1},
+    {HF_DEV, SPHBVF_F_DEV, 9}, {HF_DDEV, SPHBVF_F_DDEV, 9}, {HF_DDX, SPHBVF_F_DDX, 3}, {HF_PNEW, SPHBVF_F_PNEW, 1},
+    {HF_C, SPHBVF_F_C, -1}, {HF_Q, SPHBVF_F_Q, -1}};
   std::vector<Field> fields;
-  fields.push_back({SPHBVF_F_X, 3, &atom->x[0][0]});
-  fields.push_back({SPHBVF_F_V, 3, &atom->v[0][0]});
-  fields.push_back({SPHBVF_F_VEST, 3, &atom->vest[0][0]});
-  fields.push_back({SPHBVF_F_F, 3, &atom->f[0][0]});
-  fields.push_back({SPHBVF_F_RHO, 1, atom->rho});
-  fields.push_back({SPHBVF_F_RHOI, 1, atom->rhoI});
-  fields.push_back({SPHBVF_F_DRHO, 1, atom->drho});
-  fields.push_back({SPHBVF_F_PHI, 1, atom->phi});
-  fields.push_back({SPHBVF_F_NUMBER_DENSITY, 1, atom->number_density});
-  fields.push_back({SPHBVF_F_NW, 3, &atom->nw[0][0]});
-  fields.push_back({SPHBVF_F_DDV, 3, &atom->ddv[0][0]});
-  fields.push_back({SPHBVF_F_RHOAUX1, 1, atom->rhoAux1});
-  fields.push_back({SPHBVF_F_RHOAUX2, 1, atom->rhoAux2});
-  fields.push_back({SPHBVF_F_DEV, 9, &atom->deviatoricTensor[0][0][0]});
-  fields.push_back({SPHBVF_F_DDEV, 9, &atom->ddeviatoricTensor[0][0][0]});
-  if (variant != SPHBVF_TV) {
-    fields.push_back({SPHBVF_F_DDX, 3, &atom->ddx[0][0]});
-    fields.push_back({SPHBVF_F_PNEW, 1, atom->Pnew});
-  }
-  if (S) {
-    fields.push_back({SPHBVF_F_C, S, &atom->C[0][0]});
-    fields.push_back({SPHBVF_F_Q, S, &atom->Q[0][0]});
-  }
+  for (size_t q = 0; q < sizeof tab / sizeof tab[0]; q++)
+    if (need & tab[q].bit) fields.push_back({tab[q].id, tab[q].ncols < 0 ? S : tab[q].ncols, host_array(atom, tab[q].bit)});
   std::vector<int> count(nranks, 0);
   all([&](sphbvf_ctx *c, int r) {
     // each rank scatters its own rows: distinct tags, so the writes of different ranks never overlap
@@ -489,43 +504,92 @@ void SphbvfLmp::to_host_multi()
   bigint tot = 0;
   for (int r = 0; r < nranks; r++) tot += count[r];
   if (tot != atom->nlocal) error->one(FLERR, "Atoms lost or duplicated between the GPUs of a /cuda run");
+  for (size_t q = 0; q < fields.size(); q++) nbytes_down += (bigint)8 * atom->nlocal * fields[q].ncols;
 }
 
 /* ----------------------------------------------------------------------
-   Does anything that fires on this output step read the host per-atom arrays?  Conservative: the download is
-   skipped only when (a) no dump and no restart is due now, (b) thermo has one of the fixed keyword sets
-   (style one / multi: step temp epair emol etotal press ..., all fed by temp, pe and pressure computes;
-   `custom` may reference variables and arbitrary computes, which cannot be inspected from here), (c) every
-   compute LAMMPS knows is temp/cuda, pressure or pe, or a per-atom / local compute (only dumps, fixes and
-   variables invoke those), and (d) every fix is one of the /cuda fixes (none of them reads host arrays).
-   SPHBVF_OUTPUT=full restores the unconditional download.
+   Which host per-atom arrays can anything that fires on this output step read?  Conservative:
+   (a) a restart due now, a thermo style other than one / multi (`custom` may reference variables and arbitrary
+       computes, which cannot be inspected from here), a global compute other than temp/cuda, pressure, pe, or a
+       fix that is not one of the /cuda fixes -> everything;
+   (b) every dump that is due now contributes the columns it writes: dump custom / cfg-less styles are parsed
+       keyword by keyword (id type mass: static data; x y z xs .. : positions; vx .. : velocities; fx .. : forces;
+       c_ID: a /cuda per-atom compute fetches its own field when the dump invokes it, static per-atom computes
+       such as ssa_tsdpd/solid_tag/atom need nothing, any other compute -> everything; v_ f_ d_ i_ -> everything);
+       dump atom / xyz read positions; any other dump style -> everything;
+   (c) otherwise nothing: the thermo line is served from the device reductions.
+   SPHBVF_OUTPUT=full restores the unconditional full download.
 ------------------------------------------------------------------------- */
 
-bool SphbvfLmp::output_needs_host(bool at_setup)
+namespace {
+// legal access to two protected members of DumpCustom: &Peek::member has type `T DumpCustom::*`
+struct DumpCustomPeek : public DumpCustom {
+  static char *DumpCustom::*columns_ptr() { return &DumpCustomPeek::columns; }
+  static int DumpCustom::*nthresh_ptr() { return &DumpCustomPeek::nthresh; }
+};
+}
+
+unsigned SphbvfLmp::output_fields(bool at_setup)
 {
   static const int force_full = [] { const char *e = getenv("SPHBVF_OUTPUT"); return e && strcmp(e, "full") == 0; }();
-  if (force_full) return true;
+  if (force_full) return HF_ALL;
   const bigint now = update->ntimestep;
-  // Fix::setup runs before Output::setup has scheduled this run's dumps: any dump may fire at the first step
-  if (at_setup && (output->ndump || output->restart_flag)) return true;
-  if (output->ndump && output->next_dump_any == now) return true;
-  if (output->restart_flag && output->next_restart == now) return true;
-  if (!output->thermo) return true;
+  if (output->restart_flag && (at_setup || output->next_restart == now)) return HF_ALL;
+  if (!output->thermo) return HF_ALL;
   const char *ts = output->thermo->style;
-  if (strcmp(ts, "one") != 0 && strcmp(ts, "multi") != 0) return true;
+  if (strcmp(ts, "one") != 0 && strcmp(ts, "multi") != 0) return HF_ALL;
   for (int i = 0; i < modify->ncompute; i++) {
     Compute *c = modify->compute[i];
     if (c->peratom_flag || c->local_flag) continue;
     if (strcmp(c->style, "temp/cuda") == 0 || strcmp(c->style, "pressure") == 0 || strcmp(c->style, "pe") == 0) continue;
-    return true;
+    return HF_ALL;
   }
   for (int i = 0; i < modify->nfix; i++) {
     const char *fs = modify->fix[i]->style;
     const size_t n = strlen(fs);
-    if (n < 5 || strcmp(fs + n - 5, "/cuda") != 0) return true;
+    if (n < 5 || strcmp(fs + n - 5, "/cuda") != 0) return HF_ALL;
   }
-  nskipped++;
-  return false;
+  unsigned mask = 0;
+  for (int i = 0; i < output->ndump; i++) {
+    // Fix::setup runs before Output::setup has scheduled this run's dumps: any dump may fire at the first step
+    if (!at_setup && output->next_dump[i] != now) continue;
+    Dump *dp = output->dump[i];
+    if (strcmp(dp->style, "atom") == 0 || strcmp(dp->style, "xyz") == 0) { mask |= HF_X; continue; }
+    if (strcmp(dp->style, "custom") != 0) return HF_ALL;
+    DumpCustom *dc = (DumpCustom *)dp;
+    if (dc->*DumpCustomPeek::nthresh_ptr() > 0) return HF_ALL;
+    const char *cols = dc->*DumpCustomPeek::columns_ptr();
+    if (!cols) return HF_ALL;
+    std::string all(cols);
+    size_t pos = 0;
+    while (pos < all.size()) {
+      size_t e = all.find(' ', pos);
+      if (e == std::string::npos) e = all.size();
+      const std::string w = all.substr(pos, e - pos);
+      pos = e + 1;
+      if (w.empty()) continue;
+      if (w == "id" || w == "type" || w == "mass" || w == "mol" || w == "proc" || w == "procp1" || w == "element") continue;
+      if (w == "x" || w == "y" || w == "z" || w == "xs" || w == "ys" || w == "zs" || w == "xu" || w == "yu" || w == "zu" ||
+          w == "xsu" || w == "ysu" || w == "zsu" || w == "ix" || w == "iy" || w == "iz") { mask |= HF_X; continue; }
+      if (w == "vx" || w == "vy" || w == "vz") { mask |= HF_V; continue; }
+      if (w == "fx" || w == "fy" || w == "fz") { mask |= HF_F; continue; }
+      if (w.compare(0, 2, "c_") == 0) {
+        std::string id = w.substr(2);
+        const size_t br = id.find('[');
+        if (br != std::string::npos) id = id.substr(0, br);
+        const int ic = modify->find_compute(id.c_str());
+        if (ic < 0) return HF_ALL;
+        const char *cs = modify->compute[ic]->style;
+        const size_t n = strlen(cs);
+        if (n >= 5 && strcmp(cs + n - 5, "/cuda") == 0) continue;              // fetches its own field
+        if (strcmp(cs, "ssa_tsdpd/solid_tag/atom") == 0) continue;               // static per-atom data
+        return HF_ALL;
+      }
+      return HF_ALL;   // v_ f_ d_ i_ q mux ... : cannot be inspected
+    }
+  }
+  if (!mask) nskipped++;
+  return mask;
 }
 
 void SphbvfLmp::stop()
@@ -534,7 +598,8 @@ void SphbvfLmp::stop()
   if (getenv("SPHBVF_VERBOSE") && comm->me == 0) {
     char msg[256];
     snprintf(msg, sizeof msg, "sphbvf: " BIGINT_FORMAT " full downloads, " BIGINT_FORMAT " output steps served from the device, "
-             BIGINT_FORMAT " device kinetic-energy reductions\n", ndownloads, nskipped, ndevice_thermo);
+             BIGINT_FORMAT " device kinetic-energy reductions, " BIGINT_FORMAT " bytes device->host before the final sync\n",
+             ndownloads, nskipped, ndevice_thermo, nbytes_down);
     if (screen) fputs(msg, screen);
     if (logfile) fputs(msg, logfile);
   }

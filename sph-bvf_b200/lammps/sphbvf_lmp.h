@@ -62,21 +62,35 @@ class SphbvfLmp : protected Pointers {
   void virial(double *v6);                    // summed over the ranks
   void ke_tensor(int groupbit, double *t6);   // summed over the ranks
   double max_vsq(int groupbit);
-  void to_host();               // device -> class Atom arrays (all fields the package owns)
-  void mark_dirty() { host_current = 0; }
-  bool host_is_current() const { return host_current != 0; }
-  // output step: true if nothing scheduled now can read the host per-atom arrays (thermo of style one / multi
-  // fed by compute temp/cuda + the device virial, no dump, no restart, only /cuda fixes) -> no download
-  bool output_needs_host(bool at_setup = false);
+  // ---- host mirrors.  The device owns the state during a run; a host array of class Atom is refreshed only when
+  // something is about to read it.  Fields are tracked one by one (HF_* bits), so a dump step copies the columns
+  // the dump writes and nothing else.
+  enum HostField {
+    HF_X = 1 << 0, HF_V = 1 << 1, HF_VEST = 1 << 2, HF_F = 1 << 3, HF_RHO = 1 << 4, HF_RHOI = 1 << 5, HF_DRHO = 1 << 6,
+    HF_PHI = 1 << 7, HF_ND = 1 << 8, HF_NW = 1 << 9, HF_DDV = 1 << 10, HF_RAUX1 = 1 << 11, HF_RAUX2 = 1 << 12,
+    HF_DEV = 1 << 13, HF_DDEV = 1 << 14, HF_DDX = 1 << 15, HF_PNEW = 1 << 16, HF_C = 1 << 17, HF_Q = 1 << 18,
+    HF_ALL = (1 << 19) - 1
+  };
+  void fetch(unsigned mask);    // device -> class Atom arrays for the fields of `mask` that are not current yet
+  void to_host() { fetch(HF_ALL); }   // every field the package owns
+  void mark_dirty() { host_mask = 0; }
+  bool host_is_current() const { return (host_mask & HF_ALL) == HF_ALL; }
+  bool host_has(unsigned mask) const { return (host_mask & mask) == mask; }
+  // output step: the fields anything scheduled now may read from the host arrays.  0 when thermo of style one /
+  // multi is fed by compute temp/cuda + the device virial and no dump or restart is due; the columns of the dumps
+  // that are due (dump custom / atom / xyz; /cuda per-atom computes fetch their own field) otherwise; HF_ALL when
+  // something that cannot be inspected is involved (stock fixes, variables, other dump styles, restarts ...)
+  unsigned output_fields(bool at_setup = false);
+  bigint nbytes_down;           // bytes copied device -> host so far in this run (SPHBVF_VERBOSE)
   void count_device_thermo() { ndevice_thermo++; }
   sphbvf_ctx *ctx;
 
  private:
-  int host_current;
+  unsigned host_mask;           // HF_* bits of the fields that are current on the host
   int nlocal_uploaded;
   class SphbvfWorkers *workers;
   std::vector<int> tag2idx;   // atom tag -> row of the host arrays (multi-GPU: atoms migrate between ranks)
-  void to_host_multi();
+  void fetch_multi(unsigned mask);
   bigint ndownloads, ndevice_thermo, nskipped;   // statistics printed at the end of a run (SPHBVF_VERBOSE)
 };
 

@@ -102,3 +102,58 @@ def test_neighbour_capacity_grows_transparently():
     a, b = eng.get("number_density"), orc.get("number_density")
     assert np.abs(a - b).max() <= 1e-10 * np.abs(b).max()
     eng.close()
+
+
+def test_uploaded_e_and_type_reach_the_kernel_selection():
+    """set_atoms(e = 0) followed by upload(e != 0) must switch the stochastic term on (the flags that select the pair
+    kernel come from the device state, not from what set_atoms saw), and an uploaded type change must reach the
+    packed neighbour-list entries (forced rebuild): both runs must equal a run that was given the data up front."""
+    from common import feed_atoms, load_fixture
+    pkg = load_package()
+    meta, z = load_fixture("mixedh2d_n30")
+    n = meta["natoms"]
+    e_new = np.full(n, 1e-6)
+    type_new = z["init_type"].copy()
+    type_new[::7] = 1 + (type_new[::7] % meta["ntypes"])
+
+    def arrays(e, typ):
+        return (z["init_tag"], typ, z["init_mask"], z["init_solid_tag"], z["init_fixed_tag"], z["init_x"], z["init_v"],
+                z["init_rho"], e, z["init_C"], z["init_dev"])
+
+    ref = pkg.Engine(meta)
+    ref.set_atoms(*arrays(e_new, type_new))
+    ref.set_random(1.380649e-23, 7)
+    ref.set_run_length(6)
+    ref.setup()
+    ref.run(6)
+    got = pkg.Engine(meta)
+    got.set_atoms(*arrays(np.zeros(n), z["init_type"]))
+    got.set_random(1.380649e-23, 7)
+    got.put("e", e_new)
+    got.put("type", type_new)
+    got.set_run_length(6)
+    got.setup()
+    got.run(6)
+    for f in ("x", "v", "f", "rho"):
+        assert np.array_equal(ref.get(f), got.get(f)), f
+    # after setup: upload during the run, the next step re-derives the flags and rebuilds
+    late = pkg.Engine(meta)
+    late.set_atoms(*arrays(np.zeros(n), z["init_type"]))
+    late.set_random(1.380649e-23, 7)
+    late.set_run_length(6)
+    late.setup()
+    nb0 = late.nbuilds
+    late.put("e", e_new)
+    late.put("type", type_new)
+    late.run(1)
+    assert late.nbuilds == nb0 + 1
+    f_late = late.get("f")
+    chk = pkg.Engine(meta)
+    chk.set_atoms(*arrays(np.zeros(n), z["init_type"]))
+    chk.set_random(1.380649e-23, 7)
+    chk.set_run_length(6)
+    chk.setup()
+    chk.run(1)
+    assert not np.array_equal(f_late, chk.get("f")), "the uploaded e / type had no effect"
+    for e in (ref, got, late, chk):
+        e.close()

@@ -23,4 +23,5 @@ def test_bricks_match_reference(nranks):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks),
            "--master-addr", "127.0.0.1", "--master-port", str(29610 + nranks), os.path.join(HERE, "mgpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    print("\n".join(l for l in out.stdout.splitlines() if l.startswith("mgpu ")))   # kept in the committed logs (pytest -s)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
