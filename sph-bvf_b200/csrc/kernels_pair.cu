@@ -483,22 +483,11 @@ __device__ __forceinline__ void cp_async4(int *smem_dst, const int *gsrc) {
 // per-atom output is written; for every neighbour that is a periodic image (shift s != 0) the force
 // F it exerts on atom i is obtained as the change of the force accumulator and -1/2 s (x) F is summed
 // into virial_out[6] (see sphbvf_virial in capi.cu for the derivation).
-template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL = false>
-__global__ void __launch_bounds__(PAIR_T, PAIR_MINB)
-pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
-            const PairConsts pc, const int *__restrict__ aorder, const int a0, const int a1, double *virial_out = nullptr) {
-  __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
-  __shared__ int ring[RING][PAIR_T];
-  if (!UNIFORM) {
-    for (int q = threadIdx.x; q < MAXT * MAXT; q += blockDim.x) srow[q] = tb.row[q];
-    __syncthreads();
-  }
-  // atoms [a0, a1) of the launch, through the atom order when the pass is split (interior of the brick while the
-  // halo is in flight, then the atoms that can see a ghost): consecutive positions stay consecutive atoms of a tile
-  const int p = a0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= a1) return;
-  const int i = aorder ? aorder[p] : p;
-
+// one owned atom of the gather form: the whole neighbour loop and the stores (myring = this thread's column of the
+// CTA's list-entry ring)
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL>
+__device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, const PairTables &tb, const PairConsts &pc,
+                                          const PairRow *srow, int *myring, const int i, double *virial_out) {
   PairAcc<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM> acc;
   acc.init(d, co, tb, srow, i, d.pflags[i], d.prec[i].A, d.prec[i].B, d.prec[i].C);
 
@@ -532,7 +521,6 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   const int nn = d.numneigh[i];
   const int *np = d.neigh + i;
   const size_t stride = d.stride;
-  int *myring = &ring[0][threadIdx.x];
   auto fetch2 = [&](int k) {   // entries k, k+1 -> ring slots k % RING, (k+1) % RING; one group
     if (k < nn) cp_async4(myring + (k % RING) * PAIR_T, np + (size_t)k * stride);
     if (k + 1 < nn) cp_async4(myring + ((k + 1) % RING) * PAIR_T, np + (size_t)(k + 1) * stride);
@@ -609,6 +597,68 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     for (int k = 0; k < 9; k++) d.ddev[9 * (size_t)i + k] = acc.si ? acc.ddev[k] : 0.0;
   if (SPECIES)
     for (int k = 0; k < co.nspecies; k++) d.Q[(size_t)i * co.nspecies + k] = acc.Qs[k];
+}
+
+// Gather-form kernel.  Two schedules of the chunks of PAIR_T consecutive atoms:
+//   queues == nullptr (default): one CTA per chunk (chunk = blockIdx.x), the hardware hands CTAs to SMs as they free up, so the
+//     CTAs that share an SM work on unrelated parts of the brick and every CTA starts on a cold L1;
+//   queues != nullptr (SPHBVF_PAIR_SCHED=smid): PERSISTENT CTAs, two per SM, that pull chunks from a queue chosen by the SM they run
+//     on (%smid): SM s owns the chunks [s cpq, (s + 1) cpq) -- a contiguous run of tiles -- and its two CTAs take them
+//     in order, so consecutive and concurrent chunks of an SM are neighbouring tiles whose candidate records (half
+//     of them shared) are already in that SM's L1; the last tenth of the chunks sits in one shared queue that
+//     evens out the tail.  The 16 % of record gathers that missed L1 (first touch of a line by an SM) put an L2
+//     round trip on nearly every warp-visit: this is the cheapest way to make fewer of them.  MEASURED (8 M atoms,
+//     gpurun_out/r2g_*): L1 sector hit rate 84 -> 89 %, L1 data pipe 80 -> 71 %, but 6.08 instead of 5.66 ms -- the
+//     launch loses the hardware's dynamic balance (296 CTAs whose chunk costs differ by the wall / bulk mix) and pays a
+//     block-wide barrier pair plus an atomic round trip per chunk; kept as a switch, not the default.
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL = false>
+__global__ void __launch_bounds__(PAIR_T, PAIR_MINB)
+pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
+            const PairConsts pc, const int *__restrict__ aorder, const int a0, const int a1, int *queues, const int nq,
+            const int cpq, double *virial_out = nullptr) {
+  __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
+  __shared__ int ring[RING][PAIR_T];
+  __shared__ int s_chunk;
+  if (!UNIFORM) {
+    for (int q = threadIdx.x; q < MAXT * MAXT; q += blockDim.x) srow[q] = tb.row[q];
+    __syncthreads();
+  }
+  int *myring = &ring[0][threadIdx.x];
+  // atoms [a0, a1) of the launch, through the atom order when the pass is split (interior of the brick while the
+  // halo is in flight, then the atoms that can see a ghost): consecutive positions stay consecutive atoms of a tile
+  if (!queues) {
+    const int p = a0 + blockIdx.x * PAIR_T + threadIdx.x;
+    if (p < a1) pair_atom<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL>(d, co, tb, pc, srow, myring, aorder ? aorder[p] : p, virial_out);
+    return;
+  }
+  const int nchunks = (a1 - a0 + PAIR_T - 1) / PAIR_T;
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  const int q = (int)(smid % (unsigned)nq);
+  for (;;) {
+    __syncthreads();   // s_chunk of the previous round has been read by everyone
+    if (threadIdx.x == 0) {
+      // own queue, then the shared tail, then whatever another SM's queue still holds (%smid values need not cover
+      // 0 .. nq-1: a queue no SM maps to is emptied this way)
+      int chunk = nchunks;
+      const int ntail = nchunks - nq * cpq;
+      int c = queues[q] < cpq ? atomicAdd(&queues[q], 1) : cpq;
+      if (c < cpq) chunk = q * cpq + c;
+      else if (queues[nq] < ntail && (c = atomicAdd(&queues[nq], 1)) < ntail) chunk = nq * cpq + c;
+      else
+        for (int k = 1; k < nq; k++) {
+          const int qq = (q + k) % nq;
+          if (queues[qq] < cpq && (c = atomicAdd(&queues[qq], 1)) < cpq) { chunk = qq * cpq + c; break; }
+        }
+      s_chunk = chunk;
+    }
+    __syncthreads();
+    const int chunk = s_chunk;
+    if (chunk >= nchunks) break;
+    const int p = a0 + chunk * PAIR_T + threadIdx.x;
+    if (p < a1) pair_atom<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL>(d, co, tb, pc, srow, myring, aorder ? aorder[p] : p, virial_out);
+    asm volatile("cp.async.wait_all;" ::: "memory");   // the ring is reused by the next chunk
+  }
 }
 
 // ==========================================================================================
@@ -839,6 +889,8 @@ struct TileArgs {
   int ntiles;
   const int *aorder;      // gather form: positions [a0, a1) of this atom order (nullptr: atoms a0 .. a1)
   int a0, a1;
+  int *queues;            // gather form: per-SM chunk queues of the persistent schedule (nullptr: one CTA per chunk)
+  int nq;
 };
 
 template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL>
@@ -861,8 +913,17 @@ static void launch_one(const DevState &d, const Coeffs &co, const PairTables &tb
     kern<<<ta.ntiles, PT_T, smem, st>>>(d, *ta.g, co, tb, ta.w->cell_start, ta.w->gcell_start, ta.w->gorder, ta.tile_list, pc, vout);
   } else {
     if (ta.a1 <= ta.a0) return;
-    const int blocks = (ta.a1 - ta.a0 + PAIR_T - 1) / PAIR_T;
-    pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<blocks, PAIR_T, 0, st>>>(d, co, tb, pc, ta.aorder, ta.a0, ta.a1, vout);
+    const int nchunks = (ta.a1 - ta.a0 + PAIR_T - 1) / PAIR_T;
+    if (ta.queues && nchunks > 4 * ta.nq) {
+      // persistent schedule: 9/10 of the chunks in per-SM queues (contiguous runs of tiles), the rest in a shared one
+      const int cpq = (int)(0.9 * nchunks / ta.nq);
+      cudaMemsetAsync(ta.queues, 0, sizeof(int) * (ta.nq + 1), st);
+      pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<PAIR_MINB * ta.nq, PAIR_T, 0, st>>>(
+          d, co, tb, pc, ta.aorder, ta.a0, ta.a1, ta.queues, ta.nq, cpq, vout);
+    } else {
+      pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<nchunks, PAIR_T, 0, st>>>(
+          d, co, tb, pc, ta.aorder, ta.a0, ta.a1, nullptr, 1, 0, vout);
+    }
   }
   SPHBVF_LAUNCHED(1);
 }
@@ -943,7 +1004,7 @@ static PairConsts consts_of(const PairFlags &pf) {
 
 // Pair::virial_fdotr_compute for the gather formulation; out[6] must be zeroed by the caller
 static TileArgs all_atoms(const DevState &d, const Grid &g, const NeighWork &w) {
-  TileArgs ta = {&g, &w, nullptr, (int)((long)g.nt[0] * g.nt[1] * g.nt[2]), nullptr, 0, d.nlocal};
+  TileArgs ta = {&g, &w, nullptr, (int)((long)g.nt[0] * g.nt[1] * g.nt[2]), nullptr, 0, d.nlocal, nullptr, 1};
   return ta;
 }
 
@@ -979,6 +1040,7 @@ void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, const
   if (part) {
     ta.tile_list = part->tile_list; ta.ntiles = part->ntiles;
     ta.aorder = part->aorder; ta.a0 = part->a0; ta.a1 = part->a1;
+    ta.queues = part->queues; ta.nq = part->nq;
   }
 #ifdef SPHBVF_HOT_ONLY   // tuning builds (tools/build_variant.sh): only the benchmark's instantiations, seconds to compile
   (void)uniform;

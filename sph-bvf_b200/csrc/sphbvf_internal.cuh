@@ -201,6 +201,8 @@ struct PairSubset {
   int ntiles;
   const int *aorder;
   int a0, a1;
+  int *queues;   // gather form: nq + 1 chunk counters of the persistent, SM-local schedule (nullptr: one CTA per chunk)
+  int nq;
 };
 void launch_pair(const DevState &d, const Coeffs &co, const PairFlags &pf, const Grid &g, const NeighWork &w,
                  const PairSubset *part, cudaStream_t st);
