@@ -14,6 +14,7 @@
 // evaluated without FMA contraction in the reference's operation order, so the lists compare
 // bit-exactly as sorted tag pairs.
 #include <stdlib.h>
+#include <string.h>
 
 #include "sphbvf_internal.cuh"
 #include "tile_common.cuh"
@@ -461,6 +462,242 @@ build_list_tile_kernel(const DevState d, const __grid_constant__ Grid g, const _
   }
 }
 
+// (A') build_list_tile32_kernel (default since round 2): same tile geometry, candidate enumeration and output as (A),
+//     but the lock-step sweep CLASSIFIES in FP32 and only the candidates the classification cannot decide see FP64:
+//       * positions relative to the centre of the tile's halo box are rounded to float (p); a candidate is staged as
+//         {-2 p.x, -2 p.y, -2 p.z, |p|^2} (16 B, ONE broadcast LDS.128) and atom i keeps p_i and c_i = |p_i|^2 - cut, so
+//         t = r^2 - cut = fma(p_i.x, s.x, fma(p_i.y, s.y, fma(p_i.z, s.z, s.w))) + c_i costs 3 FFMA + 1 FADD (the
+//         all-FP64 sweep: 8 FP64 instructions at a quarter of the issue rate); the sign of t is shifted into a bit word
+//         (one funnel shift) and min |t| of 32 candidates is tracked (FMNMX3);
+//       * with u = 2^-24, R_i = |p_i|, R_c = max |p| of the staged candidates (tracked while staging) and
+//         M = (R_i + R_c)^2 + cut, the roundings of the inputs (2 r u (R_i + R_c)) and of the five float results
+//         (each <= u M) keep |t - (rsq_ref - cut)| below 8 u M for EVERY candidate; `band` is twice that (about 3e-5
+//         cut in the bulk).  |t| > band: the sign of t decides; otherwise (about 0.01 candidates per atom) the
+//         reference's exact FP64 test (rsq_nofma on the FP64 records) does, so the pair set stays bit-exact
+//         (tests: tile32 == tile64 == thread walk on every fixture, pairs placed ON the cutoff, golden pair sets);
+//       * hits are compacted per 32-candidate block into a per-thread ring of 16-bit candidate indices in shared memory
+//         (column of the thread: conflict-free) and written out by row flushes with the lanes in lock step on the
+//         neighbour index k: a warp store covers one row of the transposed list (out[k * stride + i], consecutive i)
+//         instead of one scattered 4-byte store per hit.
+#ifndef TB32_CH
+#define TB32_CH 1408
+#endif
+#ifndef TB32_KS
+#define TB32_KS 64
+#endif
+constexpr int TB_CH32 = TB32_CH;              // staged candidates per chunk (a bulk halo holds about 1160)
+constexpr int TB_KS = TB32_KS;                // ring rows per thread (power of two, >= 32)
+constexpr int TB_NST = (TB_CH32 + TB_T - 1) / TB_T;   // staged candidates per thread and chunk
+#ifndef TB_SB
+#define TB_SB 4
+#endif
+constexpr size_t TB32_SMEM = (size_t)TB_CH32 * 16 + (size_t)TB_CH32 * 4 + (size_t)TB_KS * TB_T * 2;
+
+template <bool UNIFORM, bool LIST16>
+__global__ void __launch_bounds__(TB_T, 3)
+build_list_tile32_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_constant__ Coeffs co,
+                         const int *__restrict__ cell_start, const int *__restrict__ gcell_start,
+                         const int *__restrict__ gorder, const double cutmaxsq, int *flags) {
+  extern __shared__ __align__(16) unsigned char tb_smem[];
+  float4 *cand = reinterpret_cast<float4 *>(tb_smem);                          // {-2 p, |p|^2}
+  int *ents = reinterpret_cast<int *>(tb_smem + (size_t)TB_CH32 * 16);         // global index, then the packed 32-bit list entry
+  unsigned short *ring = reinterpret_cast<unsigned short *>(tb_smem + (size_t)TB_CH32 * 20);   // [row][thread]
+  __shared__ int seg_src[TB_MAXSEG];
+  __shared__ int seg_off[TB_MAXSEG + 1];
+  __shared__ int layer_off[TB_MAXLAY + 1];
+  __shared__ int qself[TB_T];
+  __shared__ int s_rmax;
+
+  const int tid = threadIdx.x;
+  TileGeom t;
+  if (!tile_geometry(g, blockIdx.x, cell_start, t)) return;   // empty tile (whole CTA)
+  const int first = t.first, last = t.last, hz0 = t.hz0, hz1 = t.hz1, nz = t.nz, nseg = t.nseg;
+  tile_segments(g, t, cell_start, gcell_start, d.nghost > 0, seg_src, seg_off);
+  if (tid <= nz) layer_off[tid] = seg_off[tid * t.ny * 6];
+  if (tid == 0) { atomicMax(&flags[4], seg_off[nseg]); s_rmax = 0; }
+  qself[tid] = 0;
+  __syncthreads();
+  const int total = seg_off[nseg];
+  const size_t stride = d.stride;
+  // centre of the halo box: the float coordinates stay within a few cell sizes of zero
+  const double ox = g.lo[0] + 0.5 * (t.hx0 + t.hx1 + 1) / g.inv[0];
+  const double oy = g.lo[1] + 0.5 * (t.hy0 + t.hy1 + 1) / g.inv[1];
+  const double oz = g.lo[2] + 0.5 * (t.hz0 + t.hz1 + 1) / g.inv[2];
+  constexpr unsigned FULL = 0xffffffffu;
+
+  for (int base = first; base < last; base += TB_T) {
+    const int i = base + tid;
+    const bool valid = i < last;
+    Rec4 Ai = make_rec4(0, 0, 0, 0);
+    int ti = 1;
+    float pix = 0.f, piy = 0.f, piz = 0.f;
+    double pi2 = 0.0;
+    if (valid) {
+      Ai = d.prec[i].A; ti = d.pflags[i] & 7;
+      pix = __double2float_rn(Ai.x - ox); piy = __double2float_rn(Ai.y - oy); piz = __double2float_rn(Ai.z - oz);
+      pi2 = (double)pix * pix + (double)piy * piy + (double)piz * piz;
+    }
+    // halo z-layers this WARP can reach
+    int llo = TB_MAXLAY, lhi = -1;
+    if (valid) {
+      int cz = g.dim == 2 ? 0 : (int)floor((Ai.z - g.lo[2]) * g.inv[2]);
+      cz = min(max(cz, hz0), hz1);
+      llo = max(cz - g.s[2], hz0) - hz0;
+      lhi = min(cz + g.s[2], hz1) - hz0;
+    }
+    llo = __reduce_min_sync(FULL, llo);
+    lhi = __reduce_max_sync(FULL, lhi);
+    int n = 0, nfl = 0;   // hits so far (= next row of this atom), rows already written out
+    int *out = d.neigh + (valid ? i : first);
+    const int maxn = valid ? (LIST16 ? d.pitch16 : d.maxneigh) : 0;
+    unsigned long long *row64 = LIST16 ? reinterpret_cast<unsigned long long *>(d.neigh16 + (size_t)(valid ? i : first) * d.pitch16) : nullptr;
+    unsigned long long acc = 0;
+    const int wq0 = lhi >= 0 ? layer_off[llo] : 0, wq1 = lhi >= 0 ? layer_off[lhi + 1] : 0;
+
+    for (int clo = 0; clo < total; clo += TB_CH32) {
+      const int chi = min(total, clo + TB_CH32), cnt = chi - clo, cpad = (cnt + 31) & ~31;
+      // ---- stage candidates clo .. chi.  Global indices segment by segment (a segment is a run of consecutive atoms) ...
+      for (int sid = tid; sid < nseg; sid += TB_T) {
+        const int off = seg_off[sid], src = seg_src[sid];
+        const int k0 = max(0, clo - off), k1 = min(seg_off[sid + 1], chi) - off;
+        for (int k = k0; k < k1; k++) ents[off + k - clo] = tile_source(src, k, d.nlocal, gorder);
+      }
+      __syncthreads();
+      // ... then the records, TB_SB loads per thread in flight together
+      float rmax = 0.f;
+#pragma unroll
+      for (int u0 = 0; u0 < TB_NST; u0 += TB_SB) {
+        Rec4 A[TB_SB];
+        int fl[TB_SB], jj[TB_SB];
+#pragma unroll
+        for (int u = 0; u < TB_SB; u++) {
+          const int q = tid + (u0 + u) * TB_T;
+          if (u0 + u < TB_NST && q < cnt) { jj[u] = ents[q]; A[u] = d.prec[jj[u]].A; fl[u] = d.pflags[jj[u]]; }
+        }
+#pragma unroll
+        for (int u = 0; u < TB_SB; u++) {
+          const int q = tid + (u0 + u) * TB_T;
+          if (u0 + u >= TB_NST) continue;
+          if (q < cnt) {
+            const int j = jj[u];
+            const float px = __double2float_rn(A[u].x - ox), py = __double2float_rn(A[u].y - oy), pz = __double2float_rn(A[u].z - oz);
+            const float p2 = __double2float_rn((double)px * px + (double)py * py + (double)pz * pz);
+            rmax = fmaxf(rmax, p2);
+            cand[q] = make_float4(-2.f * px, -2.f * py, -2.f * pz, p2);
+            ents[q] = j | ((fl[u] & 7) << NEIGH_JBITS) | (((fl[u] >> 4) & 1) << 30);
+            if (j >= base && j < base + TB_T && j < last) qself[j - base] = q;
+          } else if (q < cpad) {
+            cand[q] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));   // +inf: never inside
+          }
+        }
+      }
+      rmax = __int_as_float(__reduce_max_sync(FULL, __float_as_int(rmax)));   // non-negative floats order like their bit patterns
+      if ((tid & 31) == 0) atomicMax(&s_rmax, __float_as_int(rmax));
+      __syncthreads();
+      // ---- error bound of the float classification (s_rmax only grows: later chunks stay covered)
+      const double Rsum = sqrt(pi2) + sqrt((double)__int_as_float(s_rmax) * (1.0 + 1e-6));
+      const float bandf = __double2float_ru(1.001 * (16.0 / 16777216.0) * (Rsum * Rsum + cutmaxsq) + 1e-12 * cutmaxsq);
+      float ci_i[MAXT];
+      double cut_i[MAXT];
+#pragma unroll
+      for (int q = 0; q < MAXT; q++) {
+        cut_i[q] = UNIFORM ? cutmaxsq : co.cutneighsq[ti][q];
+        ci_i[q] = valid ? __double2float_rn(pi2 - cut_i[q]) : __int_as_float(0x7f800000);
+      }
+      // this atom's own slot (its bit is cleared instead of testing every hit)
+      int qs = qself[tid];
+      if (!(valid && qs < cnt && (ents[qs] & NEIGH_JMASK) == i)) qs = -1;
+      // ---- converged float sweep, 32 candidates per bit word
+      const int qa = (max(wq0, clo) - clo) & ~31, qb = min((min(wq1, chi) - clo + 31) & ~31, cpad);
+      for (int q0 = qa; q0 < qb; q0 += 32) {
+        unsigned bits = 0;
+        float tmin = 3.0e38f;
+#pragma unroll
+        for (int u = 0; u < 32; u++) {
+          const float4 c = cand[q0 + u];
+          float ci = ci_i[0];
+          if (!UNIFORM) {
+            const int tj = (ents[q0 + u] >> NEIGH_JBITS) & 7;
+#pragma unroll
+            for (int q2 = 1; q2 < MAXT; q2++) ci = tj == q2 ? ci_i[q2] : ci;
+          }
+          const float tt = fmaf(pix, c.x, fmaf(piy, c.y, fmaf(piz, c.z, c.w))) + ci;   // r^2 - cut; < 0: inside
+          bits = __funnelshift_l((unsigned)__float_as_int(tt), bits, 1);   // (bits << 1) | sign(tt): candidate u ends up in bit 31 - u
+          tmin = fminf(tmin, fabsf(tt));
+        }
+        bits = __brev(bits);
+        if (tmin <= bandf) {   // rare: some candidate of the block is undecided in float -> the reference's FP64 criterion on the FP64 records
+          for (int u = 0; u < 32; u++) {
+            const float4 c = cand[q0 + u];
+            const int ent = ents[q0 + u];
+            float ci = ci_i[0];
+            double cut = cut_i[0];
+            if (!UNIFORM) {
+              const int tj = (ent >> NEIGH_JBITS) & 7;
+#pragma unroll
+              for (int q2 = 1; q2 < MAXT; q2++) { ci = tj == q2 ? ci_i[q2] : ci; cut = tj == q2 ? cut_i[q2] : cut; }
+            }
+            const float tt = fmaf(pix, c.x, fmaf(piy, c.y, fmaf(piz, c.z, c.w))) + ci;
+            if (fabsf(tt) <= bandf) {
+              const Rec4 Aj = d.prec[ent & NEIGH_JMASK].A;
+              const double rsq = rsq_nofma(Ai.x - Aj.x, Ai.y - Aj.y, Ai.z - Aj.z);
+              if (rsq <= cut) bits |= 1u << u; else bits &= ~(1u << u);
+            }
+          }
+        }
+        if ((qs & ~31) == q0) bits &= ~(1u << (qs & 31));
+        // ---- compaction into the ring; rows are written out when some lane could run out of ring
+        if (__any_sync(FULL, n - nfl + __popc(bits) > TB_KS)) {
+          const int k0 = __reduce_min_sync(FULL, nfl), k1 = __reduce_max_sync(FULL, n);
+          for (int k = k0; k < k1; k++)
+            if (k >= nfl && k < n) {
+              const int q = ring[(k & (TB_KS - 1)) * TB_T + tid];
+              const int ent = ents[q];
+              if (LIST16) {
+                const unsigned e16 = (unsigned)(q + clo) | (((unsigned)ent >> NEIGH_JBITS) & 7u) << TILE_SLOT_BITS | (((unsigned)ent >> 30) & 1u) << 15;
+                acc = (acc >> 16) | ((unsigned long long)e16 << 48);
+                if (((k + 1) & 3) == 0 && k < maxn) row64[k >> 2] = acc;
+              } else if (k < maxn) {
+                out[(size_t)k * stride] = ent;
+              }
+            }
+          nfl = n;
+        }
+        while (bits) {
+          const int bq = __ffs(bits) - 1;
+          bits &= bits - 1;
+          ring[(n & (TB_KS - 1)) * TB_T + tid] = (unsigned short)(q0 + bq);
+          n++;
+        }
+      }
+      // ---- the rest of the ring (its entries index this chunk's staging area)
+      {
+        const int k0 = __reduce_min_sync(FULL, nfl), k1 = __reduce_max_sync(FULL, n);
+        for (int k = k0; k < k1; k++)
+          if (k >= nfl && k < n) {
+            const int q = ring[(k & (TB_KS - 1)) * TB_T + tid];
+            const int ent = ents[q];
+            if (LIST16) {
+              const unsigned e16 = (unsigned)(q + clo) | (((unsigned)ent >> NEIGH_JBITS) & 7u) << TILE_SLOT_BITS | (((unsigned)ent >> 30) & 1u) << 15;
+              acc = (acc >> 16) | ((unsigned long long)e16 << 48);
+              if (((k + 1) & 3) == 0 && k < maxn) row64[k >> 2] = acc;
+            } else if (k < maxn) {
+              out[(size_t)k * stride] = ent;
+            }
+          }
+        nfl = n;
+      }
+      // the staging area is reused only if another chunk or batch of atoms follows (CTA-uniform)
+      if (chi < total || base + TB_T < last) __syncthreads();
+    }
+    if (valid) {
+      if (LIST16 && (n & 3) && n < maxn) row64[n >> 2] = acc >> (16 * (4 - (n & 3)));   // partial last word (maxn is a multiple of 8)
+      d.numneigh[i] = n < maxn ? n : maxn;
+      atomicMax(&flags[2], n);
+    }
+  }
+}
+
 // tile form -> gather form: d.neigh[k * stride + i] = j | type_j << 27 | solid_j << 30 for every 16-bit entry.  One CTA
 // per tile; slot -> global index through the same enumeration the builder used.  For sphbvf_get_pairs and for tests
 // that run the gather kernel on a list built in tile form; never on the timestep path.
@@ -587,26 +824,37 @@ void launch_build_list(const DevState &d, const Grid &g, const Coeffs &co, const
       if (co.cutneighsq[i][j] != co.cutneighsq[1][1]) uniform = false;
     }
   if (!d.nlocal) return;
-  const char *env = getenv("SPHBVF_LIST_BUILD");   // read per rebuild so that tests can compare both builders
+  const char *env = getenv("SPHBVF_LIST_BUILD");   // read per rebuild so that tests can compare the builders
   const bool per_thread = env && env[0] == 't' && env[1] == 'h' && !d.list16;
+  const bool sweep64 = env && !strcmp(env, "tile64");   // the all-FP64 sweep (A) instead of the float classification (A')
   if (!per_thread && tile_form_possible(g)) {
     const long ntiles = (long)g.nt[0] * g.nt[1] * g.nt[2];
-    constexpr int smem = TB_CH * (int)sizeof(Cand);
+    constexpr int smem64 = TB_CH * (int)sizeof(Cand);
+    constexpr int smem32 = (int)TB32_SMEM;
     // the opt-in to > 48 KB of dynamic shared memory is per device (one process may drive several GPUs, each from
     // its own thread): setting it again is harmless, missing it is a launch failure
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      cudaFuncSetAttribute(build_list_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      cudaFuncSetAttribute(build_list_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      cudaFuncSetAttribute(build_list_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      cudaFuncSetAttribute(build_list_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(build_list_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64);
+      cudaFuncSetAttribute(build_list_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64);
+      cudaFuncSetAttribute(build_list_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64);
+      cudaFuncSetAttribute(build_list_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64);
+      cudaFuncSetAttribute(build_list_tile32_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+      cudaFuncSetAttribute(build_list_tile32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+      cudaFuncSetAttribute(build_list_tile32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+      cudaFuncSetAttribute(build_list_tile32_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-#define TBK(U, L) build_list_tile_kernel<U, L><<<(int)ntiles, TB_T, smem, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags)
-    if (d.list16) { if (uniform) TBK(true, true); else TBK(false, true); }
-    else { if (uniform) TBK(true, false); else TBK(false, false); }
+#define TBK(K, SM, U, L) K<U, L><<<(int)ntiles, TB_T, SM, st>>>(d, g, co, w.cell_start, w.gcell_start, w.gorder, cutmax, w.flags)
+    if (sweep64) {
+      if (d.list16) { if (uniform) TBK(build_list_tile_kernel, smem64, true, true); else TBK(build_list_tile_kernel, smem64, false, true); }
+      else { if (uniform) TBK(build_list_tile_kernel, smem64, true, false); else TBK(build_list_tile_kernel, smem64, false, false); }
+    } else {
+      if (d.list16) { if (uniform) TBK(build_list_tile32_kernel, smem32, true, true); else TBK(build_list_tile32_kernel, smem32, false, true); }
+      else { if (uniform) TBK(build_list_tile32_kernel, smem32, true, false); else TBK(build_list_tile32_kernel, smem32, false, false); }
+    }
 #undef TBK
     SPHBVF_LAUNCHED(1);
     return;
