@@ -482,6 +482,18 @@ static PairFlags pair_flags(const sphbvf_ctx *ctx) {
 // any_solid / with_dev / e_nonzero select the pair-kernel instantiation and the halo record width.  They are derived
 // from the DEVICE state (a reduction over the owned atoms), so that fields changed through sphbvf_upload after
 // sphbvf_set_atoms count: set_atoms(e = NULL) followed by upload(E != 0) must switch the stochastic term on.
+// the flags must agree on every brick; with_dev is a type mask, so its bits are reduced one by one (max = or)
+static int allreduce_kernel_flags(sphbvf_ctx *ctx) {
+  int v[2 + 8] = {ctx->any_solid, ctx->e_nonzero};
+  for (int t = 0; t < 8; t++) v[2 + t] = (ctx->with_dev >> t) & 1;
+  const int rc = comm_allreduce_max(ctx, v, 10);
+  if (rc) return rc;
+  ctx->any_solid = v[0]; ctx->e_nonzero = v[1];
+  ctx->with_dev = 0;
+  for (int t = 0; t < 8; t++) ctx->with_dev |= v[2 + t] << t;
+  return 0;
+}
+
 static int derive_flags(sphbvf_ctx *ctx) {
   int *out = ctx->w.flags + 5;   // flags[5..7]: scratch between rebuilds
   CK(cudaMemsetAsync(out, 0, sizeof(int) * 3, ctx->st));
@@ -659,12 +671,15 @@ int sphbvf_set_atoms(sphbvf_ctx *ctx, int n, const int *tag, const int *type, co
   for (int i = 0; i < n; i++) {
     if (solid[i]) {
       ctx->any_solid = 1;
-      if (ctx->co.G0[type[i]] != 0.0) has_dev = 1;
+      if (ctx->co.G0[type[i]] != 0.0) has_dev |= 1 << type[i];
     }
   }
   if (dev)
-    for (size_t q = 0; q < (size_t)9 * n && !has_dev; q++) if (dev[q] != 0.0) has_dev = 1;
-  ctx->with_dev = has_dev;
+    for (int i = 0; i < n; i++) {
+      if ((has_dev >> type[i]) & 1) continue;
+      for (int q = 0; q < 9; q++) if (dev[9 * (size_t)i + q] != 0.0) { has_dev |= 1 << type[i]; break; }
+    }
+  ctx->with_dev = has_dev;   // bit t: atoms of type t may carry a deviatoric stress (non-zero = elastic solids present)
 #define UP(dst, src, cnt, T)                                                                         \
   do {                                                                                               \
     if (src) CK(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)(cnt), cudaMemcpyHostToDevice, st));   \
@@ -793,9 +808,7 @@ int sphbvf_setup(sphbvf_ctx *ctx) {
   if ((rc = derive_flags(ctx))) return rc;
   if (ctx->cfg.nranks > 1) {
     // kernel specialisation and halo record width must agree on every brick
-    int v[3] = {ctx->any_solid, ctx->with_dev, ctx->e_nonzero};
-    if ((rc = comm_allreduce_max(ctx, v, 3))) return rc;
-    ctx->any_solid = v[0]; ctx->with_dev = v[1]; ctx->e_nonzero = v[2];
+    if ((rc = allreduce_kernel_flags(ctx))) return rc;
   }
   if ((rc = sphbvf_build_neighbors(ctx))) return rc;
   ctx->nbuilds = 0;   // neighbor->ncalls = 0 (verlet.cpp:128)
@@ -814,9 +827,7 @@ int sphbvf_setup_neighbors(sphbvf_ctx *ctx) {
   FLUSH();
   if ((rc = derive_flags(ctx))) return rc;
   if (ctx->cfg.nranks > 1) {
-    int v[3] = {ctx->any_solid, ctx->with_dev, ctx->e_nonzero};
-    if ((rc = comm_allreduce_max(ctx, v, 3))) return rc;
-    ctx->any_solid = v[0]; ctx->with_dev = v[1]; ctx->e_nonzero = v[2];
+    if ((rc = allreduce_kernel_flags(ctx))) return rc;
   }
   if ((rc = sphbvf_build_neighbors(ctx))) return rc;
   ctx->nbuilds = 0;
@@ -868,9 +879,7 @@ int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt) {
     force_rebuild = (ctx->flags_dirty & 2) != 0;
     if ((rc = derive_flags(ctx))) return rc;
     if (ctx->cfg.nranks > 1) {
-      int v[3] = {ctx->any_solid, ctx->with_dev, ctx->e_nonzero};
-      if ((rc = comm_allreduce_max(ctx, v, 3))) return rc;
-      ctx->any_solid = v[0]; ctx->with_dev = v[1]; ctx->e_nonzero = v[2];
+      if ((rc = allreduce_kernel_flags(ctx))) return rc;
     }
   }
   // Neighbor::decide (neighbor.cpp:1922-1937)

@@ -376,7 +376,7 @@ __global__ void derive_flags_kernel(const DevState d, const __grid_constant__ Co
   bool dev = solid && co.G0[d.type[i]] != 0.0;
   for (int k = 0; k < 9 && !dev; k++) dev = d.dev[9 * (size_t)i + k] != 0.0;
   if (solid && !out[0]) out[0] = 1;
-  if (dev && !out[1]) out[1] = 1;
+  if (dev && !((out[1] >> d.type[i]) & 1)) atomicOr(&out[1], 1 << d.type[i]);   // mask of the types that can carry stress
   if (d.e[i] != 0.0 && !out[2]) out[2] = 1;
 }
 

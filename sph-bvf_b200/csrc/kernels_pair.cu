@@ -69,12 +69,17 @@ struct __align__(16) TypeRow {
   double imass, c0, G0, pad;    // 1/m, c0, G0
 };
 
+// species transport of one (type_i, type_j): 64 B, read from shared memory (type pairs differ: lanes read different
+// rows) or straight from the constant bank with a compile-time index (UNIFORM: every pair has the same row)
+struct __align__(16) SpecRow {
+  double cutc, cwfdc, mred2, hc2eps;   // concentration cutoff, (1/r)dW/dr coefficient with h = cutc, 2 mi mj / (mi + mj), 0.01 cutc^2
+  double kappa[MAXS];
+};
+
 struct PairTables {
   PairRow row[MAXT * MAXT];
   TypeRow type[MAXT];
-  double cwfdc[MAXT][MAXT];  // same as cwfd with h = cutc
-  double hc2eps[MAXT][MAXT]; // 0.01 cutc^2
-  double mred2[MAXT][MAXT];  // 2 mi mj / (mi + mj)
+  SpecRow spec[MAXT * MAXT];
   double geff[MAXT][MAXT];   // 2 Gi Gj / (Gi + Gj + 1e-12)
 };
 
@@ -100,7 +105,8 @@ static bool make_tables(const Coeffs &co, PairTables &t) {
       PairRow &r = t.row[i * MAXT + j];
       double h = co.cut[i][j], hc = co.cutc[i][j], dummy;
       coef(h, r.cwfd, r.cwf);
-      coef(hc > 0 ? hc : h, t.cwfdc[i][j], dummy);
+      SpecRow &sr = t.spec[i * MAXT + j];
+      coef(hc > 0 ? hc : h, sr.cwfdc, dummy);
       double delta = delta_fac * h, td = h - delta;
       double wdelta = r.cwf * td * td * td * (h + 3. * delta);
       r.cutsq = co.cutsq[i][j];
@@ -109,11 +115,16 @@ static bool make_tables(const Coeffs &co, PairTables &t) {
       r.h2eps = 0.01 * h * h;
       r.mimj = co.mass[i] * co.mass[j];
       r.eta = co.eta[i][j];
-      t.hc2eps[i][j] = 0.01 * hc * hc;
-      t.mred2[i][j] = 2.0 * ((co.mass[i] * co.mass[j]) / (co.mass[i] + co.mass[j]));
+      sr.cutc = hc;
+      sr.hc2eps = 0.01 * hc * hc;
+      sr.mred2 = 2.0 * ((co.mass[i] * co.mass[j]) / (co.mass[i] + co.mass[j]));
+      for (int k = 0; k < MAXS; k++) sr.kappa[k] = k < co.nspecies ? co.kappa[i][j][k] : 0.0;
       t.geff[i][j] = (2.0 * co.G0[i] * co.G0[j]) / (co.G0[i] + co.G0[j] + 1e-12);
       const PairRow &r11 = t.row[MAXT + 1];
       if (r.cutsq != r11.cutsq || r.h != r11.h || r.mimj != r11.mimj || r.eta != r11.eta) uniform = false;
+      // the UNIFORM instantiations also read the species row (and 1/m) of pair (1,1) for every pair
+      if (co.nspecies > 0 && memcmp(&sr, &t.spec[MAXT + 1], sizeof sr)) uniform = false;
+      if (co.mass[i] != co.mass[1]) uniform = false;
     }
   }
   return uniform;
@@ -172,6 +183,7 @@ struct PairConsts {
   double damp, rand_pref;
   unsigned long long seed;
   long ntimestep;
+  int elmask;   // bit t: atoms of type t with solid_tag may carry a deviatoric stress (G0[t] != 0 or some dev != 0)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -181,18 +193,98 @@ struct PairConsts {
 // A neighbour is handed over as the fields of its record; `j` (its global index) is only used by the
 // instantiations that gather extras (species, deviatoric tensors, stochastic term).
 // ------------------------------------------------------------------------------------------
-template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM>
+// Everything a pair adds because atom i or atom j carries a deviatoric stress (SOLIDS == 2; reference:
+// pair_ssa_tsdpd_bvf_mechanics.cpp:435-494, ..._fsi.cpp same blocks): artificial stress, the stress-divergence force on
+// a solid i, and the Jaumann rate of i's stress.  Only called when atom i or atom j is ELASTIC (solid_tag and a type that
+// can carry stress: PairConsts::elmask); rigid walls (dev == 0 for ever) take the scalar shortcut of SOLIDS == 1.
+// Measured as a __noinline__ call (registers saved only around the call): fsi deck 1.06 -> 1.68 ms, so it is inlined.
+// sol: dev_i = sol[k * stride], d(dev_i)/dt accumulator = sol[(9 + k) * stride].
+struct SolidIn {
+  double delx, dely, delz, velx, vely, velz;
+  double wf, wfd, mmw, iwdelta, Vj, rhoj, Prrj, irhoi, irhoj, Pi, geff;
+};
+template <int VARIANT>
+__device__ __forceinline__ double3 solid2_visit(const SolidIn in, const bool si, const bool sj, const double *__restrict__ devj_g,
+                                             double *sol, const int stride) {
+  constexpr double c_art = VARIANT == SPHBVF_FSI ? 0.1 : 0.35;
+  double devj[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) devj[k] = sj ? devj_g[k] : 0.0;
+  const double Pj = in.Prrj * in.rhoj * in.rhoj;
+  const double Psj = VARIANT == SPHBVF_MECHANICS ? fabs(Pj) : Pj;
+  const double Psi = VARIANT == SPHBVF_MECHANICS ? fabs(in.Pi) : in.Pi;
+  const double q = in.wf * in.iwdelta, q2 = q * q;
+  const double pre = in.mmw * q2 * q2;
+  double R[9];
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+#pragma unroll
+    for (int n = 0; n < 3; n++) {
+      const double tsj = devj[3 * m + n] - (m == n ? Psj : 0.0);
+      const double Rj = (sj && tsj > 0.0) ? -c_art * tsj * in.irhoj * in.irhoj : 0.0;
+      double Ri = 0.0;
+      if (si) {
+        const double tsi = sol[(3 * m + n) * stride] - (m == n ? Psi : 0.0);
+        Ri = tsi > 0.0 ? -c_art * tsi * in.irhoi * in.irhoi : 0.0;
+      }
+      R[3 * m + n] = Ri + Rj;
+    }
+  double3 F;
+  F.x = pre * (in.delx * R[0] + in.dely * R[3] + in.delz * R[6]);
+  F.y = pre * (in.delx * R[1] + in.dely * R[4] + in.delz * R[7]);
+  F.z = pre * (in.delx * R[2] + in.dely * R[5] + in.delz * R[8]);
+  if (si) {
+    // ---- Jaumann rate for solid i (:435-451)
+    const double hw = -0.5 * in.Vj * in.wfd;   // 0.5 * Vj * wfd * (v_j - v_i) = hw * vel
+    const double vel[3] = {in.velx, in.vely, in.velz}, del[3] = {in.delx, in.dely, in.delz};
+    double devi[9], eps[9], om[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) devi[k] = sol[k * stride];
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+      for (int n = 0; n < 3; n++) {
+        const double a = vel[m] * del[n], b = vel[n] * del[m];
+        eps[3 * m + n] = hw * (a + b);
+        om[3 * m + n] = hw * (a - b);
+      }
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+      for (int n = 0; n < 3; n++) {
+        const double dDotR = devi[3 * m] * om[3 * n] + devi[3 * m + 1] * om[3 * n + 1] + devi[3 * m + 2] * om[3 * n + 2];
+        const double rDotD = om[3 * m] * devi[n] + om[3 * m + 1] * devi[3 + n] + om[3 * m + 2] * devi[6 + n];
+        const double e = eps[3 * m + n];
+        sol[(9 + 3 * m + n) * stride] += 2.0 * in.geff * (m == n ? e - (1. / 3.) * e : e) + dDotR + rDotD;
+      }
+    // ---- stress divergence on a solid i (:511-522)
+    const double ii = in.irhoi * in.irhoi, jj = in.irhoj * in.irhoj;
+    F.x += in.mmw * (in.delx * (devi[0] * ii + devj[0] * jj) + in.dely * (devi[3] * ii + devj[3] * jj) + in.delz * (devi[6] * ii + devj[6] * jj));
+    F.y += in.mmw * (in.delx * (devi[1] * ii + devj[1] * jj) + in.dely * (devi[4] * ii + devj[4] * jj) + in.delz * (devi[7] * ii + devj[7] * jj));
+    F.z += in.mmw * (in.delx * (devi[2] * ii + devj[2] * jj) + in.dely * (devi[5] * ii + devj[5] * jj) + in.delz * (devi[8] * ii + devj[8] * jj));
+  }
+  return F;
+}
+
+// SOLSMEM (gather form, SOLIDS == 2): the deviatoric stress of atom i and its rate accumulator -- 18 doubles that only
+// solid atoms ever touch -- live in a shared-memory column of the thread (sol[k * SOLSTRIDE]) instead of 36 registers:
+// at 168 registers the SOLIDS == 2 instantiations spilled 1.9 KB per thread into the neighbour loop of EVERY atom.
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool SOLSMEM = false, int SOLSTRIDE = 1>
 struct PairAcc {
   // atom i
   double xi, yi, zi, rhoi, vxi, vyi, vzi, Vi, wxi, wyi, wzi, Prri;   // record: A = {x,y,z,rho} B = {vest,V} C = {w,P/rho^2}
   double Vi2, c0i, Pi, irhoi, G0i, ei, arti;
   int ti, tagi;
   bool si;
-  double devi[9], Ri[9], Cspec_i[MAXS];
+  double solr[(SOLIDS == 2 && !SOLSMEM) ? 18 : 1], Cspec_i[MAXS];
+  double *sol;   // devi = sol[0..8], ddev = sol[9..17] (times SOLSTRIDE): shared-memory column (SOLSMEM) or solr
+  __device__ __forceinline__ double &devi(int k) { return sol[k * SOLSTRIDE]; }
+  __device__ __forceinline__ double &ddev(int k) { return sol[(9 + k) * SOLSTRIDE]; }
   const PairRow *myrow;
+  const SpecRow *myspec;   // row ti of a shared-memory copy of tb.spec, or nullptr: read tb.spec (constant bank)
   // sums
   double fx, fy, fz, drho, nd, rA1, rA2, phi, ddvx, ddvy, ddvz, nwx, nwy, nwz, ddxx, ddxy, ddxz, spi;
-  double ddev[9], Qs[MAXS];
+  double Qs[MAXS];
 
   __host__ __device__ static constexpr double c_art() { return VARIANT == SPHBVF_FSI ? 0.1 : 0.35; }
 
@@ -208,24 +300,20 @@ struct PairAcc {
     Pi = Prri * rhoi * rhoi;
     irhoi = Vi * tb.type[ti].imass;
     myrow = srow + (UNIFORM ? 0 : ti * MAXT);
+    myspec = nullptr;
     arti = 0.0;
     // stress-free solid (dev == 0): R = -c_art max(0, -Psigma)/rho^2 = c_art P/rho^2 where P < 0 (TV, fsi);
     // mechanics uses |P| (:471,487) so the bracket is never positive
-    if (SOLIDS == 1) arti = (si && VARIANT != SPHBVF_MECHANICS && Prri < 0.0) ? c_art() * Prri : 0.0;
+    if (SOLIDS) arti = (si && VARIANT != SPHBVF_MECHANICS && Prri < 0.0) ? c_art() * Prri : 0.0;   // SOLIDS == 2: used when neither atom is elastic
     if (SOLIDS == 2) {
+      if (!SOLSMEM) sol = solr;
 #pragma unroll
-      for (int k = 0; k < 9; k++) devi[k] = si ? d.pdev[9 * (size_t)i + k] : 0.0;
-      const double Ps = VARIANT == SPHBVF_MECHANICS ? fabs(Pi) : Pi;
-#pragma unroll
-      for (int m = 0; m < 3; m++)
-#pragma unroll
-        for (int n = 0; n < 3; n++) {
-          double ts = devi[3 * m + n] - (m == n ? Ps : 0.0);
-          Ri[3 * m + n] = (si && ts > 0.0) ? -c_art() * ts * irhoi * irhoi : 0.0;
-        }
+      for (int k = 0; k < 9; k++) devi(k) = si ? d.pdev[9 * (size_t)i + k] : 0.0;
     }
-    if (SPECIES)
-      for (int k = 0; k < co.nspecies; k++) Cspec_i[k] = d.pCs[(size_t)i * co.nspecies + k];
+    if (SPECIES) {   // fully unrolled with a predicate: the arrays live in registers, not in local memory
+#pragma unroll
+      for (int k = 0; k < MAXS; k++) Cspec_i[k] = k < co.nspecies ? d.pCs[(size_t)i * co.nspecies + k] : 0.0;
+    }
     ei = RANDOM ? d.pD[i].w : 0.0;
     tagi = RANDOM ? d.ptag[i] : 0;
     G0i = co.G0[ti];
@@ -236,7 +324,7 @@ struct PairAcc {
     spi = 0.0;   // sum_j s_ij rho_i a_i: the i-side transport term is vest_i times this
     if (SOLIDS == 2)
 #pragma unroll
-      for (int k = 0; k < 9; k++) ddev[k] = 0.0;
+      for (int k = 0; k < 9; k++) ddev(k) = 0.0;
     if (SPECIES)
 #pragma unroll
       for (int k = 0; k < MAXS; k++) Qs[k] = 0.0;
@@ -248,7 +336,7 @@ struct PairAcc {
                                         const int tj, const bool sj_in, const int j, const double xj, const double yj,
                                         const double zj, const double rhoj, const double vxj, const double vyj,
                                         const double vzj, const double Vj, const double wxj, const double wyj,
-                                        const double wzj, const double Prrj, const double rhoIj) {
+                                        const double wzj, const double Prrj, const double rhoIj, const double Cj0) {
     const bool sj = SOLIDS && sj_in;
     const double delx = xi - xj, dely = yi - yj, delz = zi - zj;
     const double rsq = delx * delx + dely * dely + delz * delz;
@@ -296,8 +384,9 @@ struct PairAcc {
 
     // ---- artificial stress (:454-494)
     double fartx = 0, farty = 0, fartz = 0;
-    if (SOLIDS == 1) {
-      if (si || sj) {
+    const bool eli = SOLIDS == 2 && si && ((pc.elmask >> ti) & 1), elj = SOLIDS == 2 && sj && ((pc.elmask >> tj) & 1);
+    if (SOLIDS) {
+      if ((si || sj) && !(eli || elj)) {
         const double q = wf * iwdelta, q2 = q * q;
         const double artj = (sj && VARIANT != SPHBVF_MECHANICS && Prrj < 0.0) ? c_art() * Prrj : 0.0;
         const double cc = mmw * q2 * q2 * (arti + artj);
@@ -305,57 +394,19 @@ struct PairAcc {
       }
     }
 
-    double devj[9];
     if (SOLIDS == 2) {
-      const double irhoj = Vj * tb.type[tj].imass;
-      if (si || sj) {
-#pragma unroll
-        for (int k = 0; k < 9; k++) devj[k] = sj ? d.pdev[9 * (size_t)j + k] : 0.0;
-        const double Pj = Prrj * rhoj * rhoj;
-        const double Psj = VARIANT == SPHBVF_MECHANICS ? fabs(Pj) : Pj;
-        const double q = wf * iwdelta, q2 = q * q;
-        const double pre = mmw * q2 * q2;
-        double R[9];
-#pragma unroll
-        for (int m = 0; m < 3; m++)
-#pragma unroll
-          for (int n = 0; n < 3; n++) {
-            double ts = devj[3 * m + n] - (m == n ? Psj : 0.0);
-            double Rj = (sj && ts > 0.0) ? -c_art() * ts * irhoj * irhoj : 0.0;
-            R[3 * m + n] = Ri[3 * m + n] + Rj;
-          }
-        fartx = pre * (delx * R[0] + dely * R[3] + delz * R[6]);
-        farty = pre * (delx * R[1] + dely * R[4] + delz * R[7]);
-        fartz = pre * (delx * R[2] + dely * R[5] + delz * R[8]);
-      }
-      // ---- Jaumann rate for solid i (:435-451)
-      if (si) {
-        double G0j = tb.type[tj].G0;
-        double geff;
-        if (VARIANT == SPHBVF_FSI && SPECIES) {
-          G0j = tb.type[tj].G0 * (1.0 - 0.99 * d.pCs[(size_t)j * co.nspecies]);
-          geff = (2.0 * G0i * G0j) / (G0i + G0j + 1e-12);
-        } else geff = tb.geff[ti][tj];
-        const double hw = -0.5 * Vj * wfd;   // 0.5 * Vj * wfd * (v_j - v_i) = hw * vel
-        const double vel[3] = {velx, vely, velz}, del[3] = {delx, dely, delz};
-        double eps[9], om[9];
-#pragma unroll
-        for (int m = 0; m < 3; m++)
-#pragma unroll
-          for (int n = 0; n < 3; n++) {
-            const double a = vel[m] * del[n], b = vel[n] * del[m];
-            eps[3 * m + n] = hw * (a + b);
-            om[3 * m + n] = hw * (a - b);
-          }
-#pragma unroll
-        for (int m = 0; m < 3; m++)
-#pragma unroll
-          for (int n = 0; n < 3; n++) {
-            const double dDotR = devi[3 * m] * om[3 * n] + devi[3 * m + 1] * om[3 * n + 1] + devi[3 * m + 2] * om[3 * n + 2];
-            const double rDotD = om[3 * m] * devi[n] + om[3 * m + 1] * devi[3 + n] + om[3 * m + 2] * devi[6 + n];
-            const double e = eps[3 * m + n];
-            ddev[3 * m + n] += 2.0 * geff * (m == n ? e - (1. / 3.) * e : e) + dDotR + rDotD;
-          }
+      if (eli || elj) {
+        double geff = 0.0;
+        if (si) {
+          if (VARIANT == SPHBVF_FSI && SPECIES) {
+            const double G0j = tb.type[tj].G0 * (1.0 - 0.99 * Cj0);
+            geff = (2.0 * G0i * G0j) / (G0i + G0j + 1e-12);
+          } else geff = tb.geff[ti][tj];
+        }
+        const SolidIn in = {delx, dely, delz, velx, vely, velz, wf, wfd, mmw, iwdelta, Vj, rhoj, Prrj, irhoi,
+                            Vj * tb.type[tj].imass, Pi, geff};
+        const double3 F = solid2_visit<VARIANT>(in, si, sj, d.pdev + 9 * (size_t)j, sol, SOLSTRIDE);
+        fartx = F.x; farty = F.y; fartz = F.z;
       }
     }
 
@@ -416,13 +467,6 @@ struct PairAcc {
       fx += cc * delx + fartx;
       fy += cc * dely + farty;
       fz += cc * delz + fartz;
-      if (SOLIDS == 2) {
-        const double irhoj = Vj * tb.type[tj].imass;
-        const double ii = irhoi * irhoi, jj = irhoj * irhoj;
-        fx += mmw * (delx * (devi[0] * ii + devj[0] * jj) + dely * (devi[3] * ii + devj[3] * jj) + delz * (devi[6] * ii + devj[6] * jj));
-        fy += mmw * (delx * (devi[1] * ii + devj[1] * jj) + dely * (devi[4] * ii + devj[4] * jj) + delz * (devi[7] * ii + devj[7] * jj));
-        fz += mmw * (delx * (devi[2] * ii + devj[2] * jj) + dely * (devi[5] * ii + devj[5] * jj) + delz * (devi[8] * ii + devj[8] * jj));
-      }
     }
 
     // ---- density rate (:548-555); (vt_i - vt_j).del = dvr - a_i + a_j
@@ -442,19 +486,23 @@ struct PairAcc {
     }
 
     // ---- species (:678-720)
+    // Cj0 = C_j[0] arrives with the record (requested one visit ahead); further species are gathered here
     if (SPECIES) {
-      const double hc = co.cutc[ti][tj];
+      const SpecRow &sr = UNIFORM ? tb.spec[MAXT + 1] : (myspec ? myspec[tj] : tb.spec[ti * MAXT + tj]);
+      const double hc = sr.cutc;
       if (r < hc) {
         const double tc = hc - r;
-        const double wfdc = tb.cwfdc[ti][tj] * tc * tc;
-        const double irhoj = Vj * tb.type[tj].imass;
-        const double q0 = tb.mred2[ti][tj] * (irhoi + irhoj) * rsq * wfdc / (rsq + tb.hc2eps[ti][tj]);
-        for (int k = 0; k < co.nspecies; k++) {
-          const double Cjk = d.pCs[(size_t)j * co.nspecies + k];
-          double dq = co.kappa[ti][tj][k] * (Cspec_i[k] - Cjk) * q0;
-          if (VARIANT == SPHBVF_TV) dq -= Vj * (Cspec_i[k] * ai + Cjk * aj) * wfdc;
-          Qs[k] += dq;
-        }
+        const double wfdc = sr.cwfdc * tc * tc;
+        const double irhoj = Vj * (UNIFORM ? tb.type[1].imass : tb.type[tj].imass);
+        const double q0 = sr.mred2 * (irhoi + irhoj) * rsq * wfdc * fast_rcp(rsq + sr.hc2eps);
+#pragma unroll
+        for (int k = 0; k < MAXS; k++)
+          if (k < co.nspecies) {
+            const double Cjk = k == 0 ? Cj0 : d.pCs[(size_t)j * co.nspecies + k];
+            double dq = sr.kappa[k] * (Cspec_i[k] - Cjk) * q0;
+            if (VARIANT == SPHBVF_TV) dq -= Vj * (Cspec_i[k] * ai + Cjk * aj) * wfdc;
+            Qs[k] += dq;
+          }
       }
     }
   }
@@ -483,21 +531,30 @@ __device__ __forceinline__ void cp_async4(int *smem_dst, const int *gsrc) {
 // per-atom output is written; for every neighbour that is a periodic image (shift s != 0) the force
 // F it exerts on atom i is obtained as the change of the force accumulator and -1/2 s (x) F is summed
 // into virial_out[6] (see sphbvf_virial in capi.cu for the derivation).
+// threads per CTA of the gather form: the elastic-solid instantiations (SOLIDS == 2) need more than the 168 registers
+// that 2 x 192 threads leave per thread (they spilled > 1 KB per thread into the neighbour loop): 2 x 128 threads at
+// up to 255 registers
+__host__ __device__ constexpr int pair_threads(int solids) { return solids == 2 ? 128 : PAIR_T; }
+
 // one owned atom of the gather form: the whole neighbour loop and the stores (myring = this thread's column of the
 // CTA's list-entry ring)
 template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL>
 __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, const PairTables &tb, const PairConsts &pc,
-                                          const PairRow *srow, int *myring, const int i, double *virial_out) {
-  PairAcc<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM> acc;
+                                          const PairRow *srow, const SpecRow *sspec, int *myring, double *mysol,
+                                          const int i, double *virial_out) {
+  constexpr int PTH = pair_threads(SOLIDS);
+  PairAcc<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, SOLIDS == 2, PTH> acc;
+  acc.sol = mysol;
   acc.init(d, co, tb, srow, i, d.pflags[i], d.prec[i].A, d.prec[i].B, d.prec[i].C);
+  if (SPECIES && !UNIFORM) acc.myspec = sspec + acc.ti * MAXT;
 
   double vir[6] = {0, 0, 0, 0, 0, 0};
-  auto visit = [&](const int ent, const Rec4 &Aj, const Rec4 &Bj, const Rec4 &Cj, const double rhoIj) {
+  auto visit = [&](const int ent, const Rec4 &Aj, const Rec4 &Bj, const Rec4 &Cj, const double rhoIj, const double Cj0) {
     const int j = ent & NEIGH_JMASK;
     const int tj = (ent >> NEIGH_JBITS) & 7;
     const bool sj = (ent >> 30) & 1;
     if (!VIRIAL) {
-      acc.visit(d, co, tb, pc, tj, sj, j, Aj.x, Aj.y, Aj.z, Aj.w, Bj.x, Bj.y, Bj.z, Bj.w, Cj.x, Cj.y, Cj.z, Cj.w, rhoIj);
+      acc.visit(d, co, tb, pc, tj, sj, j, Aj.x, Aj.y, Aj.z, Aj.w, Bj.x, Bj.y, Bj.z, Bj.w, Cj.x, Cj.y, Cj.z, Cj.w, rhoIj, Cj0);
       return;
     }
     const int g = j - d.nlocal;
@@ -506,7 +563,7 @@ __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, c
     if (sx == 0.0 && sy == 0.0 && sz == 0.0) return;
     double f0x, f0y, f0z, f1x, f1y, f1z;
     acc.force_now(f0x, f0y, f0z);
-    acc.visit(d, co, tb, pc, tj, sj, j, Aj.x, Aj.y, Aj.z, Aj.w, Bj.x, Bj.y, Bj.z, Bj.w, Cj.x, Cj.y, Cj.z, Cj.w, rhoIj);
+    acc.visit(d, co, tb, pc, tj, sj, j, Aj.x, Aj.y, Aj.z, Aj.w, Bj.x, Bj.y, Bj.z, Bj.w, Cj.x, Cj.y, Cj.z, Cj.w, rhoIj, Cj0);
     acc.force_now(f1x, f1y, f1z);
     const double Fx = f1x - f0x, Fy = f1y - f0y, Fz = f1z - f0z;
     vir[0] -= 0.5 * sx * Fx; vir[1] -= 0.5 * sy * Fy; vir[2] -= 0.5 * sz * Fz;
@@ -522,8 +579,8 @@ __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, c
   const int *np = d.neigh + i;
   const size_t stride = d.stride;
   auto fetch2 = [&](int k) {   // entries k, k+1 -> ring slots k % RING, (k+1) % RING; one group
-    if (k < nn) cp_async4(myring + (k % RING) * PAIR_T, np + (size_t)k * stride);
-    if (k + 1 < nn) cp_async4(myring + ((k + 1) % RING) * PAIR_T, np + (size_t)(k + 1) * stride);
+    if (k < nn) cp_async4(myring + (k % RING) * PTH, np + (size_t)k * stride);
+    if (k + 1 < nn) cp_async4(myring + ((k + 1) % RING) * PTH, np + (size_t)(k + 1) * stride);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   // groups allowed in flight after a wait: entries <= kk + 17 - 2 * PEND have landed
@@ -532,7 +589,7 @@ __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, c
   for (int k = 0; k < RING; k += 2) fetch2(k);
   asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries 0..3 landed
   int e0 = nn > 0 ? myring[0] : 0;
-  int e1 = nn > 1 ? myring[PAIR_T] : 0;
+  int e1 = nn > 1 ? myring[PTH] : 0;
   // Register pipeline: while the record of one neighbour is evaluated, the record of the next one is in flight.
   // ptxas puts all six record loads of the loop on ONE scoreboard, and a scoreboard is a counter: the first use of a
   // record waits until EVERY load issued before it has returned.  Issued in source order (next record's loads, then
@@ -542,11 +599,14 @@ __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, c
   // compiler cannot fold), so they are issued right after record k has arrived and have a whole visit to complete.
   Rec4 A0, B0, C0, A1, B1, C1;
   double D0 = 0.0, D1 = 0.0;   // rhoI_j of the Shepard numerator, part of the pipeline on filter steps
+  double S0 = 0.0, S1 = 0.0;   // C_j[0], part of the pipeline when species are transported
+  const int nsp = SPECIES ? co.nspecies : 0;
   auto gate = [&](const Rec4 &A) { const double g = acc.xi - A.x; return g != g ? 1 : 0; };
   {
     const Prec *p = d.prec + (e0 & NEIGH_JMASK);
     A0 = p->A; B0 = p->B; C0 = p->C;
     if (FILTER) D0 = d.pD[e0 & NEIGH_JMASK].x;
+    if (SPECIES) S0 = d.pCs[(size_t)(e0 & NEIGH_JMASK) * nsp];
   }
   for (int kk = 0; kk < nn; kk += 2) {
     {
@@ -554,19 +614,21 @@ __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, c
       const Prec *p = d.prec + j1;
       A1 = p->A; B1 = p->B; C1 = p->C;
       if (FILTER) D1 = d.pD[j1].x;
+      if (SPECIES) S1 = d.pCs[(size_t)j1 * nsp];
     }
     fetch2(kk + RING);   // slots of entries kk, kk+1: already in e0, e1
     asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");   // entries <= kk+5 landed
-    const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * PAIR_T] : 0;
-    const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * PAIR_T] : 0;
-    visit(e0, A0, B0, C0, D0);
+    const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * PTH] : 0;
+    const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * PTH] : 0;
+    visit(e0, A0, B0, C0, D0, S0);
     {
       const int j2 = (e2 & NEIGH_JMASK) + gate(A1);
       const Prec *p = d.prec + j2;
       A0 = p->A; B0 = p->B; C0 = p->C;
       if (FILTER) D0 = d.pD[j2].x;
+      if (SPECIES) S0 = d.pCs[(size_t)j2 * nsp];
     }
-    if (kk + 1 < nn) visit(e1, A1, B1, C1, D1);
+    if (kk + 1 < nn) visit(e1, A1, B1, C1, D1, S1);
     e0 = e2;
     e1 = e3;
   }
@@ -594,12 +656,15 @@ __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, c
   }
   if (SOLIDS == 2)
 #pragma unroll
-    for (int k = 0; k < 9; k++) d.ddev[9 * (size_t)i + k] = acc.si ? acc.ddev[k] : 0.0;
-  if (SPECIES)
-    for (int k = 0; k < co.nspecies; k++) d.Q[(size_t)i * co.nspecies + k] = acc.Qs[k];
+    for (int k = 0; k < 9; k++) d.ddev[9 * (size_t)i + k] = acc.si ? acc.ddev(k) : 0.0;
+  if (SPECIES) {
+#pragma unroll
+    for (int k = 0; k < MAXS; k++)
+      if (k < co.nspecies) d.Q[(size_t)i * co.nspecies + k] = acc.Qs[k];
+  }
 }
 
-// Gather-form kernel.  Two schedules of the chunks of PAIR_T consecutive atoms:
+// Gather-form kernel.  Two schedules of the chunks of PTH = pair_threads(SOLIDS) consecutive atoms:
 //   queues == nullptr (default): one CTA per chunk (chunk = blockIdx.x), the hardware hands CTAs to SMs as they free up, so the
 //     CTAs that share an SM work on unrelated parts of the brick and every CTA starts on a cold L1;
 //   queues != nullptr (SPHBVF_PAIR_SCHED=smid): PERSISTENT CTAs, two per SM, that pull chunks from a queue chosen by the SM they run
@@ -612,26 +677,33 @@ __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, c
 //     launch loses the hardware's dynamic balance (296 CTAs whose chunk costs differ by the wall / bulk mix) and pays a
 //     block-wide barrier pair plus an atomic round trip per chunk; kept as a switch, not the default.
 template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL = false>
-__global__ void __launch_bounds__(PAIR_T, PAIR_MINB)
+__global__ void __launch_bounds__(pair_threads(SOLIDS), PAIR_MINB)
 pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
             const PairConsts pc, const int *__restrict__ aorder, const int a0, const int a1, int *queues, const int nq,
             const int cpq, double *virial_out = nullptr) {
+  constexpr int PTH = pair_threads(SOLIDS);
   __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
-  __shared__ int ring[RING][PAIR_T];
+  __shared__ SpecRow sspec[(SPECIES && !UNIFORM) ? MAXT * MAXT : 1];
+  __shared__ int ring[RING][PTH];
+  __shared__ double ssol[SOLIDS == 2 ? 18 : 1][SOLIDS == 2 ? PTH : 1];   // devi / ddev columns of the threads
   __shared__ int s_chunk;
+  double *mysol = &ssol[0][SOLIDS == 2 ? threadIdx.x : 0];
   if (!UNIFORM) {
-    for (int q = threadIdx.x; q < MAXT * MAXT; q += blockDim.x) srow[q] = tb.row[q];
+    for (int q = threadIdx.x; q < MAXT * MAXT; q += blockDim.x) {
+      srow[q] = tb.row[q];
+      if (SPECIES) sspec[q] = tb.spec[q];
+    }
     __syncthreads();
   }
   int *myring = &ring[0][threadIdx.x];
   // atoms [a0, a1) of the launch, through the atom order when the pass is split (interior of the brick while the
   // halo is in flight, then the atoms that can see a ghost): consecutive positions stay consecutive atoms of a tile
   if (!queues) {
-    const int p = a0 + blockIdx.x * PAIR_T + threadIdx.x;
-    if (p < a1) pair_atom<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL>(d, co, tb, pc, srow, myring, aorder ? aorder[p] : p, virial_out);
+    const int p = a0 + blockIdx.x * PTH + threadIdx.x;
+    if (p < a1) pair_atom<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL>(d, co, tb, pc, srow, sspec, myring, mysol, aorder ? aorder[p] : p, virial_out);
     return;
   }
-  const int nchunks = (a1 - a0 + PAIR_T - 1) / PAIR_T;
+  const int nchunks = (a1 - a0 + PTH - 1) / PTH;
   unsigned smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
   const int q = (int)(smid % (unsigned)nq);
@@ -655,8 +727,8 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     __syncthreads();
     const int chunk = s_chunk;
     if (chunk >= nchunks) break;
-    const int p = a0 + chunk * PAIR_T + threadIdx.x;
-    if (p < a1) pair_atom<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL>(d, co, tb, pc, srow, myring, aorder ? aorder[p] : p, virial_out);
+    const int p = a0 + chunk * PTH + threadIdx.x;
+    if (p < a1) pair_atom<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL>(d, co, tb, pc, srow, sspec, myring, mysol, aorder ? aorder[p] : p, virial_out);
     asm volatile("cp.async.wait_all;" ::: "memory");   // the ring is reused by the next chunk
   }
 }
@@ -804,8 +876,9 @@ pair_tile_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_
           const bool sj = (e >> 15) & 1;
           const int j = NEEDJ ? gidx[slot] : 0;
           const double rhoIj = FILTER ? d.pD[j].x : 0.0;
+          const double Cj0 = SPECIES ? d.pCs[(size_t)j * co.nspecies] : 0.0;
           if (!VIRIAL) {
-            acc.visit(d, co, tb, pc, tj, sj, j, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y, g4.x, g4.y, g5.x, g5.y, rhoIj);
+            acc.visit(d, co, tb, pc, tj, sj, j, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y, g4.x, g4.y, g5.x, g5.y, rhoIj, Cj0);
           } else {
             const int gh = j - d.nlocal;
             if (gh >= 0) {
@@ -813,7 +886,7 @@ pair_tile_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_
               if (sx != 0.0 || sy != 0.0 || sz != 0.0) {
                 double f0x, f0y, f0z, f1x, f1y, f1z;
                 acc.force_now(f0x, f0y, f0z);
-                acc.visit(d, co, tb, pc, tj, sj, j, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y, g4.x, g4.y, g5.x, g5.y, rhoIj);
+                acc.visit(d, co, tb, pc, tj, sj, j, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y, g4.x, g4.y, g5.x, g5.y, rhoIj, Cj0);
                 acc.force_now(f1x, f1y, f1z);
                 const double Fx = f1x - f0x, Fy = f1y - f0y, Fz = f1z - f0z;
                 vir[0] -= 0.5 * sx * Fx; vir[1] -= 0.5 * sy * Fy; vir[2] -= 0.5 * sz * Fz;
@@ -865,7 +938,7 @@ pair_tile_kernel(const DevState d, const __grid_constant__ Grid g, const __grid_
     if (SOLIDS == 2) {
 #pragma unroll
       for (int k = 0; k < 9; k++) {
-        const double sk = octet_sum(acc.ddev[k]);
+        const double sk = octet_sum(acc.ddev(k));
         if (valid && sub == 0) d.ddev[9 * (size_t)i + k] = acc.si ? sk : 0.0;
       }
     }
@@ -913,15 +986,16 @@ static void launch_one(const DevState &d, const Coeffs &co, const PairTables &tb
     kern<<<ta.ntiles, PT_T, smem, st>>>(d, *ta.g, co, tb, ta.w->cell_start, ta.w->gcell_start, ta.w->gorder, ta.tile_list, pc, vout);
   } else {
     if (ta.a1 <= ta.a0) return;
-    const int nchunks = (ta.a1 - ta.a0 + PAIR_T - 1) / PAIR_T;
+    constexpr int PTH = pair_threads(SOLIDS);
+    const int nchunks = (ta.a1 - ta.a0 + PTH - 1) / PTH;
     if (ta.queues && nchunks > 4 * ta.nq) {
       // persistent schedule: 9/10 of the chunks in per-SM queues (contiguous runs of tiles), the rest in a shared one
       const int cpq = (int)(0.9 * nchunks / ta.nq);
       cudaMemsetAsync(ta.queues, 0, sizeof(int) * (ta.nq + 1), st);
-      pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<PAIR_MINB * ta.nq, PAIR_T, 0, st>>>(
+      pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<PAIR_MINB * ta.nq, PTH, 0, st>>>(
           d, co, tb, pc, ta.aorder, ta.a0, ta.a1, ta.queues, ta.nq, cpq, vout);
     } else {
-      pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<nchunks, PAIR_T, 0, st>>>(
+      pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<nchunks, PTH, 0, st>>>(
           d, co, tb, pc, ta.aorder, ta.a0, ta.a1, nullptr, 1, 0, vout);
     }
   }
@@ -999,6 +1073,7 @@ static PairConsts consts_of(const PairFlags &pf) {
   pc.rand_pref = pf.rand_pref;
   pc.seed = pf.seed;
   pc.ntimestep = pf.ntimestep;
+  pc.elmask = pf.with_dev;
   return pc;
 }
 

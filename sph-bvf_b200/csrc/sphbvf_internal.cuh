@@ -186,7 +186,7 @@ struct NeighWork;
 struct PairFlags {
   int filter_step;   // Shepard sums rhoAux1/2 are consumed this step
   int uniform;       // every type pair shares h, eta and the masses are equal
-  int with_dev;      // deviatoric tensors may be non-zero (elastic solids present)
+  int with_dev;      // deviatoric tensors may be non-zero (elastic solids present): bit t = solid atoms of type t can carry stress
   int any_solid;     // some atom has solid_tag == 1
   double damp;       // density-diffusion amplitude of the fsi variant (0 otherwise)
   int random;        // stochastic stress term on (some e != 0 and sphbvf_set_random was called)

@@ -381,6 +381,7 @@ void SphbvfLmp::start()
       return sphbvf_setup_neighbors(c);
     });
   }
+  if (getenv("SPHBVF_PROFILE")) all([&](sphbvf_ctx *c, int) { return sphbvf_set_profiling(c, 1); });
   nlocal_uploaded = n;
   host_mask = 0;
   ndownloads = ndevice_thermo = nskipped = 0;
@@ -602,6 +603,23 @@ void SphbvfLmp::stop()
              ndownloads, nskipped, ndevice_thermo, nbytes_down);
     if (screen) fputs(msg, screen);
     if (logfile) fputs(msg, logfile);
+  }
+  if (getenv("SPHBVF_PROFILE") && comm->me == 0) {
+    // per-kernel-family device time of GPU 0 (CUDA events on the context's stream, sphbvf_set_profiling)
+    static const char *fam[] = {"pair", "initial_integrate", "final_integrate", "neighbor_rebuild", "pack_halo", "fixes",
+                                "final_initial_pack_fused"};
+    sphbvf_ctx *c0 = nranks == 1 ? ctx : ctxs[0];
+    std::string msg = "sphbvf profile (GPU 0, ms / launches):";
+    for (int k = 0; k < 7; k++) {
+      long nl = 0;
+      const double ms = sphbvf_kernel_ms(c0, k, &nl);
+      char one[96];
+      snprintf(one, sizeof one, " %s %.3f / %ld;", fam[k], ms, nl);
+      msg += one;
+    }
+    msg += "\n";
+    if (screen) fputs(msg.c_str(), screen);
+    if (logfile) fputs(msg.c_str(), logfile);
   }
   to_host();
   if (nranks == 1) sphbvf_destroy(ctx);
