@@ -7,11 +7,10 @@
 
 using namespace LAMMPS_NS;
 
-void LAMMPS_NS::sphbvf_fetch_for_compute(unsigned mask)
-{
-  SphbvfLmp *engine = SphbvfLmp::peek();
-  if (engine && engine->active()) engine->fetch(mask);
-}
+#include "atom.h"
+
+/* the host array behind the column: allocate it if it is a lazy mirror, refresh it if a device context holds newer data */
+#define sphbvf_fetch_for_compute(mask) SphbvfLmp::host_fields(atom, mask)
 
 /* each compute reads ONE column of class Atom (stress: the pressure and the deviatoric tensor) */
 

@@ -3,8 +3,9 @@
    (compute_ssa_tsdpd_rho_atom.cpp:61-87, ..._phi_atom.cpp:61-87, ..._p_atom.cpp:61-87, ..._C_atom.cpp:64-92,
    ..._stress_atom.cpp:40-41,66-100).  Same arguments, same numbers: each class IS the reference compute; before it
    reads its column of class Atom it asks the engine for exactly that column (SphbvfLmp::fetch), so a dump step of
-   a /cuda run copies the fields its dump lists and nothing else.  Without an active device
-   context they are the reference computes.
+   a /cuda run copies the fields its dump lists and nothing else; with atom_style
+   ssa_tsdpd/atomic/cuda that request is also what allocates the host array.  Without a device context they are
+   the reference computes.
 ------------------------------------------------------------------------- */
 
 #ifdef COMPUTE_CLASS
@@ -28,7 +29,6 @@ ComputeStyle(ssa_tsdpd/stress/atom/cuda,ComputeSsaTsdpdStressAtomCuda)
 
 namespace LAMMPS_NS {
 
-void sphbvf_fetch_for_compute(unsigned mask);   // SphbvfLmp::peek()->fetch(mask) if a device context is active
 
 #define SPHBVF_ATOM_COMPUTE(Name, Base)                                              \
   class Name : public Base {                                                         \

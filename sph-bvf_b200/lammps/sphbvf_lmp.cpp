@@ -11,6 +11,7 @@
 #include <string>
 #include <thread>
 #include "sphbvf_lmp.h"
+#include "atom_vec_ssa_tsdpd_atomic_cuda.h"
 #include "atom.h"
 #include "comm.h"
 #include "domain.h"
@@ -128,13 +129,22 @@ SphbvfLmp::SphbvfLmp(LAMMPS *lmp) : Pointers(lmp)
   nbytes_down = 0;
   nranks = 1;
   workers = NULL;
+  parked = false;
 }
 
 SphbvfLmp::~SphbvfLmp()
 {
-  if (ctxs.size() > 1 && workers) workers->run([&](int r) { sphbvf_destroy(ctxs[r]); return 0; });
-  else if (ctxs.size() == 1) sphbvf_destroy(ctxs[0]);
+  destroy_contexts();
   delete workers;
+}
+
+void SphbvfLmp::destroy_contexts()
+{
+  if (ctxs.size() > 1 && workers) workers->run([&](int r) { sphbvf_destroy(ctxs[r]); return 0; });   // on the thread that owns the device
+  else if (ctxs.size() == 1) sphbvf_destroy(ctxs[0]);
+  ctxs.clear();
+  ctx = NULL;
+  parked = false;
 }
 
 /* f(ctx_r, r) on every rank at the same time; the first failing rank's message becomes the LAMMPS error */
@@ -214,7 +224,8 @@ void SphbvfLmp::start()
     error->all(FLERR, "SSA species are not supported by the /cuda styles");   // serial-only upstream as well
   if (sphbvf_device_count() < 1)
     error->all(FLERR, "No CUDA device: the /cuda styles have no CPU fallback (drop -sf cuda)");
-  if (ctx) stop();
+  if (ctx && !parked) stop();
+  if (ctx) destroy_contexts();   // the parked state of the previous run: the host arrays are authoritative now
 
   const int S = atom->num_sdpd_species, ntypes = atom->ntypes;
   sphbvf_config cfg;
@@ -248,9 +259,18 @@ void SphbvfLmp::start()
   }
   nranks = MAX(1, MIN(want, sphbvf_device_count()));
   {
+    // brick grid: procmap.cpp's surface-minimising factorisation, or SPHBVF_GRID=PxxPyxPz.  (The `processors`
+    // command cannot carry it: with one MPI rank comm.cpp:325-327 rejects any grid whose product is not 1.)
     double prd[3] = {domain->xprd, domain->yprd, domain->zprd};
     int grid[3] = {1, 1, 1};
-    check(sphbvf_proc_grid(nranks, cfg.dim, prd, grid));
+    const char *genv = getenv("SPHBVF_GRID");
+    if (genv) {
+      if (sscanf(genv, "%dx%dx%d", &grid[0], &grid[1], &grid[2]) != 3 || grid[0] < 1 || grid[1] < 1 || grid[2] < 1 ||
+          (cfg.dim == 2 && grid[2] != 1) || grid[0] * grid[1] * grid[2] > sphbvf_device_count())
+        error->all(FLERR, "SPHBVF_GRID must be PxxPyxPz with Px*Py*Pz <= number of GPUs (Pz = 1 in 2d)");
+      nranks = grid[0] * grid[1] * grid[2];
+    } else
+      check(sphbvf_proc_grid(nranks, cfg.dim, prd, grid));
     for (int k = 0; k < 3; k++) cfg.procgrid[k] = grid[k];
   }
   cfg.nranks = nranks;
@@ -430,6 +450,39 @@ static double *host_array(Atom *atom, unsigned bit)
   return NULL;
 }
 
+/* lazy host mirrors (atom_style ssa_tsdpd/atomic/cuda): the arrays of the pair-sweep outputs named in mask */
+
+namespace {
+const struct { unsigned bit; int derived; } lazy_map[] = {
+  {SphbvfLmp::HF_DRHO, AtomVecSsaTsdpdAtomicCuda::DRHO}, {SphbvfLmp::HF_PHI, AtomVecSsaTsdpdAtomicCuda::PHI},
+  {SphbvfLmp::HF_ND, AtomVecSsaTsdpdAtomicCuda::NUMBER_DENSITY}, {SphbvfLmp::HF_NW, AtomVecSsaTsdpdAtomicCuda::NW},
+  {SphbvfLmp::HF_DDV, AtomVecSsaTsdpdAtomicCuda::DDV}, {SphbvfLmp::HF_RAUX1, AtomVecSsaTsdpdAtomicCuda::RHOAUX1},
+  {SphbvfLmp::HF_RAUX2, AtomVecSsaTsdpdAtomicCuda::RHOAUX2}, {SphbvfLmp::HF_DDEV, AtomVecSsaTsdpdAtomicCuda::DDEV},
+  {SphbvfLmp::HF_DDX, AtomVecSsaTsdpdAtomicCuda::DDX}, {SphbvfLmp::HF_PNEW, AtomVecSsaTsdpdAtomicCuda::PNEW},
+  {SphbvfLmp::HF_Q, AtomVecSsaTsdpdAtomicCuda::Q}};
+}
+
+void SphbvfLmp::materialize(unsigned mask)
+{
+  AtomVecSsaTsdpdAtomicCuda *av = dynamic_cast<AtomVecSsaTsdpdAtomicCuda *>(atom->avec);
+  if (!av) return;   // stock atom style: everything is allocated
+  for (size_t q = 0; q < sizeof lazy_map / sizeof lazy_map[0]; q++)
+    if (mask & lazy_map[q].bit) av->materialize(lazy_map[q].derived);
+}
+
+void SphbvfLmp::host_fields(Atom *atom, unsigned mask)
+{
+  if (the_engine) {
+    the_engine->materialize(mask);
+    the_engine->fetch(mask);
+    return;
+  }
+  AtomVecSsaTsdpdAtomicCuda *av = dynamic_cast<AtomVecSsaTsdpdAtomicCuda *>(atom->avec);
+  if (!av) return;
+  for (size_t q = 0; q < sizeof lazy_map / sizeof lazy_map[0]; q++)
+    if (mask & lazy_map[q].bit) av->materialize(lazy_map[q].derived);
+}
+
 void SphbvfLmp::fetch(unsigned want)
 {
   if (!ctx) return;
@@ -441,7 +494,12 @@ void SphbvfLmp::fetch(unsigned want)
   host_mask |= absent;
   unsigned need = want & HF_ALL & ~host_mask;
   if (!need) return;
-  if (n != nlocal_uploaded) error->one(FLERR, "Atom count changed during a /cuda run");
+  materialize(need);
+  if (n != nlocal_uploaded) {
+    if (!parked) error->one(FLERR, "Atom count changed during a /cuda run");
+    destroy_contexts();   // atoms were created or deleted after the run: its device state describes another system
+    return;
+  }
   if (n) {
     if (nranks > 1) fetch_multi(need);
     else {
@@ -596,6 +654,10 @@ unsigned SphbvfLmp::output_fields(bool at_setup)
 void SphbvfLmp::stop()
 {
   if (!ctx) return;
+  if (parked) {   // second stop (next run's setup, clear): the parked state goes away
+    destroy_contexts();
+    return;
+  }
   if (getenv("SPHBVF_VERBOSE") && comm->me == 0) {
     char msg[256];
     snprintf(msg, sizeof msg, "sphbvf: " BIGINT_FORMAT " full downloads, " BIGINT_FORMAT " output steps served from the device, "
@@ -621,9 +683,25 @@ void SphbvfLmp::stop()
     if (screen) fputs(msg.c_str(), screen);
     if (logfile) fputs(msg.c_str(), logfile);
   }
+  // lazy host mirrors: copy back the state and the outputs that are mirrored already, keep the rest fetchable
+  AtomVecSsaTsdpdAtomicCuda *av = dynamic_cast<AtomVecSsaTsdpdAtomicCuda *>(atom->avec);
+  if (av && getenv("SPHBVF_VERBOSE") && comm->me == 0) {
+    char msg[256];
+    snprintf(msg, sizeof msg, "sphbvf: host mirrors of %d of the %d pair-sweep output arrays were allocated "
+             "(atom_style ssa_tsdpd/atomic/cuda), %d bytes of host arrays per atom slot\n",
+             (int)AtomVecSsaTsdpdAtomicCuda::NDERIVED - av->nlazy(), (int)AtomVecSsaTsdpdAtomicCuda::NDERIVED,
+             (int)(av->memory_usage() / MAX(1, atom->nmax)));
+    if (screen) fputs(msg, screen);
+    if (logfile) fputs(msg, logfile);
+  }
+  if (av && av->nlazy() > 0) {
+    unsigned want = HF_ALL;
+    for (size_t q = 0; q < sizeof lazy_map / sizeof lazy_map[0]; q++)
+      if (!av->materialized(lazy_map[q].derived)) want &= ~lazy_map[q].bit;
+    fetch(want);
+    parked = true;
+    return;
+  }
   to_host();
-  if (nranks == 1) sphbvf_destroy(ctx);
-  else workers->run([&](int r) { sphbvf_destroy(ctxs[r]); return 0; });   // on the thread that owns the device
-  ctxs.clear();
-  ctx = NULL;
+  destroy_contexts();
 }

@@ -559,3 +559,47 @@ def test_thermo_only_steps_need_no_download(monkeypatch):
                 continue
             sc = max(np.abs(a[:, k]).max(), 1e-300)
             assert np.abs(a[:, k] - b[:, k]).max() <= TOL * sc, (s, c)
+
+
+# ---------------------------------------------------------------------------------------------
+# atom_style ssa_tsdpd/atomic/cuda (picked by -sf cuda): the host arrays of the pair-sweep outputs are allocated when
+# something on the host first asks for them, also AFTER the run (the device contexts are parked, not destroyed)
+# ---------------------------------------------------------------------------------------------
+def test_lazy_host_mirrors_and_late_fetch(monkeypatch):
+    if not (os.path.exists(REF) and os.path.exists(CUDA)):
+        pytest.skip("lmp_serial / lmp_cuda not built (make -C oracle ref; make -C sph-bvf_b200/lammps)")
+    # the dump lists positions, velocities and rho only; phi and drho are first asked for by write_dump after the run,
+    # number_density by nobody
+    deck = CAVITY3D.replace("vx vy vz fx fy fz c_crho c_cphi", "vx vy vz c_crho")
+    assert deck != CAVITY3D
+    deck += ("compute pa all property/atom drho\n"
+             "write_dump all custom late.txt id x y z c_cphi c_pa modify sort id format float %.17g\n")
+    wd_ref, _ = run_deck(REF, deck, [])
+    monkeypatch.setenv("SPHBVF_VERBOSE", "1")
+    wd_cuda, out = run_deck(CUDA, deck, ["-sf", "cuda"])
+    ln = [l for l in out.splitlines() if l.startswith("sphbvf: host mirrors")]
+    assert ln, out[-2000:]
+    m = re.search(r"host mirrors of (\d+) of the (\d+) pair-sweep output arrays were allocated .* (\d+) bytes", ln[-1])
+    assert m, ln[-1]
+    # at the end of the run nothing derived had been asked for: 0 of 21 arrays, < 300 B per atom on the host
+    # (upstream's style: ~ 830 B per atom)
+    natoms = 14 ** 3
+    assert int(m.group(1)) == 0 and int(m.group(2)) == 21, ln[-1]
+    assert 200 < int(m.group(3)) < 300, ln[-1]
+    ref, got = read_dumps(wd_ref), read_dumps(wd_cuda)
+    assert sorted(ref) == sorted(got) and len(ref) >= 3
+    for s in ref:
+        for k, c in enumerate(ref[s][0]):
+            sc = max(np.abs(ref[s][1][:, k]).max(), 1e-300)
+            assert np.abs(ref[s][1][:, k] - got[s][1][:, k]).max() <= TOL * sc, (s, c)
+
+    def late(wd):
+        lines = open(os.path.join(wd, "late.txt")).read().splitlines()
+        k = next(i for i, l in enumerate(lines) if l.startswith("ITEM: ATOMS"))
+        return np.array([[float(v) for v in l.split()] for l in lines[k + 1:]])
+    a, b = late(wd_ref), late(wd_cuda)
+    assert a.shape == b.shape == (natoms, 6)
+    for k, c in enumerate(("id", "x", "y", "z", "phi", "drho")):
+        sc = np.abs(a[:, k]).max()
+        assert sc > 0, c
+        assert np.abs(a[:, k] - b[:, k]).max() <= TOL * sc, c

@@ -41,4 +41,11 @@ for n in (56, 106, 206, 412):
     dt = time.perf_counter() - t0
     print("cavity2d n=%d: %d atoms, %.1f us/step, %.3g atom-steps/s, %.1f launches/step, %d rebuilds" % (
         n, n * n, dt / 2000 * 1e6, n * n * 2000 / dt, (eng.launch_count - l0) / 2000.0, eng.nbuilds))
+    # second pass with CUDA events around every kernel family (serialises nothing, but adds two event records per
+    # family call): where the device time of a step goes
+    eng.profiling(True)
+    eng.run(400)
+    eng.sync()
+    fam = ["pair", "initial_integrate", "final_integrate", "neighbor_rebuild", "pack_halo", "fixes", "final_initial_pack_fused"]
+    print("   device us/step:", ", ".join("%s %.2f (%d)" % (f, eng.kernel_ms(k)[0] * 1e3 / 400, eng.kernel_ms(k)[1]) for k, f in enumerate(fam)))
     eng.close()
