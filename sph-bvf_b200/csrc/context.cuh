@@ -36,6 +36,7 @@ struct sphbvf_ctx {
   long pend_step = 0;
   int *pair_queues = nullptr;  // 2 x (nq + 1) chunk counters of the gather form's persistent schedule (two concurrent launches)
   int pair_nq = 1;             // queues = SMs of the device
+  bool pair_warp = false;      // chunks are drawn per warp (32 atoms) instead of per CTA
   int flags_dirty = 0;         // bit 0: e / dev uploaded, bit 1: type / solid_tag / fixed_tag uploaded since the flags were derived
   int pair_pref = 0;           // 0: gather form (default), 1: tile form when it fits (SPHBVF_PAIR=tile)
   int smem_optin = 0;          // cudaDevAttrMaxSharedMemoryPerBlockOptin of the device

@@ -703,10 +703,42 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     if (p < a1) pair_atom<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL>(d, co, tb, pc, srow, sspec, myring, mysol, aorder ? aorder[p] : p, virial_out);
     return;
   }
-  const int nchunks = (a1 - a0 + PTH - 1) / PTH;
   unsigned smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
   const int q = (int)(smid % (unsigned)nq);
+  if (cpq < 0) {
+    // SPHBVF_PAIR_SCHED=warp: the same SM-local queues, but every WARP pulls its own chunks of 32 consecutive atoms
+    // (-cpq per queue).  No block-wide barrier, no idle warps behind the slowest one of a 192-atom chunk, and the
+    // ticket for the next chunk is drawn BEFORE the current chunk is worked on, so the atomic's round trip hides
+    // behind ~40 us of work; the warps of an SM walk through one run of tiles together (shared L1 lines).
+    const int wcpq = -cpq, lane = threadIdx.x & 31;
+    const int nw = (a1 - a0 + 31) / 32, ntail = nw - nq * wcpq;
+    auto draw = [&]() { return lane == 0 ? atomicAdd(&queues[q], 1) : 0; };   // may overshoot wcpq: only compared
+    int ticket = draw();
+    for (;;) {
+      int c = __shfl_sync(0xffffffffu, ticket, 0), chunk = nw;
+      if (c < wcpq) chunk = q * wcpq + c;
+      else {
+        if (lane == 0) {   // own queue empty: the shared tail, then other SMs' queues
+          if (queues[nq] < ntail && (c = atomicAdd(&queues[nq], 1)) < ntail) chunk = nq * wcpq + c;
+          else
+            for (int k = 1; k < nq; k++) {
+              const int qq = (q + k) % nq;
+              if (queues[qq] < wcpq && (c = atomicAdd(&queues[qq], 1)) < wcpq) { chunk = qq * wcpq + c; break; }
+            }
+        }
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+      }
+      if (chunk >= nw) break;
+      ticket = draw();
+      const int p = a0 + chunk * 32 + lane;
+      if (p < a1) pair_atom<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL>(d, co, tb, pc, srow, sspec, myring, mysol, aorder ? aorder[p] : p, virial_out);
+      asm volatile("cp.async.wait_all;" ::: "memory");   // the ring columns are reused by the next chunk
+      __syncwarp();
+    }
+    return;
+  }
+  const int nchunks = (a1 - a0 + PTH - 1) / PTH;
   for (;;) {
     __syncthreads();   // s_chunk of the previous round has been read by everyone
     if (threadIdx.x == 0) {
@@ -988,12 +1020,14 @@ static void launch_one(const DevState &d, const Coeffs &co, const PairTables &tb
     if (ta.a1 <= ta.a0) return;
     constexpr int PTH = pair_threads(SOLIDS);
     const int nchunks = (ta.a1 - ta.a0 + PTH - 1) / PTH;
-    if (ta.queues && nchunks > 4 * ta.nq) {
-      // persistent schedule: 9/10 of the chunks in per-SM queues (contiguous runs of tiles), the rest in a shared one
-      const int cpq = (int)(0.9 * nchunks / ta.nq);
-      cudaMemsetAsync(ta.queues, 0, sizeof(int) * (ta.nq + 1), st);
-      pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<PAIR_MINB * ta.nq, PTH, 0, st>>>(
-          d, co, tb, pc, ta.aorder, ta.a0, ta.a1, ta.queues, ta.nq, cpq, vout);
+    const int nq = ta.nq < 0 ? -ta.nq : ta.nq;
+    if (ta.queues && nchunks > 4 * nq) {
+      // persistent schedule: 9/10 of the chunks in per-SM queues (contiguous runs of tiles), the rest in a shared one;
+      // nq < 0 (SPHBVF_PAIR_SCHED=warp): chunks of one warp (32 atoms) drawn per warp, passed as a negative count
+      const int cpq = ta.nq < 0 ? -(int)(0.9 * ((ta.a1 - ta.a0 + 31) / 32) / nq) : (int)(0.9 * nchunks / nq);
+      cudaMemsetAsync(ta.queues, 0, sizeof(int) * (nq + 1), st);
+      pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<PAIR_MINB * nq, PTH, 0, st>>>(
+          d, co, tb, pc, ta.aorder, ta.a0, ta.a1, ta.queues, nq, cpq, vout);
     } else {
       pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<nchunks, PTH, 0, st>>>(
           d, co, tb, pc, ta.aorder, ta.a0, ta.a1, nullptr, 1, 0, vout);

@@ -68,3 +68,28 @@ def test_lattice_matches_oracle(n, delay, nsteps):
         n, n ** 3, nsteps, eng.nbuilds, {k: "%.1e" % v for k, v in worst.items()}))
     eng.close()
     orc.close()
+
+
+@pytest.mark.parametrize("sched", ["smid", "warp"])
+def test_persistent_schedules_are_bitwise_the_default(sched, monkeypatch):
+    """SPHBVF_PAIR_SCHED=smid / warp (persistent CTAs pulling 192-atom / 32-atom chunks from SM-local queues) only
+    change WHICH thread evaluates an atom, never the order of its neighbour sum: every pair-pass output must be
+    bit-identical to the one-CTA-per-chunk launch.  64^3 = 1366 chunks, past the 4 x SMs threshold below which the
+    persistent launch is not used."""
+    import bench
+    pkg = load_package()
+    meta = bench.cavity_meta(64)
+    a = bench.cavity_atoms(meta, meta["boxlo"], meta["boxhi"])
+    out = {}
+    for mode in ("grid", sched):
+        monkeypatch.setenv("SPHBVF_PAIR_SCHED", mode)
+        eng = pkg.Engine(meta)
+        eng.set_atoms(a["tag"], a["type"], a["mask"], a["solid"], a["fixed"], a["x"], a["v"], a["rho"], a["e"])
+        eng.set_run_length(10 ** 6)
+        eng.setup()
+        eng.run(21)     # two rebuilds and the Shepard-filter step 20 (the FILTER instantiation)
+        out[mode] = {f: eng.get(f) for f in FIELDS}
+        assert eng.nbuilds >= 2
+        eng.close()
+    for f in FIELDS:
+        assert np.array_equal(out["grid"][f], out[sched][f]), f
