@@ -538,10 +538,20 @@ __host__ __device__ constexpr int pair_threads(int solids) { return solids == 2 
 
 // one owned atom of the gather form: the whole neighbour loop and the stores (myring = this thread's column of the
 // CTA's list-entry ring)
-template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL>
+// LANES > 1 (small systems, pair_split_kernel): LANES adjacent lanes share atom i; lane `sub` takes the entries
+// sub, sub + LANES, ... of its list and the partial sums meet in an xor butterfly before lane 0 stores.  `valid` = false
+// pads the last warp: such a lane visits nothing and stores nothing but takes part in the shuffles.
+template <int LANES>
+__device__ __forceinline__ double lane_sum(double x) {
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL, int LANES = 1>
 __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, const PairTables &tb, const PairConsts &pc,
                                           const PairRow *srow, const SpecRow *sspec, int *myring, double *mysol,
-                                          const int i, double *virial_out) {
+                                          const int i, double *virial_out, const int sub = 0, const bool valid = true) {
   constexpr int PTH = pair_threads(SOLIDS);
   PairAcc<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, SOLIDS == 2, PTH> acc;
   acc.sol = mysol;
@@ -575,9 +585,10 @@ __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, c
   // entries RING rows ahead into a shared-memory ring with cp.async (no registers, no barrier:
   // a thread only ever reads the slots it wrote).  The records of neighbour k+1 are requested
   // before neighbour k is evaluated.
-  const int nn = d.numneigh[i];
-  const int *np = d.neigh + i;
-  const size_t stride = d.stride;
+  const int nn_all = valid ? d.numneigh[i] : 0;
+  const int nn = LANES == 1 ? nn_all : (nn_all > sub ? (nn_all - sub + LANES - 1) / LANES : 0);
+  const int *np = d.neigh + i + (LANES == 1 ? (size_t)0 : (size_t)sub * d.stride);
+  const size_t stride = d.stride * LANES;
   auto fetch2 = [&](int k) {   // entries k, k+1 -> ring slots k % RING, (k+1) % RING; one group
     if (k < nn) cp_async4(myring + (k % RING) * PTH, np + (size_t)k * stride);
     if (k + 1 < nn) cp_async4(myring + ((k + 1) % RING) * PTH, np + (size_t)(k + 1) * stride);
@@ -640,6 +651,27 @@ __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, c
       if (vir[q] != 0.0) atomicAdd(virial_out + q, vir[q]);
     return;
   }
+  if (LANES > 1) {
+    acc.fx = lane_sum<LANES>(acc.fx); acc.fy = lane_sum<LANES>(acc.fy); acc.fz = lane_sum<LANES>(acc.fz);
+    acc.spi = lane_sum<LANES>(acc.spi);
+    acc.drho = lane_sum<LANES>(acc.drho); acc.nd = lane_sum<LANES>(acc.nd); acc.rA2 = lane_sum<LANES>(acc.rA2);
+    if (FILTER) acc.rA1 = lane_sum<LANES>(acc.rA1);
+    acc.ddvx = lane_sum<LANES>(acc.ddvx); acc.ddvy = lane_sum<LANES>(acc.ddvy); acc.ddvz = lane_sum<LANES>(acc.ddvz);
+    if (SOLIDS) {
+      acc.phi = lane_sum<LANES>(acc.phi);
+      acc.nwx = lane_sum<LANES>(acc.nwx); acc.nwy = lane_sum<LANES>(acc.nwy); acc.nwz = lane_sum<LANES>(acc.nwz);
+    }
+    if (VARIANT != SPHBVF_TV) {
+      acc.ddxx = lane_sum<LANES>(acc.ddxx); acc.ddxy = lane_sum<LANES>(acc.ddxy); acc.ddxz = lane_sum<LANES>(acc.ddxz);
+    }
+    if (SOLIDS == 2)
+#pragma unroll
+      for (int k = 0; k < 9; k++) acc.ddev(k) = lane_sum<LANES>(acc.ddev(k));
+    if (SPECIES)
+#pragma unroll
+      for (int k = 0; k < MAXS; k++) acc.Qs[k] = lane_sum<LANES>(acc.Qs[k]);
+    if (sub != 0 || !valid) return;
+  }
   const double ddvc = 10.0 * 7.0 * co.B[acc.ti];
   const size_t i3 = 3 * (size_t)i;
   d.f[i3] = fma(acc.spi, acc.vxi, acc.fx); d.f[i3 + 1] = fma(acc.spi, acc.vyi, acc.fy); d.f[i3 + 2] = fma(acc.spi, acc.vzi, acc.fz);
@@ -676,7 +708,13 @@ __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, c
 //     gpurun_out/r2g_*): L1 sector hit rate 84 -> 89 %, L1 data pipe 80 -> 71 %, but 6.08 instead of 5.66 ms -- the
 //     launch loses the hardware's dynamic balance (296 CTAs whose chunk costs differ by the wall / bulk mix) and pays a
 //     block-wide barrier pair plus an atomic round trip per chunk; kept as a switch, not the default.
-template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL = false>
+// PERSIST is a template parameter so that the default launch carries none of the queue code (three inlined copies of
+// the neighbour loop in one kernel cost the species instantiations up to 150 bytes of extra spills); the persistent
+// schedules exist for the instantiations without species, elastic solids, noise or virial (can_persist).
+template <bool SPECIES, int SOLIDS, bool RANDOM, bool VIRIAL>
+struct CanPersist { static constexpr bool value = !SPECIES && SOLIDS < 2 && !RANDOM && !VIRIAL; };
+
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM, bool VIRIAL = false, bool PERSIST = false>
 __global__ void __launch_bounds__(pair_threads(SOLIDS), PAIR_MINB)
 pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
             const PairConsts pc, const int *__restrict__ aorder, const int a0, const int a1, int *queues, const int nq,
@@ -698,7 +736,7 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
   int *myring = &ring[0][threadIdx.x];
   // atoms [a0, a1) of the launch, through the atom order when the pass is split (interior of the brick while the
   // halo is in flight, then the atoms that can see a ghost): consecutive positions stay consecutive atoms of a tile
-  if (!queues) {
+  if (!PERSIST) {
     const int p = a0 + blockIdx.x * PTH + threadIdx.x;
     if (p < a1) pair_atom<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL>(d, co, tb, pc, srow, sspec, myring, mysol, aorder ? aorder[p] : p, virial_out);
     return;
@@ -763,6 +801,39 @@ pair_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_co
     if (p < a1) pair_atom<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL>(d, co, tb, pc, srow, sspec, myring, mysol, aorder ? aorder[p] : p, virial_out);
     asm volatile("cp.async.wait_all;" ::: "memory");   // the ring is reused by the next chunk
   }
+}
+
+// Gather form for SMALL systems (the reference's shipped decks: 3 k - 42 k atoms).  With one thread per atom such a
+// launch leaves most of the GPU empty and its duration is the latency of ONE thread's serial walk over its neighbours
+// (16.6 us for the 3 136-atom cavity: ~20 visits x ~1 600 cycles of dependent entry -> record -> arithmetic).  Here
+// PAIR_SPLIT adjacent lanes share an atom and each walks a quarter of its list (same pipeline, same arithmetic body);
+// the sums meet in a butterfly.  Only the summation order differs from pair_kernel.
+#ifndef PAIR_SPLIT
+#define PAIR_SPLIT 4
+#endif
+template <int VARIANT, bool SPECIES, int SOLIDS, bool UNIFORM, bool FILTER, bool RANDOM>
+__global__ void __launch_bounds__(pair_threads(SOLIDS), PAIR_MINB)
+pair_split_kernel(const DevState d, const __grid_constant__ Coeffs co, const __grid_constant__ PairTables tb,
+                  const PairConsts pc, const int *__restrict__ aorder, const int a0, const int a1) {
+  constexpr int PTH = pair_threads(SOLIDS);
+  __shared__ PairRow srow[UNIFORM ? 1 : MAXT * MAXT];
+  __shared__ SpecRow sspec[(SPECIES && !UNIFORM) ? MAXT * MAXT : 1];
+  __shared__ int ring[RING][PTH];
+  __shared__ double ssol[SOLIDS == 2 ? 18 : 1][SOLIDS == 2 ? PTH : 1];
+  double *mysol = &ssol[0][SOLIDS == 2 ? threadIdx.x : 0];
+  if (!UNIFORM) {
+    for (int q = threadIdx.x; q < MAXT * MAXT; q += blockDim.x) {
+      srow[q] = tb.row[q];
+      if (SPECIES) sspec[q] = tb.spec[q];
+    }
+    __syncthreads();
+  }
+  const int t = blockIdx.x * PTH + threadIdx.x;
+  const int p = a0 + t / PAIR_SPLIT;
+  const bool valid = p < a1;
+  const int pp = valid ? p : a0;
+  pair_atom<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, false, PAIR_SPLIT>(
+      d, co, tb, pc, srow, sspec, &ring[0][threadIdx.x], mysol, aorder ? aorder[pp] : pp, nullptr, t % PAIR_SPLIT, valid);
 }
 
 // ==========================================================================================
@@ -1021,13 +1092,22 @@ static void launch_one(const DevState &d, const Coeffs &co, const PairTables &tb
     constexpr int PTH = pair_threads(SOLIDS);
     const int nchunks = (ta.a1 - ta.a0 + PTH - 1) / PTH;
     const int nq = ta.nq < 0 ? -ta.nq : ta.nq;
-    if (ta.queues && nchunks > 4 * nq) {
+    // small launches: PAIR_SPLIT lanes per atom (SPHBVF_PAIR_LANES=1 never, =4 always; default: up to split_max atoms)
+    static const int split_max = [] { const char *e = getenv("SPHBVF_PAIR_LANES"); return !e ? 65536 : (atoi(e) > 1 ? 0x7fffffff : 0); }();
+    if (!VIRIAL && ta.a1 - ta.a0 <= split_max) {
+      if constexpr (!VIRIAL) {
+        const long nthreads = (long)(ta.a1 - ta.a0) * PAIR_SPLIT;
+        pair_split_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM><<<(int)((nthreads + PTH - 1) / PTH), PTH, 0, st>>>(
+            d, co, tb, pc, ta.aorder, ta.a0, ta.a1);
+      }
+    } else if (CanPersist<SPECIES, SOLIDS, RANDOM, VIRIAL>::value && ta.queues && nchunks > 4 * nq) {
       // persistent schedule: 9/10 of the chunks in per-SM queues (contiguous runs of tiles), the rest in a shared one;
       // nq < 0 (SPHBVF_PAIR_SCHED=warp): chunks of one warp (32 atoms) drawn per warp, passed as a negative count
       const int cpq = ta.nq < 0 ? -(int)(0.9 * ((ta.a1 - ta.a0 + 31) / 32) / nq) : (int)(0.9 * nchunks / nq);
       cudaMemsetAsync(ta.queues, 0, sizeof(int) * (nq + 1), st);
-      pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<PAIR_MINB * nq, PTH, 0, st>>>(
-          d, co, tb, pc, ta.aorder, ta.a0, ta.a1, ta.queues, nq, cpq, vout);
+      if constexpr (CanPersist<SPECIES, SOLIDS, RANDOM, VIRIAL>::value)
+        pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL, true><<<PAIR_MINB * nq, PTH, 0, st>>>(
+            d, co, tb, pc, ta.aorder, ta.a0, ta.a1, ta.queues, nq, cpq, vout);
     } else {
       pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL><<<nchunks, PTH, 0, st>>>(
           d, co, tb, pc, ta.aorder, ta.a0, ta.a1, nullptr, 1, 0, vout);

@@ -140,6 +140,8 @@ void AtomVecSsaTsdpdAtomicCuda::build_table()
   static const int brd[] = {S_X, S_V, S_TAG, S_TYPE, S_MASK, S_RHO, S_E, S_CV, S_VEST, S_C, S_SOLID, S_FIXED, S_DEV, S_RHOI, -1};
   static const int exc[] = {S_X, S_V, S_TAG, S_TYPE, S_MASK, S_IMAGE, S_RHO, S_E, S_CV, S_VEST, S_C, S_SOLID, S_FIXED, S_DEV, S_RHOI, -1};
   static const int rst[] = {S_X, S_TAG, S_TYPE, S_MASK, S_IMAGE, S_V, S_RHO, S_E, S_CV, S_VEST, S_C, S_SOLID, S_FIXED, S_DEV, S_RHOI, -1};
+  static_assert(sizeof fwd <= sizeof order_fwd && sizeof brd <= sizeof order_brd && sizeof exc <= sizeof order_exc &&
+                    sizeof rst <= sizeof order_rst, "message layouts must fit their order arrays");
   memcpy(order_fwd, fwd, sizeof fwd);
   memcpy(order_brd, brd, sizeof brd);
   memcpy(order_exc, exc, sizeof exc);
@@ -191,8 +193,16 @@ void AtomVecSsaTsdpdAtomicCuda::grow(int n)
 {
   if (!nfld) build_table();   // atom_style given without arguments cannot happen (process_args errors), but replicate / restart re-create the class
   const int old = nmax;
-  if (n == 0) grow_nmax();
-  else nmax = n;
+  if (n == 0) {
+    // AtomVec::grow_nmax adds 16384 rows per call; every call re-points the row tables of all [n][3] arrays, so filling
+    // 64 M atoms that way costs N^2 / 32768 = 1.2e11 pointer stores per array (a quarter of an hour of create_atoms).
+    // Past a million rows grow by an eighth instead: ~ 35 calls from 1 M to 64 M.
+    grow_nmax();
+    if (old >= (1 << 20)) {
+      const bigint want = (bigint)old + old / 8;
+      if (want > nmax) nmax = (int)MIN(want, (bigint)MAXSMALLINT);
+    }
+  } else nmax = n;
   atom->nmax = nmax;
   if (nmax < 0 || nmax > MAXSMALLINT) error->one(FLERR, "Per-processor system is too big");
   for (int q = 0; q < nfld; q++) {
@@ -216,7 +226,7 @@ int AtomVecSsaTsdpdAtomicCuda::nlazy() const
 {
   int n = 0;
   for (int q = NSTATE; q < nfld; q++)
-    if (!have(fld[q]) && !(fld[q].shape == D2 && fld[q].cols == 0)) n++;
+    if (!have(fld[q])) n++;
   return n;
 }
 
@@ -627,12 +637,16 @@ void AtomVecSsaTsdpdAtomicCuda::pack_property_atom(int index, double *buf, int n
 
 /* ---------------------------------------------------------------------- */
 
-bigint AtomVecSsaTsdpdAtomicCuda::memory_usage()
+bigint AtomVecSsaTsdpdAtomicCuda::memory_usage() { return host_bytes(true); }
+
+/* Atom::memcheck is only valid inside Atom::memory_usage() (it reads a scratch string that exists only there) */
+
+bigint AtomVecSsaTsdpdAtomicCuda::host_bytes(bool from_atom_memory_usage)
 {
   bigint bytes = 0;
   for (int q = 0; q < nfld; q++) {
     const Field &f = fld[q];
-    if (!have(f) || !atom->memcheck(f.name)) continue;
+    if (!have(f) || (from_atom_memory_usage && !atom->memcheck(f.name))) continue;
     switch (f.shape) {
       case I1: bytes += memory->usage(*(int **)f.slot, nmax); break;
       case D1: bytes += memory->usage(*(double **)f.slot, nmax); break;

@@ -79,6 +79,7 @@ class AtomVecSsaTsdpdAtomicCuda : public AtomVec {
   void materialize_all();
   bool materialized(int which) const;
   int nlazy() const;                // derived fields that are still unallocated
+  bigint host_bytes(bool from_atom_memory_usage = false);   // bytes of the per-atom arrays that are allocated
 
  private:
   enum Shape { I1, D1, D2, D33 };
@@ -93,7 +94,7 @@ class AtomVecSsaTsdpdAtomicCuda : public AtomVec {
   enum { NSTATE = 16, NFIELD = NSTATE + NDERIVED };
   Field fld[NFIELD];
   int nfld;
-  int order_fwd[8], order_brd[16], order_exc[16], order_rst[16];   // field indices, -1 terminated
+  int order_fwd[12], order_brd[16], order_exc[16], order_rst[16];   // field indices, -1 terminated
   bool have(const Field &f) const { return *(void *const *)f.slot != NULL; }
   double *row(const Field &f, int i) const;    // the cols doubles of atom i (D1 / D2 / D33)
   int &ival(const Field &f, int i) const { return (*(int *const *)f.slot)[i]; }

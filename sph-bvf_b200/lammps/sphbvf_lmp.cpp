@@ -129,7 +129,6 @@ SphbvfLmp::SphbvfLmp(LAMMPS *lmp) : Pointers(lmp)
   nbytes_down = 0;
   nranks = 1;
   workers = NULL;
-  parked = false;
 }
 
 SphbvfLmp::~SphbvfLmp()
@@ -144,7 +143,6 @@ void SphbvfLmp::destroy_contexts()
   else if (ctxs.size() == 1) sphbvf_destroy(ctxs[0]);
   ctxs.clear();
   ctx = NULL;
-  parked = false;
 }
 
 /* f(ctx_r, r) on every rank at the same time; the first failing rank's message becomes the LAMMPS error */
@@ -224,8 +222,7 @@ void SphbvfLmp::start()
     error->all(FLERR, "SSA species are not supported by the /cuda styles");   // serial-only upstream as well
   if (sphbvf_device_count() < 1)
     error->all(FLERR, "No CUDA device: the /cuda styles have no CPU fallback (drop -sf cuda)");
-  if (ctx && !parked) stop();
-  if (ctx) destroy_contexts();   // the parked state of the previous run: the host arrays are authoritative now
+  if (ctx) stop();
 
   const int S = atom->num_sdpd_species, ntypes = atom->ntypes;
   sphbvf_config cfg;
@@ -495,11 +492,7 @@ void SphbvfLmp::fetch(unsigned want)
   unsigned need = want & HF_ALL & ~host_mask;
   if (!need) return;
   materialize(need);
-  if (n != nlocal_uploaded) {
-    if (!parked) error->one(FLERR, "Atom count changed during a /cuda run");
-    destroy_contexts();   // atoms were created or deleted after the run: its device state describes another system
-    return;
-  }
+  if (n != nlocal_uploaded) error->one(FLERR, "Atom count changed during a /cuda run");
   if (n) {
     if (nranks > 1) fetch_multi(need);
     else {
@@ -654,10 +647,6 @@ unsigned SphbvfLmp::output_fields(bool at_setup)
 void SphbvfLmp::stop()
 {
   if (!ctx) return;
-  if (parked) {   // second stop (next run's setup, clear): the parked state goes away
-    destroy_contexts();
-    return;
-  }
   if (getenv("SPHBVF_VERBOSE") && comm->me == 0) {
     char msg[256];
     snprintf(msg, sizeof msg, "sphbvf: " BIGINT_FORMAT " full downloads, " BIGINT_FORMAT " output steps served from the device, "
@@ -683,25 +672,21 @@ void SphbvfLmp::stop()
     if (screen) fputs(msg.c_str(), screen);
     if (logfile) fputs(msg.c_str(), logfile);
   }
-  // lazy host mirrors: copy back the state and the outputs that are mirrored already, keep the rest fetchable
+  // lazy host mirrors: copy back the state and the outputs that are mirrored; nothing ever asked for the rest
   AtomVecSsaTsdpdAtomicCuda *av = dynamic_cast<AtomVecSsaTsdpdAtomicCuda *>(atom->avec);
   if (av && getenv("SPHBVF_VERBOSE") && comm->me == 0) {
     char msg[256];
     snprintf(msg, sizeof msg, "sphbvf: host mirrors of %d of the %d pair-sweep output arrays were allocated "
              "(atom_style ssa_tsdpd/atomic/cuda), %d bytes of host arrays per atom slot\n",
              (int)AtomVecSsaTsdpdAtomicCuda::NDERIVED - av->nlazy(), (int)AtomVecSsaTsdpdAtomicCuda::NDERIVED,
-             (int)(av->memory_usage() / MAX(1, atom->nmax)));
+             (int)(av->host_bytes() / MAX(1, atom->nmax)));
     if (screen) fputs(msg, screen);
     if (logfile) fputs(msg, logfile);
   }
-  if (av && av->nlazy() > 0) {
-    unsigned want = HF_ALL;
+  unsigned want = HF_ALL;
+  if (av)
     for (size_t q = 0; q < sizeof lazy_map / sizeof lazy_map[0]; q++)
       if (!av->materialized(lazy_map[q].derived)) want &= ~lazy_map[q].bit;
-    fetch(want);
-    parked = true;
-    return;
-  }
-  to_host();
+  fetch(want);
   destroy_contexts();
 }

@@ -48,9 +48,8 @@ class SphbvfLmp : protected Pointers {
 
   // ---- the hooks, called by the pair style and the integrator fix
   void start();                 // first Pair::compute of a run: create ctx, upload, neighbour setup
-  void stop();                  // end of run (Fix::post_run): download; destroy ctx, or park it (lazy host mirrors, below)
-  bool active() const { return ctx != NULL && !parked; }      // a run is in progress on the device
-  bool has_device_state() const { return ctx != NULL; }       // ... or its final state is still there (parked)
+  void stop();                  // end of run (Fix::post_run) or destruction: download, destroy ctx
+  bool active() const { return ctx != NULL; }
   void check(int rc);           // rc != 0 -> error->one(FLERR, sphbvf_last_error())
   // ---- fan-out over the GPUs: f(ctx_r, r) on every rank concurrently (worker threads), status codes checked
   int nranks;
@@ -74,10 +73,9 @@ class SphbvfLmp : protected Pointers {
   };
   void fetch(unsigned mask);    // device -> class Atom arrays for the fields of `mask` that are not current yet
   // With atom_style ssa_tsdpd/atomic/cuda the host arrays of the pair-sweep outputs (drho, phi, nw, ...) exist only once
-  // something asked for them (AtomVecSsaTsdpdAtomicCuda::materialize).  So that "ask later" keeps working after the run
-  // (write_dump, a compute evaluated between runs), stop() then copies back the state fields and the outputs that are
-  // already mirrored and PARKS the device contexts instead of destroying them; they go away when the next run starts
-  // or with the pair style.
+  // something asked for them (AtomVecSsaTsdpdAtomicCuda::materialize); stop() copies back the state fields and the
+  // outputs that are mirrored.  (LAMMPS refuses to evaluate a compute between runs unless it was invoked on the run's
+  // last step -- "Compute used in dump between runs is not current" -- so nothing can ask for a new column afterwards.)
   static void host_fields(class Atom *, unsigned mask);   // materialise + fetch: what a reader of host arrays calls first
   void to_host() { fetch(HF_ALL); }   // every field the package owns
   void mark_dirty() { host_mask = 0; }
@@ -94,7 +92,6 @@ class SphbvfLmp : protected Pointers {
 
  private:
   unsigned host_mask;           // HF_* bits of the fields that are current on the host
-  bool parked;                  // run over, contexts kept for late fetches (lazy host mirrors only)
   void destroy_contexts();
   void materialize(unsigned mask);   // lazy host mirrors: allocate the arrays of the derived fields in mask
   int nlocal_uploaded;

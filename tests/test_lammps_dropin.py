@@ -24,6 +24,8 @@ ROOT = os.path.dirname(HERE)
 REF = os.path.join(ROOT, "oracle", "_ref", "lmp_serial")
 CUDA = os.path.join(ROOT, "sph-bvf_b200", "lammps", "_build", "lmp_cuda")
 TOL = 1e-10
+# thermo `Press` of the wall-bounded transportVelocity decks against the reference: see _check_deck
+PRESS_ARTEFACT_BOUND = {"cavity2d": 0.5, "cavity3d": 0.5, "natconv2d": 0.5, "react2d": 0.5}
 
 CAVITY2D = """
 dimension 2
@@ -406,7 +408,14 @@ def _check_deck(name):
         # agree only where no fluid-solid pair matters: tight for the ring deck (solid away from the
         # periodic faces), loose for the channel deck (walls cross a periodic face), not at all for the
         # wall-bounded transportVelocity decks.
+        #
+        # Wall-bounded transportVelocity decks: not skipped but held to the measured size of that artefact (max over
+        # the thermo rows of |P_cuda - P_ref| / max |P_ref|, printed below; bounds = twice the values measured on a
+        # B200 in round 2), so that a regression of the device virial beyond it still fails.
         if what == "Press" and name.startswith(("cavity", "natconv", "react")):
+            err = np.abs(ta[:, col] - tb[:, col]).max() / scale
+            print("thermo Press, %s: orientation artefact of the reference = %.3e of max |P|" % (name, err))
+            assert err <= PRESS_ARTEFACT_BOUND[name], (name, err, ta[:, col], tb[:, col])
             continue
         tol = 2e-3 if (what == "Press" and name == "fsi2d") else 2e-5
         if what == "Press" and name == "fsi2d":
@@ -563,43 +572,41 @@ def test_thermo_only_steps_need_no_download(monkeypatch):
 
 # ---------------------------------------------------------------------------------------------
 # atom_style ssa_tsdpd/atomic/cuda (picked by -sf cuda): the host arrays of the pair-sweep outputs are allocated when
-# something on the host first asks for them, also AFTER the run (the device contexts are parked, not destroyed)
+# something on the host first asks for them
 # ---------------------------------------------------------------------------------------------
-def test_lazy_host_mirrors_and_late_fetch(monkeypatch):
-    if not (os.path.exists(REF) and os.path.exists(CUDA)):
-        pytest.skip("lmp_serial / lmp_cuda not built (make -C oracle ref; make -C sph-bvf_b200/lammps)")
-    # the dump lists positions, velocities and rho only; phi and drho are first asked for by write_dump after the run,
-    # number_density by nobody
-    deck = CAVITY3D.replace("vx vy vz fx fy fz c_crho c_cphi", "vx vy vz c_crho")
-    assert deck != CAVITY3D
-    deck += ("compute pa all property/atom drho\n"
-             "write_dump all custom late.txt id x y z c_cphi c_pa modify sort id format float %.17g\n")
-    wd_ref, _ = run_deck(REF, deck, [])
-    monkeypatch.setenv("SPHBVF_VERBOSE", "1")
-    wd_cuda, out = run_deck(CUDA, deck, ["-sf", "cuda"])
+def _host_mirror_stats(out):
     ln = [l for l in out.splitlines() if l.startswith("sphbvf: host mirrors")]
     assert ln, out[-2000:]
-    m = re.search(r"host mirrors of (\d+) of the (\d+) pair-sweep output arrays were allocated .* (\d+) bytes", ln[-1])
+    m = re.search(r"host mirrors of (\d+) of the (\d+) pair-sweep output arrays were allocated .* (\d+) bytes of host arrays per atom slot", ln[-1])
     assert m, ln[-1]
-    # at the end of the run nothing derived had been asked for: 0 of 21 arrays, < 300 B per atom on the host
-    # (upstream's style: ~ 830 B per atom)
-    natoms = 14 ** 3
-    assert int(m.group(1)) == 0 and int(m.group(2)) == 21, ln[-1]
-    assert 200 < int(m.group(3)) < 300, ln[-1]
-    ref, got = read_dumps(wd_ref), read_dumps(wd_cuda)
-    assert sorted(ref) == sorted(got) and len(ref) >= 3
-    for s in ref:
-        for k, c in enumerate(ref[s][0]):
-            sc = max(np.abs(ref[s][1][:, k]).max(), 1e-300)
-            assert np.abs(ref[s][1][:, k] - got[s][1][:, k]).max() <= TOL * sc, (s, c)
+    return tuple(int(v) for v in m.groups())
 
-    def late(wd):
-        lines = open(os.path.join(wd, "late.txt")).read().splitlines()
-        k = next(i for i, l in enumerate(lines) if l.startswith("ITEM: ATOMS"))
-        return np.array([[float(v) for v in l.split()] for l in lines[k + 1:]])
-    a, b = late(wd_ref), late(wd_cuda)
-    assert a.shape == b.shape == (natoms, 6)
-    for k, c in enumerate(("id", "x", "y", "z", "phi", "drho")):
-        sc = np.abs(a[:, k]).max()
-        assert sc > 0, c
-        assert np.abs(a[:, k] - b[:, k]).max() <= TOL * sc, c
+
+def test_lazy_host_mirrors(monkeypatch):
+    if not (os.path.exists(REF) and os.path.exists(CUDA)):
+        pytest.skip("lmp_serial / lmp_cuda not built (make -C oracle ref; make -C sph-bvf_b200/lammps)")
+    monkeypatch.setenv("SPHBVF_VERBOSE", "1")
+    # (a) the dump lists positions, velocities and rho only: no output array is ever mirrored, < 300 B per atom on the
+    # host (upstream's style: ~ 830 B per atom)
+    lean = CAVITY3D.replace("vx vy vz fx fy fz c_crho c_cphi", "vx vy vz c_crho")
+    assert lean != CAVITY3D
+    # (b) phi through its /cuda compute and drho through property/atom (AtomVec::pack_property_atom): two mirrors
+    two = CAVITY3D.replace("compute cphi all ssa_tsdpd/phi/atom\n", "compute cphi all ssa_tsdpd/phi/atom\ncompute pa all property/atom drho\n")
+    two = two.replace("vx vy vz fx fy fz c_crho c_cphi", "vx vy vz c_crho c_cphi c_pa")
+    assert two != CAVITY3D
+    for deck, nmirrors in ((lean, 0), (two, 2)):
+        wd_ref, _ = run_deck(REF, deck, [])
+        wd_cuda, out = run_deck(CUDA, deck, ["-sf", "cuda"])
+        got_n, total, per_slot = _host_mirror_stats(out)
+        assert (got_n, total) == (nmirrors, 21), (got_n, total)
+        assert 200 < per_slot < 300 + 8 * nmirrors, per_slot
+        ref, got = read_dumps(wd_ref), read_dumps(wd_cuda)
+        assert sorted(ref) == sorted(got) and len(ref) >= 3
+        for s in ref:
+            assert ref[s][0] == got[s][0]
+            for k, c in enumerate(ref[s][0]):
+                sc = max(max(np.abs(ref[q][1][:, k]).max() for q in ref), 1e-300)
+                assert np.abs(ref[s][1][:, k] - got[s][1][:, k]).max() <= TOL * sc, (s, c)
+        if nmirrors:
+            cols = ref[max(ref)][0]
+            assert np.abs(ref[max(ref)][1][:, cols.index("c_pa")]).max() > 0
