@@ -572,15 +572,17 @@ int sphbvf_create(const sphbvf_config *cfg, sphbvf_ctx **out) {
   { const char *e = getenv("SPHBVF_NO_FUSE"); ctx->fuse = !(e && atoi(e)); }
   { const char *e = getenv("SPHBVF_PAIR"); ctx->pair_pref = (e && e[0] == 't') ? 1 : 0; }   // tile | gather (default)
   { const char *e = getenv("SPHBVF_HALO"); ctx->overlap_halo = !(e && e[0] == 's'); }       // serial | overlap (default)
-  {   // gather form: one CTA per chunk (default) | persistent CTAs with SM-local chunk queues (SPHBVF_PAIR_SCHED=smid: chunk per CTA; =warp: chunk per warp;
-      // measured slower at 8 M atoms, 6.08 vs 5.66 ms: L1 hit rate 84 -> 89 %, but the tail and the queue round trips cost more)
+  {   // gather form, launches of more than 4 x SMs chunks: SPHBVF_PAIR_SCHED = warp (default: persistent CTAs, every warp
+      // draws 32-atom chunks from the queue of its SM: 5.42 vs 5.61 ms at 8 M atoms) | smid (the same queues, one 192-atom
+      // chunk per CTA and draw: 5.82 ms) | grid (one CTA per chunk, the hardware's dispatch order: 5.61 ms)
     const char *e = getenv("SPHBVF_PAIR_SCHED");
     int nsm = 0;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device);
     ctx->pair_nq = nsm > 0 ? nsm : 1;
-    if (e && (e[0] == 's' || e[0] == 'w') && cudaMalloc((void **)&ctx->pair_queues, sizeof(int) * 2 * (ctx->pair_nq + 1)) != cudaSuccess)
+    const bool grid = e && e[0] == 'g';
+    if (!grid && cudaMalloc((void **)&ctx->pair_queues, sizeof(int) * 2 * (ctx->pair_nq + 1)) != cudaSuccess)
       ctx->pair_queues = nullptr;
-    ctx->pair_warp = e && e[0] == 'w';
+    ctx->pair_warp = !(e && e[0] == 's');
   }
   if (cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device) != cudaSuccess)
     ctx->smem_optin = 48 * 1024;

@@ -12,7 +12,7 @@
 // loads.  Sweep C (v_weighted_solid / a_weighted_solid) is never consumed.  The
 // stochastic stress (active when some ssa_tsdpd/e != 0) is a counter-based pair noise (Philox), see RANDOM below.
 //
-// Two traversals share ONE arithmetic body (PairAcc::visit), so they differ only in summation order:
+// Three traversals share ONE arithmetic body (PairAcc::visit), so they differ only in summation order:
 //
 //  * pair_kernel (gather form, default): one thread per owned atom, 192-thread CTAs, 96-byte records gathered
 //    through L1 with a hand software pipeline (records of neighbour k+1 in flight while k is evaluated, list entries
@@ -30,7 +30,12 @@
 //    gathers they replace (2.5 lanes of a quarter-warp collide on a bank group: runs of consecutive slots are only
 //    ~4 long), and with 16 warps per SM issue stays at 50 %.  Kept selectable and tested; DESIGN.md section 3.
 //
-// Common to both: every per-particle division lives in the pack kernel (V = m/rho, P/rho^2),
+//  * pair_split_kernel (gather form for launches of <= 65536 atoms, i.e. the reference's shipped decks): four adjacent
+//    lanes share one atom, each walks a quarter of its list with the same pipeline, the sums meet in a butterfly.  A
+//    3 k - 42 k atom launch leaves most of the GPU empty, so its duration is the latency of one thread's serial walk
+//    over its neighbours; four lanes cut that walk to a quarter.  SPHBVF_PAIR_LANES=1 switches it off.
+//
+// Common to all: every per-particle division lives in the pack kernel (V = m/rho, P/rho^2),
 // sqrt is a branch-free Goldschmidt iteration on MUFU.RSQ64H (7 FP64 ops, < 1 ulp), per-type-pair coefficients are
 // kernel-argument constants when every type pair shares them (all cavity decks and the synthetic lattice) and
 // rows of a small shared-memory table otherwise.
@@ -1103,7 +1108,8 @@ static void launch_one(const DevState &d, const Coeffs &co, const PairTables &tb
     } else if (CanPersist<SPECIES, SOLIDS, RANDOM, VIRIAL>::value && ta.queues && nchunks > 4 * nq) {
       // persistent schedule: 9/10 of the chunks in per-SM queues (contiguous runs of tiles), the rest in a shared one;
       // nq < 0 (SPHBVF_PAIR_SCHED=warp): chunks of one warp (32 atoms) drawn per warp, passed as a negative count
-      const int cpq = ta.nq < 0 ? -(int)(0.9 * ((ta.a1 - ta.a0 + 31) / 32) / nq) : (int)(0.9 * nchunks / nq);
+      static const double own = [] { const char *e = getenv("SPHBVF_PAIR_TAIL"); const double t = e ? atof(e) : 0.1; return 1.0 - (t > 0.0 && t < 1.0 ? t : 0.1); }();
+      const int cpq = ta.nq < 0 ? -(int)(own * ((ta.a1 - ta.a0 + 31) / 32) / nq) : (int)(own * nchunks / nq);
       cudaMemsetAsync(ta.queues, 0, sizeof(int) * (nq + 1), st);
       if constexpr (CanPersist<SPECIES, SOLIDS, RANDOM, VIRIAL>::value)
         pair_kernel<VARIANT, SPECIES, SOLIDS, UNIFORM, FILTER, RANDOM, VIRIAL, true><<<PAIR_MINB * nq, PTH, 0, st>>>(

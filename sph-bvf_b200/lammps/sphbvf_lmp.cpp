@@ -567,7 +567,9 @@ void SphbvfLmp::fetch_multi(unsigned need)
    (b) every dump that is due now contributes the columns it writes: dump custom / cfg-less styles are parsed
        keyword by keyword (id type mass: static data; x y z xs .. : positions; vx .. : velocities; fx .. : forces;
        c_ID: a /cuda per-atom compute fetches its own field when the dump invokes it, static per-atom computes
-       such as ssa_tsdpd/solid_tag/atom need nothing, any other compute -> everything; v_ f_ d_ i_ -> everything);
+       such as ssa_tsdpd/solid_tag/atom need nothing, property/atom reads x / v / f and -- with atom_style
+       ssa_tsdpd/atomic/cuda -- fetches the package's columns itself, any other compute -> everything;
+       v_ f_ d_ i_ -> everything);
        dump atom / xyz read positions; any other dump style -> everything;
    (c) otherwise nothing: the thermo line is served from the device reductions.
    SPHBVF_OUTPUT=full restores the unconditional full download.
@@ -635,6 +637,12 @@ unsigned SphbvfLmp::output_fields(bool at_setup)
         const size_t n = strlen(cs);
         if (n >= 5 && strcmp(cs + n - 5, "/cuda") == 0) continue;              // fetches its own field
         if (strcmp(cs, "ssa_tsdpd/solid_tag/atom") == 0) continue;               // static per-atom data
+        if (strcmp(cs, "property/atom") == 0 && dynamic_cast<AtomVecSsaTsdpdAtomicCuda *>(atom->avec)) {
+          // core attributes read x / v / f; the package's own (rho drho e de cv phi Pnew ...) go through
+          // AtomVecSsaTsdpdAtomicCuda::pack_property_atom, which fetches its column itself
+          mask |= HF_X | HF_V | HF_F;
+          continue;
+        }
         return HF_ALL;
       }
       return HF_ALL;   // v_ f_ d_ i_ q mux ... : cannot be inspected
