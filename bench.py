@@ -50,9 +50,10 @@ F_ALG_PAIR_SURVEY = 1.2e4   # FP64 flop / atom-step, 3D bulk, SURVEY.md 8d's pap
 # FP64 flop / atom-step the kernel really executes, re-derived as SURVEY 8(d) asks from ncu's
 # smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on of one launch at 8.0 M atoms (see PROFILE below):
 # (2 x dfma + dmul + dadd) / atoms.  Updated whenever a new --set full capture is committed under profiles/.
-PROFILE = {"file": "profiles/r02d_pair_kernel_gather_192_n200.txt", "kernel": "pair_kernel<TV,0,1,UNIFORM> (gather form, 192-thread CTAs, as shipped)",
-           "flop_per_atom": 7.70e3, "fp64_inst_per_atom": 5.30e3, "dram_bytes_per_atom": 604.3,
-           "l1_data_pipe_busy": 0.797, "fp64_pipe_busy": 0.474, "issue_active": 0.424, "warps_per_sm": 10.8}
+PROFILE = {"file": "profiles/r02p_pair_kernel_warp_schedule_n200.txt",
+           "kernel": "pair_kernel<TV,0,1,UNIFORM,PERSIST> (gather form, persistent 192-thread CTAs whose warps draw 32-atom chunks, as shipped)",
+           "flop_per_atom": 7.70e3, "fp64_inst_per_atom": 5.30e3, "dram_bytes_per_atom": 732.9,
+           "l1_data_pipe_busy": 0.822, "fp64_pipe_busy": 0.491, "issue_active": 0.454, "warps_per_sm": 12.0}
 PARITY_FIXTURES = ["synth3d_n14", "solid3d_mech_n10", "cavity_n50"]   # 3D non-periodic, 3D periodic with free solids, 2D
 WEAK_N = {1: 200, 2: 252, 4: 318, 8: 400}
 

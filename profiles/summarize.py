@@ -4,6 +4,7 @@ committed under profiles/.
 
   python profiles/summarize.py launches gpurun_out/launches_X.csv   > profiles/rNN_launches.txt
   python profiles/summarize.py kernel   gpurun_out/prof_X.ncu-rep   > profiles/rNN_<kernel>.txt
+  python profiles/summarize.py kernel   gpurun_out/X.raw.csv gpurun_out/X.src.csv   (exports made on the GPU box)
 
 `launches`: per-kernel count / total / average device time and SHARE of the step from the
 `--metrics gpu__time_duration.sum` pass (cold-cache, serialised: shares are what is comparable).
@@ -47,8 +48,13 @@ def launches(path):
         print("%-58s %5d %12.1f %10.1f %6.1f%%" % (k[:58], v[0], v[1] / 1e3, v[1] / 1e3 / v[0], 100 * v[1] / tot))
 
 
-def kernel(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def kernel(path, src_path=None):
+    """path: a .ncu-rep, or the `--page raw --csv` export of one (then src_path = its `--page source --csv
+    --print-source sass` export: the report itself may have stayed on the GPU box)"""
+    if path.endswith(".csv"):
+        raw = "\n".join(l for l in open(path).read().splitlines() if l.startswith('"'))
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     seen = set()
@@ -67,7 +73,12 @@ def kernel(path):
         print("   warp stall mix (cycles per issued instruction, share):")
         for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:8]:
             print("      %-28s %6.2f  %5.1f%%" % (k.split("issue_stalled_")[1].replace("_per_issue_active.ratio", ""), v, 100 * v / tot))
-    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):
+        if not src_path:
+            return
+        src = open(src_path).read()
+    else:
+        src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
     done = set()
@@ -91,4 +102,4 @@ def kernel(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel}[sys.argv[1]](*sys.argv[2:])

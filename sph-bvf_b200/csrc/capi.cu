@@ -408,16 +408,20 @@ int make_tile_order(sphbvf_ctx *ctx) {
     (ghost ? outer : inner).push_back((int)t);
   }
   if (ntiles > ctx->tile_order_cap) {
-    for (int *q : {ctx->tile_order, ctx->tile_cnt, ctx->tile_off, ctx->aorder, ctx->pair_queues}) if (q) cudaFree(q);
-    ctx->tile_order = nullptr;
+    // the three tables sized by the tile count (the atom order and the schedule's queues have their own owners)
+    for (int **q : {&ctx->tile_order, &ctx->tile_cnt, &ctx->tile_off}) {
+      if (*q) cudaFree(*q);
+      *q = nullptr;
+    }
     CK(cudaMalloc((void **)&ctx->tile_order, sizeof(int) * (size_t)ntiles));
-    if (ctx->tile_cnt) cudaFree(ctx->tile_cnt);
-    if (ctx->tile_off) cudaFree(ctx->tile_off);
-    ctx->tile_cnt = ctx->tile_off = nullptr;
     CK(cudaMalloc((void **)&ctx->tile_cnt, sizeof(int) * (size_t)(ntiles + 2)));
     CK(cudaMalloc((void **)&ctx->tile_off, sizeof(int) * (size_t)(ntiles + 2)));
     ctx->tile_order_cap = ntiles;
   }
+  // (A Z-order sequence of the tiles behind the persistent pair schedule -- every SM then owns a compact blob of tiles
+  // instead of a slab of rows -- was measured at 8 M atoms: L2 hit rate 26 -> 36 %, DRAM reads 4.98 -> 4.85 GB per pass,
+  // L1 hit rate unchanged at 87 %, and the pass 0.04 ms SLOWER because of the atom-order indirection it needs
+  // (gpurun_out/r2q_*).  Rows stay.)
   ctx->ntiles_interior = (int)inner.size();
   ctx->ntiles_total = (int)ntiles;
   inner.insert(inner.end(), outer.begin(), outer.end());
