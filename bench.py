@@ -24,8 +24,9 @@ only and the image has no MPI runtime, so one single-rank replica runs per core 
 (an upper bound for one MPI job); if that binary did not travel, the plain-C oracle port is timed instead
 (one core) and says so.
 
-`lammps_dropin` (N=1 only, extra key) = the same deck at n=160 as an UNMODIFIED LAMMPS input through
-`lmp_cuda -sf cuda` (the /cuda style classes over the C ABI), LAMMPS' own Loop time.
+`lammps_dropin` (extra key) = the same deck as an UNMODIFIED LAMMPS input through `lmp_cuda -sf cuda` (the /cuda
+style classes over the C ABI), LAMMPS' own Loop time: n=160 at N=1; at N>1 the weak-scaling lattice of the launch
+(400^3 = 64 M atoms at N=8) driven by ONE LAMMPS process on all N GPUs, run by rank 0 after the timed ranks are gone.
 
 --impl reference runs only that CPU arm (rank 0) and prints the same line shape.
 """
@@ -209,7 +210,7 @@ def time_reference(n, steps, warm, procs=1):
     return len(a["tag"]) * steps / dt, "port", len(a["tag"])
 
 
-def time_lmp_cuda(n, steps, warm, ngpu=1):
+def time_lmp_cuda(n, steps, warm, ngpu=1, timeout=1200):
     """atom-steps/s of REF_DECK run unmodified through lmp_cuda -sf cuda (Loop time of the 2nd run); None if not built"""
     exe = os.path.join(ROOT, "sph-bvf_b200", "lammps", "_build", "lmp_cuda")
     if not os.path.exists(exe):
@@ -220,7 +221,7 @@ def time_lmp_cuda(n, steps, warm, ngpu=1):
                 fh.write(REF_DECK.format(n=n, steps=steps, warm=warm))
             env = dict(os.environ, SPHBVF_NGPU=str(ngpu))
             out = subprocess.run([exe, "-in", "in.lmp", "-log", "none", "-echo", "none", "-sf", "cuda"], cwd=wd, env=env,
-                                 capture_output=True, text=True, timeout=1200)
+                                 capture_output=True, text=True, timeout=timeout)
             loops = re.findall(r"Loop time of ([0-9.eE+-]+) on (\d+) procs for (\d+) steps with (\d+) atoms", out.stdout)
             if out.returncode != 0 or not loops:
                 return {"value": None, "error": (out.stdout[-300:] + out.stderr[-300:])}
@@ -433,6 +434,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    world_done = False
     eng.run(W)
     if rank == 0:
         sampler.mark()          # the summary's median is over the samples taken from here to stop()
@@ -533,10 +535,22 @@ def main():
             cpu = {"value": None, "unit": "atom-steps/s", "cores": 1, "kind": "reference", "sample": "failed: %r" % (ex,)}
 
     # drop-in leg: the same deck as an unmodified LAMMPS input through `lmp_cuda -sf cuda` (one LAMMPS process, the
-    # /cuda style classes of sph-bvf_b200/lammps over the C ABI): LAMMPS' own "Loop time" of the second `run`
+    # /cuda style classes of sph-bvf_b200/lammps over the C ABI): LAMMPS' own "Loop time" of the second `run`.
+    # N = 1: n = 160 (4.1 M atoms).  N > 1: the weak-scaling lattice of this launch (8 M atoms per GPU, 64 M at N = 8)
+    # driven by ONE LAMMPS process with a worker thread per GPU, after the ranks of this launch have released theirs.
     dropin = None
-    if rank == 0 and world == 1 and not args.no_lammps:
-        dropin = time_lmp_cuda(args.lammps_n, 50, 10)
+    if not args.no_lammps:
+        if world == 1:
+            dropin = time_lmp_cuda(args.lammps_n, 50, 10)
+        else:
+            eng.close()
+            eng = None
+            dist.barrier()
+            dist.destroy_process_group()
+            world_done = True
+            if rank != 0:
+                return
+            dropin = time_lmp_cuda(n, 30, 10, ngpu=world, timeout=420)
 
     if rank == 0:
         time.sleep(0.3)
@@ -551,8 +565,9 @@ def main():
                 "clocks": sampler.summary(), "lammps_dropin": dropin}
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    eng.close()
-    if world > 1:
+    if eng is not None:
+        eng.close()
+    if world > 1 and not world_done:
         dist.destroy_process_group()
 
 

@@ -488,13 +488,15 @@ static PairFlags pair_flags(const sphbvf_ctx *ctx) {
 // sphbvf_set_atoms count: set_atoms(e = NULL) followed by upload(E != 0) must switch the stochastic term on.
 // the flags must agree on every brick; with_dev is a type mask, so its bits are reduced one by one (max = or)
 static int allreduce_kernel_flags(sphbvf_ctx *ctx) {
-  int v[2 + 8] = {ctx->any_solid, ctx->e_nonzero};
-  for (int t = 0; t < 8; t++) v[2 + t] = (ctx->with_dev >> t) & 1;
-  const int rc = comm_allreduce_max(ctx, v, 10);
+  // comm_allreduce_max carries at most 8 ints: two flags + one bit per atom type (types 1 .. MAXT-1, MAXT = 5)
+  static_assert(MAXT <= 6, "with_dev bits must fit the 8-int all-reduce");
+  int v[2 + 6] = {ctx->any_solid, ctx->e_nonzero};
+  for (int t = 0; t < 6; t++) v[2 + t] = (ctx->with_dev >> t) & 1;
+  const int rc = comm_allreduce_max(ctx, v, 8);
   if (rc) return rc;
   ctx->any_solid = v[0]; ctx->e_nonzero = v[1];
   ctx->with_dev = 0;
-  for (int t = 0; t < 8; t++) ctx->with_dev |= v[2 + t] << t;
+  for (int t = 0; t < 6; t++) ctx->with_dev |= v[2 + t] << t;
   return 0;
 }
 
