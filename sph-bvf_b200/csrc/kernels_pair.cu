@@ -56,6 +56,9 @@ namespace sphbvf {
 #ifndef PAIR_MINB
 #define PAIR_MINB 2
 #endif
+#ifndef PAIR_BC_LATE
+#define PAIR_BC_LATE 0
+#endif
 #ifndef PT_T
 #define PT_T 256
 #endif
@@ -613,11 +616,52 @@ __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, c
   // full memory latency exposed on every second visit (ncu source page: one DADD held 33 % of all stall samples).
   // The loads of record k+1 are therefore made DATA dependent on the first use of record k (`gate`: a NaN test the
   // compiler cannot fold), so they are issued right after record k has arrived and have a whole visit to complete.
+  const int nsp = SPECIES ? co.nspecies : 0;
+  auto gate = [&](const Rec4 &A) { const double g = acc.xi - A.x; return g != g ? 1 : 0; };
+#if PAIR_BC_LATE
+  // -DPAIR_BC_LATE=1 (experiment): only the position quarter A of the next record is requested one visit ahead; B and C
+  // (velocities, V, P/rho^2: the other 64 bytes of the same one or two lines) are requested when the visit starts and
+  // first used after the distance test and the square root.  16 registers less.
+  Rec4 A0, A1, B, C;
+  double D0 = 0.0, D1 = 0.0, S0 = 0.0, S1 = 0.0;
+  {
+    const Prec *p = d.prec + (e0 & NEIGH_JMASK);
+    A0 = p->A;
+    if (FILTER) D0 = d.pD[e0 & NEIGH_JMASK].x;
+    if (SPECIES) S0 = d.pCs[(size_t)(e0 & NEIGH_JMASK) * nsp];
+  }
+  for (int kk = 0; kk < nn; kk += 2) {
+    {
+      const Prec *p0 = d.prec + (e0 & NEIGH_JMASK);
+      B = p0->B; C = p0->C;
+      const int j1 = (e1 & NEIGH_JMASK) + gate(A0);
+      const Prec *p = d.prec + j1;
+      A1 = p->A;
+      if (FILTER) D1 = d.pD[j1].x;
+      if (SPECIES) S1 = d.pCs[(size_t)j1 * nsp];
+    }
+    fetch2(kk + RING);
+    asm volatile("cp.async.wait_group %0;" ::"n"(PEND) : "memory");
+    const int e2 = kk + 2 < nn ? myring[((kk + 2) % RING) * PTH] : 0;
+    const int e3 = kk + 3 < nn ? myring[((kk + 3) % RING) * PTH] : 0;
+    visit(e0, A0, B, C, D0, S0);
+    {
+      const Prec *p1 = d.prec + (e1 & NEIGH_JMASK);
+      B = p1->B; C = p1->C;
+      const int j2 = (e2 & NEIGH_JMASK) + gate(A1);
+      const Prec *p = d.prec + j2;
+      A0 = p->A;
+      if (FILTER) D0 = d.pD[j2].x;
+      if (SPECIES) S0 = d.pCs[(size_t)j2 * nsp];
+    }
+    if (kk + 1 < nn) visit(e1, A1, B, C, D1, S1);
+    e0 = e2;
+    e1 = e3;
+  }
+#else
   Rec4 A0, B0, C0, A1, B1, C1;
   double D0 = 0.0, D1 = 0.0;   // rhoI_j of the Shepard numerator, part of the pipeline on filter steps
   double S0 = 0.0, S1 = 0.0;   // C_j[0], part of the pipeline when species are transported
-  const int nsp = SPECIES ? co.nspecies : 0;
-  auto gate = [&](const Rec4 &A) { const double g = acc.xi - A.x; return g != g ? 1 : 0; };
   {
     const Prec *p = d.prec + (e0 & NEIGH_JMASK);
     A0 = p->A; B0 = p->B; C0 = p->C;
@@ -648,6 +692,7 @@ __device__ __forceinline__ void pair_atom(const DevState &d, const Coeffs &co, c
     e0 = e2;
     e1 = e3;
   }
+#endif
 
   if (VIRIAL) {
     // only atoms next to a periodic face have anything to add: plain atomics
