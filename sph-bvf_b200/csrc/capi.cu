@@ -401,6 +401,10 @@ int make_tile_order(sphbvf_ctx *ctx) {
     bool ghost = false;
     for (int k = 0; k < g.dim; k++) {
       const int c0 = tc[k] << g.tb[k];
+      // The early halo also relies on "every atom a neighbour brick receives (x within cutghost of the face,
+      // border_kernel) lives in a face tile": such an atom sits in a cell c <= floor(2 cutghost / cellsize) <= 4 (= 4 only
+      // when cellsize is exactly cutghost / 2, and then glo = 4), its tile starts at c0 <= c, and c0 - s <= 2 < glo
+      // (glo carries two cells of margin, init_neighbor); symmetrically on the high side.
       const int h0 = std::max(c0 - g.s[k], 0), h1 = std::min(c0 + (1 << g.tb[k]) - 1 + g.s[k], g.n[k] - 1);
       // cells below glo / above ghi may hold ghosts, if a neighbour brick (or this brick's own periodic image) sends any
       if ((h0 < g.glo[k] && peer[k][0]) || (h1 > g.ghi[k] && peer[k][1])) ghost = true;
@@ -577,7 +581,10 @@ int sphbvf_create(const sphbvf_config *cfg, sphbvf_ctx **out) {
   ctx->run_nsteps_user = -1;
   { const char *e = getenv("SPHBVF_NO_FUSE"); ctx->fuse = !(e && atoi(e)); }
   { const char *e = getenv("SPHBVF_PAIR"); ctx->pair_pref = (e && e[0] == 't') ? 1 : 0; }   // tile | gather (default)
-  { const char *e = getenv("SPHBVF_HALO"); ctx->overlap_halo = !(e && e[0] == 's'); }       // serial | overlap (default)
+  // SPHBVF_HALO: serial (on the compute stream) | overlap (own stream, beside the interior of the pair pass) |
+  // early (default: own stream, started by the fused integrator right after it has integrated the face atoms, so the
+  // exchange hides behind the integration of the interior and the pair pass stays ONE launch)
+  { const char *e = getenv("SPHBVF_HALO"); ctx->overlap_halo = !(e && e[0] == 's'); ctx->halo_early = !e || e[0] == 'e'; }
   {   // gather form, launches of more than 4 x SMs chunks: SPHBVF_PAIR_SCHED = warp (default: persistent CTAs, every warp
       // draws 32-atom chunks from the queue of its SM: 5.42 vs 5.61 ms at 8 M atoms) | smid (the same queues, one 192-atom
       // chunk per CTA and draw: 5.82 ms) | grid (one CTA per chunk, the hardware's dispatch order: 5.61 ms)
@@ -854,13 +861,35 @@ int sphbvf_initial_integrate(sphbvf_ctx *ctx) {
       if (ctx->fixes[q].kind == FIX_FORCING || (ctx->fixes[q].kind == FIX_BUFFER && ctx->fixes[q].ia[0] != 2)) do_pack = 0;
     ctx->final_pending = 0;
     ctx->tic(K_FUSED);
-    launch_final_initial(ctx->d, ctx->co, ctx->pend_dt, ctx->pend_step, ctx->cfg.dt, ctx->ntimestep,
-                         ctx->cfg.integrate_groupbit, do_pack, ctx->with_dev, ctx->st);
+    ctx->halo_done_step = 0;
+    // Early halo (multi-rank): the atoms of the face tiles -- a superset of everything a neighbour brick receives --
+    // are integrated and packed first, the halo starts on its own stream behind them, and the interior is integrated
+    // while the records travel.  If this step turns out to be a rebuild step the exchanged ghosts are simply replaced.
+    // Every rank takes the same branch (halo_early_ok is agreed collectively at each rebuild), so the order of the
+    // communicator's operations is the same everywhere.
+    // (not while an upload of e / dev / type / solid_tag is waiting to be folded into the kernel flags: the width of the
+    // halo record depends on them)
+    const bool early = ctx->cfg.nranks > 1 && ctx->overlap_halo && ctx->halo_early && ctx->halo_early_ok && do_pack &&
+                       ctx->aorder_valid && !ctx->flags_dirty;
+    if (early) {
+      int rc;
+      launch_final_initial(ctx->d, ctx->co, ctx->pend_dt, ctx->pend_step, ctx->cfg.dt, ctx->ntimestep,
+                           ctx->cfg.integrate_groupbit, do_pack, ctx->with_dev, ctx->st, ctx->aorder, ctx->natoms_interior,
+                           ctx->d.nlocal);
+      const PairFlags pf = pair_flags(ctx);
+      if ((rc = comm_forward(ctx, pf.filter_step || pf.random))) return rc;
+      launch_final_initial(ctx->d, ctx->co, ctx->pend_dt, ctx->pend_step, ctx->cfg.dt, ctx->ntimestep,
+                           ctx->cfg.integrate_groupbit, do_pack, ctx->with_dev, ctx->st, ctx->aorder, 0, ctx->natoms_interior);
+      ctx->halo_done_step = 1;
+    } else
+      launch_final_initial(ctx->d, ctx->co, ctx->pend_dt, ctx->pend_step, ctx->cfg.dt, ctx->ntimestep,
+                           ctx->cfg.integrate_groupbit, do_pack, ctx->with_dev, ctx->st);
     ctx->toc();
     CKLAUNCH();
     ctx->pack_valid = do_pack;
     return 0;
   }
+  ctx->halo_done_step = 0;
   ctx->pack_valid = 0;
   ctx->tic(K_INITIAL);
   launch_initial_integrate(ctx->d, ctx->co, ctx->cfg.dt, ctx->ntimestep, ctx->cfg.integrate_groupbit, ctx->with_dev, ctx->st);
@@ -909,6 +938,7 @@ int sphbvf_neighbor(sphbvf_ctx *ctx, int *rebuilt) {
   if (flag) return ctx->cfg.nranks > 1 ? comm_rebuild(ctx) : rebuild(ctx);
   // Comm::forward_comm (comm_brick.cpp:460-520): refresh the packed records of owned atoms and ghosts
   if (pack_valid && ctx->cfg.nranks == 1 && !ctx->d.nghost) return 0;   // records are current, nothing to refresh
+  if (ctx->halo_done_step && pack_valid) return 0;   // the integrator has packed and started this step's halo already
   ctx->tic(K_PACK);
   if (!pack_valid) launch_pack(ctx->d, ctx->co, ctx->with_dev, ctx->st);
   if (ctx->cfg.nranks > 1) {
@@ -926,7 +956,8 @@ int sphbvf_pair_compute(sphbvf_ctx *ctx) {
   FLUSH();
   int rc;
   ctx->tic(K_PAIR);
-  if (ctx->halo_pending && ctx->tile_order && ctx->ntiles_interior > 0 && (ctx->d.list16 || ctx->aorder_valid)) {
+  if (ctx->halo_pending && !ctx->halo_done_step && ctx->tile_order && ctx->ntiles_interior > 0 &&
+      (ctx->d.list16 || ctx->aorder_valid)) {
     // the halo of this step is still in flight on its own stream: the atoms that cannot see a ghost go first, the
     // compute stream then waits for the unpack, and the atoms along the brick faces follow
     const int nin = ctx->ntiles_interior, ntot = ctx->ntiles_total;

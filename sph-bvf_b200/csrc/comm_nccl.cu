@@ -649,7 +649,16 @@ int comm_rebuild(sphbvf_ctx *ctx) {
   if ((rc = halo(ctx, 1, 1, st))) return rc;
 
   rc = rebuild_finish(ctx);
-  if ((rc = comm_agree(ctx, rc))) return rc;
+  {
+    // one all-reduce for the status (comm_agree) and for "some rank has no atom order": the early halo changes the
+    // ORDER of this communicator's operations within a step, so either every rank uses it or none does
+    int v[2] = {rc ? -rc : 0, ctx->aorder_valid ? 0 : 1};
+    const int rc2 = comm_allreduce_max(ctx, v, 2);
+    if (rc) return rc;
+    if (rc2) return rc2;
+    if (v[0]) return ctx->fail(-v[0], "another GPU of this run failed with status %d (see its message)", -v[0]);
+    ctx->halo_early_ok = v[1] == 0;
+  }
   ctx->toc();
   return 0;
 }

@@ -43,6 +43,9 @@ struct sphbvf_ctx {
   int expanded_valid = 0;      // d.neigh holds the expansion of the current tile-form list (sphbvf_get_pairs)
   int overlap_halo = 1;        // multi-rank: per-step halo on its own stream beside the interior tiles (SPHBVF_HALO=serial: 0)
   int halo_pending = 0;        // a halo is in flight on the halo stream; ghost readers join it first
+  int halo_early = 1;          // SPHBVF_HALO=early (default): start the halo from inside the fused integrator (faces first)
+  int halo_early_ok = 0;       // every rank has an atom order for it (agreed in comm_rebuild)
+  int halo_done_step = 0;      // the halo of the coming pair pass has been started already (by the integrator)
   int *tile_order = nullptr;   // [ntiles] tiles that cannot see a ghost first, then the others
   int *tile_cnt = nullptr, *tile_off = nullptr;   // [ntiles + 1] scratch of the atom order
   int *aorder = nullptr;       // [nmax] owned atoms in tile_order (gather form: the split pair pass indexes through it)

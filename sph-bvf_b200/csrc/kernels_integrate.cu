@@ -93,13 +93,18 @@ struct IntegArgs {
   double dt_final, dt_init;
   long step_final, step_init;
   int groupbit, do_pack, with_dev;
+  // the atoms of this launch: positions [a0, a1) of `order` (nullptr: the atoms a0 .. a1 themselves).  The early halo
+  // integrates the atoms along the brick faces first, so that their records travel while the interior is integrated.
+  const int *order;
+  int a0, a1;
 };
 
 template <int VARIANT, int MODE>
 __global__ void __launch_bounds__(256)
 integrate_kernel(const DevState d, const __grid_constant__ Coeffs co, const IntegArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.nlocal) return;
+  const int p = a.a0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.a1) return;
+  const int i = a.order ? a.order[p] : p;
   const size_t i3 = 3 * (size_t)i;
   constexpr bool FIN = MODE != 0, INI = MODE != 1;
   const bool filter = FIN && shepard_filter_step(VARIANT, a.step_final);
@@ -268,8 +273,8 @@ integrate_kernel(const DevState d, const __grid_constant__ Coeffs co, const Inte
 
 template <int MODE>
 static void launch_integrate(const DevState &d, const Coeffs &co, const IntegArgs &a, cudaStream_t st) {
-  if (!d.nlocal) return;
-  const int b = nblocks(d.nlocal, 256);
+  if (a.a1 <= a.a0) return;
+  const int b = nblocks(a.a1 - a.a0, 256);
   if (co.variant == SPHBVF_TV) integrate_kernel<SPHBVF_TV, MODE><<<b, 256, 0, st>>>(d, co, a);
   else if (co.variant == SPHBVF_MECHANICS) integrate_kernel<SPHBVF_MECHANICS, MODE><<<b, 256, 0, st>>>(d, co, a);
   else integrate_kernel<SPHBVF_FSI, MODE><<<b, 256, 0, st>>>(d, co, a);
@@ -278,19 +283,20 @@ static void launch_integrate(const DevState &d, const Coeffs &co, const IntegArg
 
 void launch_initial_integrate(const DevState &d, const Coeffs &co, double dt, long ntimestep, int groupbit,
                               int with_dev, cudaStream_t st) {
-  IntegArgs a = {0.0, dt, 0, ntimestep, groupbit, 0, with_dev};
+  IntegArgs a = {0.0, dt, 0, ntimestep, groupbit, 0, with_dev, nullptr, 0, d.nlocal};
   launch_integrate<0>(d, co, a, st);
 }
 
 void launch_final_integrate(const DevState &d, const Coeffs &co, double dt, long ntimestep, int groupbit,
                             int with_dev, cudaStream_t st) {
-  IntegArgs a = {dt, 0.0, ntimestep, 0, groupbit, 0, with_dev};
+  IntegArgs a = {dt, 0.0, ntimestep, 0, groupbit, 0, with_dev, nullptr, 0, d.nlocal};
   launch_integrate<1>(d, co, a, st);
 }
 
 void launch_final_initial(const DevState &d, const Coeffs &co, double dt_final, long step_final, double dt_init,
-                          long step_init, int groupbit, int do_pack, int with_dev, cudaStream_t st) {
-  IntegArgs a = {dt_final, dt_init, step_final, step_init, groupbit, do_pack, with_dev};
+                          long step_init, int groupbit, int do_pack, int with_dev, cudaStream_t st, const int *order,
+                          int a0, int a1) {
+  IntegArgs a = {dt_final, dt_init, step_final, step_init, groupbit, do_pack, with_dev, order, a0, a1 < 0 ? d.nlocal : a1};
   launch_integrate<2>(d, co, a, st);
 }
 

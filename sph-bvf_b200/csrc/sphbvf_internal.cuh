@@ -168,7 +168,8 @@ void launch_final_integrate(const DevState &d, const Coeffs &co, double dt, long
                             int groupbit, int with_dev, cudaStream_t st);
 // final_integrate(step_final) + initial_integrate(step_init) [+ pack] in one pass (bit-identical to the two calls)
 void launch_final_initial(const DevState &d, const Coeffs &co, double dt_final, long step_final, double dt_init,
-                          long step_init, int groupbit, int do_pack, int with_dev, cudaStream_t st);
+                          long step_init, int groupbit, int do_pack, int with_dev, cudaStream_t st, const int *order = nullptr,
+                          int a0 = 0, int a1 = -1);
 void launch_max_vsq(const DevState &d, int groupbit, unsigned long long *out, cudaStream_t st);
 // out[0] = some atom has solid_tag, out[1] = some solid can carry deviatoric stress (G0 of its type != 0) or some
 // dev != 0, out[2] = some e != 0: what selects the pair-kernel instantiation.  out must be zeroed by the caller.
