@@ -104,3 +104,44 @@ def test_restart_and_data_file_round_trip():
         assert np.abs(dx - 2.0 * np.round(dx / 2.0)).max() < 1e-12
     solid = np.array([int(r[1]) for r in rows])
     assert np.array_equal(solid == 1, dump[:, cols.index("type")] == 2)
+
+
+def test_delete_sort_and_replicate_commands():
+    """commands that move atoms between rows (AtomVec::copy through delete_atoms and the spatial sort) or re-create the atom
+    style and re-insert every atom (replicate -> create_avec + unpack_restart-style copies): identical dumps again"""
+    _need()
+    deck = dropin.CAVITY2D.replace("mass * $(v_d*v_d)\n", "mass * $(v_d*v_d)\nregion hole block 0.4 0.6 0.4 0.6 0 ${d} units box\n"
+                                   "delete_atoms region hole\natom_modify sort 3 0.2\n")
+    assert deck != dropin.CAVITY2D
+    wd_ref, _ = dropin.run_deck(REF, deck, [])
+    wd_new, _ = dropin.run_deck(CUDA, _with_cuda_atom_style(deck), [])
+    ref, got = dropin.read_dumps(wd_ref), dropin.read_dumps(wd_new)
+    assert sorted(ref) == sorted(got) and len(ref) >= 3
+    assert len(ref[0][1]) < 26 * 26     # the hole is there
+    for s in ref:
+        assert np.array_equal(ref[s][1], got[s][1]), s
+    # replicate 2 1 1 of the ring deck after all per-atom state has been set.  Upstream aborts here (replicate goes
+    # through pack_restart, whose buffer size_restart() undercounts: the same defect as in the restart test), so the
+    # check is on the state: both copies carry the type, velocity, density, concentration and group membership of the
+    # original atoms (forces differ: the source fix of the deck sits in the first copy only).
+    deck = dropin.RING2D
+    wd_ref, _ = dropin.run_deck(REF, deck, [])
+    rep = _with_cuda_atom_style(deck).replace("fix integ all", "replicate 2 1 1\nfix integ all")
+    assert "replicate" in rep
+    wd_new, _ = dropin.run_deck(CUDA, rep, [])
+    ref, got = dropin.read_dumps(wd_ref), dropin.read_dumps(wd_new)
+    a, b = ref[0][1], got[0][1]
+    n = len(a)
+    assert n == 40 * 40 and len(b) == 2 * n
+    cols = ref[0][0]
+    for copy in (0, 1):
+        c = b[copy * n:(copy + 1) * n]      # replicate numbers the atoms of image m as id + m * n
+        assert np.array_equal(c[:, 0] - copy * n, a[:, 0])
+        for name in ("type", "y", "vx", "vy", "c_crho", "c_cc"):
+            k = cols.index(name)
+            assert np.array_equal(c[:, k], a[:, k]), (copy, name)
+        assert np.abs(c[:, cols.index("x")] - 2.0 * copy - a[:, cols.index("x")]).max() < 1e-14
+    # the stress column is defined on group `ring`: non-zero for the same atoms in both copies at the last step
+    k = cols.index("c_syy")
+    last = got[max(got)][1]
+    assert np.array_equal(last[:n, k] != 0, last[n:, k] != 0) and (last[:n, k] != 0).any()
