@@ -60,6 +60,23 @@ def test_property_atom_columns():
         assert np.abs(ref[s][1][:, cols.index("c_pa[2]")]).max() > 0   # drho is not a column of zeros
 
 
+def test_property_atom_columns_of_the_mechanics_style():
+    """Pnew, de and deviatoricTensor (upstream's loop leaves the LAST tensor component in the column) on the channel deck"""
+    _need()
+    deck = dropin.FSI2D.replace("compute sxy beam ssa_tsdpd/stress/atom 0 1\n", "compute sxy beam ssa_tsdpd/stress/atom 0 1\n"
+                                "compute pa all property/atom Pnew de deviatoricTensor cv\n")
+    deck = deck.replace("c_sxx c_sxy", "c_sxx c_sxy c_pa[1] c_pa[2] c_pa[3] c_pa[4]")
+    assert "c_pa[3]" in deck
+    wd_ref, _ = dropin.run_deck(REF, deck, [])
+    wd_new, _ = dropin.run_deck(CUDA, _with_cuda_atom_style(deck), [])
+    ref, got = dropin.read_dumps(wd_ref), dropin.read_dumps(wd_new)
+    assert sorted(ref) == sorted(got) and len(ref) >= 3
+    for s in ref:
+        assert np.array_equal(ref[s][1], got[s][1]), s
+    cols = ref[max(ref)][0]
+    assert np.abs(ref[max(ref)][1][:, cols.index("c_pa[1]")]).max() > 0   # Pnew is populated by the mechanics style
+
+
 def test_restart_and_data_file_round_trip():
     """write_restart / clear / read_restart (the style is re-created from the restart file): every state field -- incl. the
     species concentration and the deviatoric stress of the elastic ring -- is carried over; write_data lists id,
